@@ -1,0 +1,131 @@
+/* b200chan.h - C ABI of libb200chan.so : B200-native wideband channelizer / FM demod / FFT scan.
+ *
+ * This is the drop-in boundary for the ONE hot path of MattMills/radiocapture-rf.
+ * The reference is pure Python wiring GNU Radio 3.8 C++ blocks; it has no FFI of its own, so each
+ * entry point below names the GNU Radio block call (reference file:line) whose arithmetic it replaces.
+ * The Python host (radiocapture_rf_b200/, ctypes - no PyTorch) mirrors rc_frontend/channel.py,
+ * rc_frontend/receiver.py and fft_vector.py / fft_peak_detection.py on top of these calls.
+ *
+ * Conventions: every function returns RCB_OK (0) or a negative rcb_status; nothing throws; buffers
+ * are caller owned; sample format is the reference's raw little-endian complex64 (interleaved
+ * float32 I,Q - rc_frontend/channel.py:36, logging_receiver.py:107-109).  A handle owns one CUDA
+ * device + streams and carries the streaming state of ONE wideband stream (one SDR source,
+ * rc_frontend/receiver.py:67-70); it is not thread safe (the reference serialises on access_lock,
+ * rc_frontend/receiver.py:48).  Handles on different GPUs are independent (no NCCL on this path).
+ * `mem` arguments say where a caller buffer lives: RCB_MEM_HOST (copied with cudaMemcpyAsync, pinned
+ * memory from rcb_host_alloc overlaps best) or RCB_MEM_DEVICE (used in place).
+ */
+#ifndef B200CHAN_H
+#define B200CHAN_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rcb_ctx rcb_t;
+
+typedef enum {
+    RCB_OK = 0,
+    RCB_EINVAL = -1,       /* bad argument */
+    RCB_ENOMEM = -2,       /* host or device allocation failed */
+    RCB_ECUDA = -3,        /* CUDA runtime error (see rcb_last_error) */
+    RCB_ESTATE = -4,       /* call sequence error (e.g. process before config) */
+    RCB_ENODEV = -5,       /* no such CUDA device / no GPU */
+    RCB_ERANGE = -6,       /* id / size out of range */
+    RCB_EUNSUPPORTED = -7  /* shape not supported by any kernel */
+} rcb_status;
+
+enum { RCB_MEM_HOST = 0, RCB_MEM_DEVICE = 1 };
+enum { RCB_OUT_IQ = 1, RCB_OUT_FM = 2 };
+enum { RCB_COPY_H2D = 1, RCB_COPY_D2H = 2, RCB_COPY_D2D = 3 };
+
+typedef struct {
+    uint64_t samples_in;       /* wideband samples consumed by pfb/ddc/fft process calls */
+    uint64_t channel_samples;  /* narrowband samples produced (all channels) */
+    uint64_t kernel_launches;  /* CUDA kernels launched by this handle */
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+} rcb_stats_t;
+
+/* ---- library / handle ------------------------------------------------------------------------ */
+int rcb_version(void);
+const char* rcb_strerror(int status);
+int rcb_device_count(int* count);
+int rcb_open(int device, rcb_t** out);          /* one handle per wideband stream */
+int rcb_close(rcb_t* h);
+int rcb_sync(rcb_t* h);                         /* wait for all work queued on the handle */
+const char* rcb_last_error(rcb_t* h);           /* text of the last CUDA error on this handle */
+int rcb_stats(rcb_t* h, rcb_stats_t* out);
+int rcb_device_name(rcb_t* h, char* buf, size_t cap, int* sm_count);
+
+/* ---- memory / timing helpers (the Python host has no torch) ------------------------------------ */
+int rcb_dev_alloc(rcb_t* h, size_t bytes, void** p);
+int rcb_dev_free(rcb_t* h, void* p);
+int rcb_host_alloc(rcb_t* h, size_t bytes, void** p);   /* pinned */
+int rcb_host_free(rcb_t* h, void* p);
+int rcb_memcpy(rcb_t* h, void* dst, const void* src, size_t bytes, int kind);  /* synchronous */
+int rcb_memset(rcb_t* h, void* dev, int value, size_t bytes);
+int rcb_l2_flush(rcb_t* h);                     /* overwrite a > L2-sized scratch buffer */
+int rcb_timer_start(rcb_t* h);                  /* cudaEventRecord on the compute stream */
+int rcb_timer_stop(rcb_t* h, float* ms);        /* record + synchronize + elapsed */
+
+/* ---- K1: polyphase channelizer + fused FM demod -------------------------------------------------
+ * Replaces  pfb.channelizer_ccf(nchans, taps, 1.0, ...)           rc_frontend/receiver.py:249-261
+ * and, per output bin,  analog.quadrature_demod_cf(fm_gain)       moto_control_demod.py:105,
+ *   edacs_control_demod.py:82-84, p25_control_demod.py:120-121, logging_receiver.py:234,336,346.
+ * taps = prototype filter (any length; arm i gets taps[i + k*nchans], zero padded).  Output port m
+ * carries FFT bin m (identity channel map; bins > nchans/2 are negative frequencies,
+ * rc_frontend/receiver.py:373-375).  Outputs are channel-major: element (m, n) at m*out_stride + n.
+ * nsamples must be a multiple of nchans (stream_to_streams granularity); *nout = nsamples/nchans.
+ * Streaming state (last ceil(ntaps/nchans) input rows) is carried between calls, so any split of a
+ * stream into calls gives the same samples as one call.  out_iq / out_fm may be NULL per out_mask. */
+int rcb_pfb_config(rcb_t* h, int nchans, const float* taps, int ntaps, int out_mask, float fm_gain);
+int rcb_pfb_reset(rcb_t* h);
+int rcb_pfb_process(rcb_t* h, const void* iq, size_t nsamples, int in_mem,
+                    void* out_iq, void* out_fm, size_t out_stride, int out_mem, size_t* nout);
+
+/* ---- K2: bank of arbitrary-offset DDC channels (+ optional FM demod) ----------------------------
+ * One channel = filter.freq_xlating_fir_filter_ccc(decim, taps, center_freq, samp_rate)
+ *   rc_frontend/channel.py:35 (the `channel` top_block), split-2 pair rc_frontend/receiver.py:85-86,
+ *   1x prefilter p25_control_demod.py:108 / logging_receiver.py:231;
+ * rcb_ddc_retune = set_center_freq (channel.py:61-63), rcb_ddc_set_taps = set_taps (channel.py:56-57).
+ * rcb_ddc_process runs every open channel over the same staged wideband block (one H2D copy instead
+ * of one ZMQ copy of the full-rate stream per channel, channel.py:29); outputs of the block are then
+ * fetched per channel with rcb_ddc_pull (which = RCB_OUT_IQ: complex64, RCB_OUT_FM: float32). */
+int rcb_ddc_open(rcb_t* h, int decim, const float* taps, int ntaps, double center_freq,
+                 double samp_rate, int out_mask, float fm_gain, int* chan_id);
+int rcb_ddc_retune(rcb_t* h, int chan_id, double center_freq);
+int rcb_ddc_set_taps(rcb_t* h, int chan_id, const float* taps, int ntaps);
+int rcb_ddc_close(rcb_t* h, int chan_id);
+int rcb_ddc_process(rcb_t* h, const void* iq, size_t nsamples, int in_mem);
+int rcb_ddc_pull(rcb_t* h, int chan_id, int which, void* dst, size_t cap_items, int dst_mem,
+                 size_t* nitems);
+
+/* ---- K4: stand-alone quadrature demod / AFC probe on narrowband rows ---------------------------
+ * out[r][n] = gain * atan2(Im p, Re p), p = x[r][n] conj(x[r][n-1]); prev (rows complex64, may be
+ * NULL = zeros) supplies x[r][-1] and receives the last sample of each row (streaming carry).
+ * Replaces analog.quadrature_demod_cf (call sites above).  All pointers in `mem` space. */
+int rcb_quad_demod(rcb_t* h, const void* iq, size_t rows, size_t n, size_t in_stride, float gain,
+                   void* prev, void* out_fm, size_t out_stride, int mem);
+/* scale * sum of the last `length` floats of each row: what moving_average_ff(length,1,..) ->
+ * multiply_const(scale) -> probe_signal_f holds (p25_control_demod.py:123-127). */
+int rcb_probe_mean(rcb_t* h, const void* x, size_t rows, size_t n, size_t stride, size_t length,
+                   float scale, void* out, int mem);
+
+/* ---- K3: streaming windowed FFT + log-power accumulation ---------------------------------------
+ * Replaces stream_to_vector -> fft.fft_vcc(L, True, window, True) -> complex_to_mag_squared ->
+ * nlog10_ff(1, L, 1) -> moving_average_ff(avg, 1, ...)             fft_vector.py:37-60.
+ * Frames are consecutive length-L blocks; one output vector per block of `avg` consecutive frames:
+ * S[k] = sum_f (log10(max(|fftshift(FFT(x_f*w))[k]|^2, 1e-18)) + 1).  The vector the reference
+ * writes (frames 900..999 of 1000, avg 100) is output block 9.  nsamples must be a multiple of L;
+ * partial avg blocks are carried to the next call.  *nvec = vectors written to out_sums. */
+int rcb_fft_config(rcb_t* h, int length, const float* window, int avg_frames);
+int rcb_fft_reset(rcb_t* h);
+int rcb_fft_process(rcb_t* h, const void* iq, size_t nsamples, int in_mem, void* out_sums,
+                    size_t cap_vectors, int out_mem, size_t* nvec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CHAN_H */

@@ -1,0 +1,992 @@
+// libb200chan.so - C ABI (include/b200chan.h) over the hand-written sm_100a kernels.
+// Host runtime: one handle = one CUDA device + streams + the streaming state of one wideband stream.
+#include "../../include/b200chan.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "ddc_bank.cuh"
+#include "demod.cuh"
+#include "fft_logpow.cuh"
+#include "pfb_fm.cuh"
+
+using namespace rcb;
+
+namespace {
+
+constexpr int kVersion = 100;       // 0.1.0
+constexpr int kDdcHistCap = 1 << 14;  // samples of wideband history kept for the DDC bank (>= max ntaps-1)
+constexpr int kStages = 3;          // host<->device pipeline depth of the e2e path
+constexpr size_t kChunkSamples = 1u << 22;
+
+struct DdcChan {
+    int id = 0;
+    int decim = 1, ntaps = 0, out_mask = RCB_OUT_IQ;
+    float gain = 1.f;
+    double center_freq = 0, samp_rate = 1;
+    std::vector<float> taps;
+    float2* d_ctaps_rev = nullptr;
+    float2* d_out_iq = nullptr;
+    float* d_out_fm = nullptr;
+    float2* d_prev = nullptr;
+    size_t out_cap = 0;
+    size_t nout_last = 0;
+    uint64_t start_sample = 0;  // stream position of the newest sample of output 0
+    uint64_t i_next = 0;        // next output index
+    double cyc = 0;             // frac(f0*D/fs)
+    double phase_base = 0;      // phase (cycles) at output i_base
+    uint64_t i_base = 0;
+};
+
+struct Stage {
+    float2* d_in = nullptr;
+    float* d_fm = nullptr;
+    float2* d_iq = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr;
+    bool used = false;
+};
+
+}  // namespace
+
+struct rcb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    char err[512] = {0};
+    rcb_stats_t stats{};
+    void* l2_scratch = nullptr;
+    size_t l2_scratch_bytes = 0;
+
+    // ---- PFB ----
+    struct {
+        bool configured = false;
+        int N = 0, L = 0, P = 0, R = 0, mode = 0;
+        float gain = 1.f;
+        float* d_taps = nullptr;
+        float2* d_tw = nullptr;
+        float2* d_hist[2] = {nullptr, nullptr};
+        int hist_cur = 0;
+        float2* d_ys = nullptr;  // generic path scratch [N][T+1]
+        size_t ys_cap = 0;
+        int blocks_per_sm = 0;
+        size_t smem = 0;
+        bool taps_smem = true;
+        Stage st[kStages];
+        size_t chunk_frames = 0;
+    } pfb;
+
+    // ---- DDC ----
+    struct {
+        std::map<int, DdcChan> chans;
+        int next_id = 1;
+        float2* d_hist[2] = {nullptr, nullptr};
+        int hist_cur = 0;
+        uint64_t n_consumed = 0;
+        float2* d_in = nullptr;
+        size_t in_cap = 0;
+        DdcChanDev* d_chans = nullptr;
+        DdcChanDev* h_chans = nullptr;  // pinned
+        size_t chans_cap = 0;
+    } ddc;
+
+    // ---- FFT ----
+    FftState fft;
+
+    // generic staging for small host-side helpers
+    void* d_tmp[2] = {nullptr, nullptr};
+    size_t d_tmp_cap[2] = {0, 0};
+};
+
+namespace {
+
+int fail_cuda(rcb_t* h, cudaError_t e, const char* what) {
+    if (h) snprintf(h->err, sizeof(h->err), "%s: %s", what, cudaGetErrorString(e));
+    return RCB_ECUDA;
+}
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return fail_cuda(h, e__, #call); \
+    } while (0)
+#define CKL(h)                                                       \
+    do {                                                             \
+        cudaError_t e__ = cudaGetLastError();                        \
+        if (e__ != cudaSuccess) return fail_cuda(h, e__, "kernel launch"); \
+        (h)->stats.kernel_launches++;                                \
+    } while (0)
+
+int ensure_tmp(rcb_t* h, int which, size_t bytes) {
+    if (h->d_tmp_cap[which] >= bytes) return RCB_OK;
+    if (h->d_tmp[which]) cudaFree(h->d_tmp[which]);
+    h->d_tmp[which] = nullptr;
+    h->d_tmp_cap[which] = 0;
+    CK(cudaMalloc(&h->d_tmp[which], bytes));
+    h->d_tmp_cap[which] = bytes;
+    return RCB_OK;
+}
+
+// frac(cyc * k) computed exactly (cyc is an exact binary rational, k an integer)
+double frac_mul(double cyc, uint64_t k) {
+    if (cyc == 0.0 || k == 0) return 0.0;
+    int e;
+    const double m = frexp(cyc, &e);                       // cyc = m * 2^e, m in [0.5,1)
+    const uint64_t mant = (uint64_t)ldexp(m, 53);          // exact
+    const int shift = 53 - e;                              // cyc = mant * 2^-shift, shift >= 53
+    unsigned __int128 prod = (unsigned __int128)mant * (unsigned __int128)k;
+    if (shift < 128) {
+        const unsigned __int128 mask = (((unsigned __int128)1) << shift) - 1;
+        prod &= mask;
+    }
+    const long double v = (long double)(uint64_t)(prod >> 64) * 18446744073709551616.0L + (long double)(uint64_t)prod;
+    double f = (double)ldexpl(v, -shift);
+    if (f >= 1.0) f -= 1.0;
+    return f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PFB kernel dispatch
+// ------------------------------------------------------------------------------------------------
+template <int R, int MODE, bool TS, int PT>
+int pfb_launch_t(rcb_t* h, const PfbParams& p, bool query_only) {
+    using G = PfbGeom<R>;
+    auto kern = pfb_fm_kernel<R, MODE, TS, PT>;
+    const size_t smem = G::smem_bytes(p.P, TS);
+    if (query_only) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, G::THREADS, smem));
+        h->pfb.blocks_per_sm = std::max(nb, 1);
+        h->pfb.smem = smem;
+        return RCB_OK;
+    }
+    const int NI = (p.T + G::FPI - 1) / G::FPI;
+    const int grid = std::max(1, std::min(NI, h->pfb.blocks_per_sm * h->sm_count));
+    kern<<<grid, G::THREADS, smem, h->stream>>>(p);
+    CKL(h);
+    return RCB_OK;
+}
+template <int R, int MODE>
+int pfb_launch_rm(rcb_t* h, const PfbParams& p, bool q) {
+    if (p.P == 1) return pfb_launch_t<R, MODE, true, 1>(h, p, q);
+    if (h->pfb.taps_smem) return pfb_launch_t<R, MODE, true, 0>(h, p, q);
+    return pfb_launch_t<R, MODE, false, 0>(h, p, q);
+}
+template <int R>
+int pfb_launch_r(rcb_t* h, const PfbParams& p, bool q) {
+    switch (h->pfb.mode) {
+        case RCB_OUT_IQ: return pfb_launch_rm<R, PFB_OUT_IQ>(h, p, q);
+        case RCB_OUT_FM: return pfb_launch_rm<R, PFB_OUT_FM>(h, p, q);
+        default: return pfb_launch_rm<R, PFB_OUT_IQ | PFB_OUT_FM>(h, p, q);
+    }
+}
+int pfb_launch_fast(rcb_t* h, const PfbParams& p, bool q) {
+    switch (h->pfb.R) {
+        case 8: return pfb_launch_r<8>(h, p, q);
+        case 16: return pfb_launch_r<16>(h, p, q);
+        case 32: return pfb_launch_r<32>(h, p, q);
+    }
+    return RCB_EUNSUPPORTED;
+}
+
+void pfb_free(rcb_t* h) {
+    auto& s = h->pfb;
+    cudaFree(s.d_taps);
+    cudaFree(s.d_tw);
+    cudaFree(s.d_hist[0]);
+    cudaFree(s.d_hist[1]);
+    cudaFree(s.d_ys);
+    for (auto& st : s.st) {
+        cudaFree(st.d_in);
+        cudaFree(st.d_fm);
+        cudaFree(st.d_iq);
+        if (st.ev_in) cudaEventDestroy(st.ev_in);
+        if (st.ev_k) cudaEventDestroy(st.ev_k);
+        if (st.ev_out) cudaEventDestroy(st.ev_out);
+        st = Stage{};
+    }
+    s.d_taps = nullptr;
+    s.d_tw = nullptr;
+    s.d_hist[0] = s.d_hist[1] = nullptr;
+    s.d_ys = nullptr;
+    s.ys_cap = 0;
+    s.chunk_frames = 0;
+    s.configured = false;
+}
+
+// one launch over device-resident input; advances the streaming history
+int pfb_run_device(rcb_t* h, const float2* d_x, size_t frames, float2* d_iq, float* d_fm, size_t ostride) {
+    auto& s = h->pfb;
+    if (frames == 0) return RCB_OK;
+    PfbParams p{};
+    p.x = d_x;
+    p.hist = s.d_hist[s.hist_cur];
+    p.taps = s.d_taps;
+    p.twiddle = s.d_tw;
+    p.out_fm = (s.mode & RCB_OUT_FM) ? d_fm : nullptr;
+    p.out_iq = (s.mode & RCB_OUT_IQ) ? d_iq : nullptr;
+    p.ostride = (long long)ostride;
+    p.T = (int)frames;
+    p.P = s.P;
+    p.N = s.N;
+    p.gain = s.gain;
+    if (s.R) {
+        int rc = pfb_launch_fast(h, p, false);
+        if (rc) return rc;
+    } else {
+        const size_t need = (size_t)s.N * (frames + 1);
+        if (s.ys_cap < need) {
+            cudaFree(s.d_ys);
+            s.d_ys = nullptr;
+            s.ys_cap = 0;
+            CK(cudaMalloc(&s.d_ys, need * sizeof(float2)));
+            s.ys_cap = need;
+        }
+        const int grid = (int)std::min<size_t>(frames + 1, (size_t)h->sm_count * 8);
+        const int threads = std::min(256, std::max(32, ((s.N + 31) / 32) * 32));
+        pfb_generic_kernel<<<grid, threads, 2 * (size_t)s.N * sizeof(float2), h->stream>>>(p, s.d_ys, (long long)frames + 1);
+        CKL(h);
+        dim3 g2((unsigned)((frames + 255) / 256), (unsigned)s.N);
+        pfb_generic_emit_kernel<<<g2, 256, 0, h->stream>>>(s.d_ys, (long long)frames + 1, p.out_iq, p.out_fm,
+                                                           p.ostride, p.T, p.gain);
+        CKL(h);
+    }
+    // hist <- last P rows of (hist ++ x)
+    const long long cap = (long long)s.P * s.N;
+    const int nxt = s.hist_cur ^ 1;
+    hist_update_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, h->stream>>>(s.d_hist[s.hist_cur], d_x,
+                                                                          (long long)frames * s.N, s.d_hist[nxt], cap);
+    CKL(h);
+    s.hist_cur = nxt;
+    h->stats.samples_in += frames * (uint64_t)s.N;
+    h->stats.channel_samples += frames * (uint64_t)s.N;
+    return RCB_OK;
+}
+
+int pfb_ensure_stages(rcb_t* h) {
+    auto& s = h->pfb;
+    if (s.chunk_frames) return RCB_OK;
+    size_t cf = std::max<size_t>(8, kChunkSamples / (size_t)s.N);
+    cf = (cf + 31) / 32 * 32;
+    for (auto& st : s.st) {
+        CK(cudaMalloc(&st.d_in, cf * s.N * sizeof(float2)));
+        if (s.mode & RCB_OUT_FM) CK(cudaMalloc(&st.d_fm, cf * s.N * sizeof(float)));
+        if (s.mode & RCB_OUT_IQ) CK(cudaMalloc(&st.d_iq, cf * s.N * sizeof(float2)));
+        CK(cudaEventCreateWithFlags(&st.ev_in, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&st.ev_k, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&st.ev_out, cudaEventDisableTiming));
+        st.used = false;
+    }
+    s.chunk_frames = cf;
+    return RCB_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// library / handle
+// =================================================================================================
+extern "C" int rcb_version(void) { return kVersion; }
+
+extern "C" const char* rcb_strerror(int st) {
+    switch (st) {
+        case RCB_OK: return "ok";
+        case RCB_EINVAL: return "invalid argument";
+        case RCB_ENOMEM: return "out of memory";
+        case RCB_ECUDA: return "CUDA error";
+        case RCB_ESTATE: return "invalid state / call order";
+        case RCB_ENODEV: return "no such CUDA device";
+        case RCB_ERANGE: return "out of range";
+        case RCB_EUNSUPPORTED: return "unsupported shape";
+    }
+    return "unknown status";
+}
+
+extern "C" int rcb_device_count(int* count) {
+    if (!count) return RCB_EINVAL;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        *count = 0;
+        return RCB_ENODEV;
+    }
+    *count = n;
+    return RCB_OK;
+}
+
+extern "C" int rcb_open(int device, rcb_t** out) {
+    if (!out) return RCB_EINVAL;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return RCB_ENODEV;
+    }
+    if (device < 0 || device >= n) return RCB_ENODEV;
+    rcb_t* h = new (std::nothrow) rcb_ctx();
+    if (!h) return RCB_ENOMEM;
+    h->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->t0);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->t1);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) {
+        delete h;
+        return RCB_ECUDA;
+    }
+    *out = h;
+    return RCB_OK;
+}
+
+extern "C" int rcb_close(rcb_t* h) {
+    if (!h) return RCB_EINVAL;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    pfb_free(h);
+    for (auto& kv : h->ddc.chans) {
+        cudaFree(kv.second.d_ctaps_rev);
+        cudaFree(kv.second.d_out_iq);
+        cudaFree(kv.second.d_out_fm);
+        cudaFree(kv.second.d_prev);
+    }
+    cudaFree(h->ddc.d_hist[0]);
+    cudaFree(h->ddc.d_hist[1]);
+    cudaFree(h->ddc.d_in);
+    cudaFree(h->ddc.d_chans);
+    if (h->ddc.h_chans) cudaFreeHost(h->ddc.h_chans);
+    fft_free(h->fft);
+    cudaFree(h->d_tmp[0]);
+    cudaFree(h->d_tmp[1]);
+    cudaFree(h->l2_scratch);
+    cudaEventDestroy(h->t0);
+    cudaEventDestroy(h->t1);
+    cudaStreamDestroy(h->stream);
+    cudaStreamDestroy(h->s_in);
+    cudaStreamDestroy(h->s_out);
+    delete h;
+    return RCB_OK;
+}
+
+extern "C" int rcb_sync(rcb_t* h) {
+    if (!h) return RCB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->s_in));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaStreamSynchronize(h->s_out));
+    return RCB_OK;
+}
+
+extern "C" const char* rcb_last_error(rcb_t* h) { return h ? h->err : "null handle"; }
+
+extern "C" int rcb_stats(rcb_t* h, rcb_stats_t* out) {
+    if (!h || !out) return RCB_EINVAL;
+    *out = h->stats;
+    return RCB_OK;
+}
+
+extern "C" int rcb_device_name(rcb_t* h, char* buf, size_t cap, int* sm_count) {
+    if (!h) return RCB_EINVAL;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    if (buf && cap) {
+        strncpy(buf, prop.name, cap - 1);
+        buf[cap - 1] = 0;
+    }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    return RCB_OK;
+}
+
+// =================================================================================================
+// memory / timing helpers
+// =================================================================================================
+extern "C" int rcb_dev_alloc(rcb_t* h, size_t bytes, void** p) {
+    if (!h || !p) return RCB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        return RCB_ENOMEM;
+    }
+    CK(e);
+    return RCB_OK;
+}
+extern "C" int rcb_dev_free(rcb_t* h, void* p) {
+    if (!h) return RCB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaFree(p));
+    return RCB_OK;
+}
+extern "C" int rcb_host_alloc(rcb_t* h, size_t bytes, void** p) {
+    if (!h || !p) return RCB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    cudaError_t e = cudaHostAlloc(p, bytes, cudaHostAllocDefault);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        return RCB_ENOMEM;
+    }
+    CK(e);
+    return RCB_OK;
+}
+extern "C" int rcb_host_free(rcb_t* h, void* p) {
+    if (!h) return RCB_EINVAL;
+    CK(cudaFreeHost(p));
+    return RCB_OK;
+}
+extern "C" int rcb_memcpy(rcb_t* h, void* dst, const void* src, size_t bytes, int kind) {
+    if (!h || (!dst && bytes) || (!src && bytes)) return RCB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    cudaMemcpyKind k;
+    switch (kind) {
+        case RCB_COPY_H2D: k = cudaMemcpyHostToDevice; h->stats.h2d_bytes += bytes; break;
+        case RCB_COPY_D2H: k = cudaMemcpyDeviceToHost; h->stats.d2h_bytes += bytes; break;
+        case RCB_COPY_D2D: k = cudaMemcpyDeviceToDevice; break;
+        default: return RCB_EINVAL;
+    }
+    CK(cudaMemcpyAsync(dst, src, bytes, k, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RCB_OK;
+}
+extern "C" int rcb_memset(rcb_t* h, void* dev, int value, size_t bytes) {
+    if (!h || !dev) return RCB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemsetAsync(dev, value, bytes, h->stream));
+    return RCB_OK;
+}
+extern "C" int rcb_l2_flush(rcb_t* h) {
+    if (!h) return RCB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    if (!h->l2_scratch) {
+        int l2 = 0;
+        CK(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, h->device));
+        h->l2_scratch_bytes = std::max<size_t>((size_t)l2 * 2, (size_t)256 << 20);
+        CK(cudaMalloc(&h->l2_scratch, h->l2_scratch_bytes));
+    }
+    CK(cudaMemsetAsync(h->l2_scratch, 0x5a, h->l2_scratch_bytes, h->stream));
+    return RCB_OK;
+}
+extern "C" int rcb_timer_start(rcb_t* h) {
+    if (!h) return RCB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->t0, h->stream));
+    return RCB_OK;
+}
+extern "C" int rcb_timer_stop(rcb_t* h, float* ms) {
+    if (!h || !ms) return RCB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->t1, h->stream));
+    CK(cudaEventSynchronize(h->t1));
+    CK(cudaEventElapsedTime(ms, h->t0, h->t1));
+    return RCB_OK;
+}
+
+// =================================================================================================
+// K1  PFB + FM
+// =================================================================================================
+extern "C" int rcb_pfb_config(rcb_t* h, int nchans, const float* taps, int ntaps, int out_mask, float fm_gain) {
+    if (!h || !taps || nchans < 1 || ntaps < 1) return RCB_EINVAL;
+    if (!(out_mask & (RCB_OUT_IQ | RCB_OUT_FM)) || (out_mask & ~(RCB_OUT_IQ | RCB_OUT_FM))) return RCB_EINVAL;
+    if (nchans > 65536) return RCB_EUNSUPPORTED;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    pfb_free(h);
+    auto& s = h->pfb;
+    s.N = nchans;
+    s.L = ntaps;
+    s.P = (ntaps + nchans - 1) / nchans;
+    s.mode = out_mask;
+    s.gain = fm_gain;
+    s.R = (nchans == 64) ? 8 : (nchans == 256) ? 16 : (nchans == 1024) ? 32 : 0;
+    const int N = s.N, P = s.P, R = s.R;
+    std::vector<float> hp((size_t)P * N, 0.f);
+    for (int i = 0; i < ntaps; ++i) hp[i] = taps[i];
+    std::vector<float> tperm((size_t)P * N);
+    std::vector<float2> tw;
+    if (R) {
+        for (int k = 0; k < P; ++k)
+            for (int jj = 0; jj < R; ++jj)
+                for (int ll = 0; ll < R; ++ll)
+                    tperm[((size_t)k * R + jj) * R + ll] = hp[(size_t)R * (R - 1 - jj) + (R - 1 - ll) + (size_t)k * N];
+        const int S = R + 2;
+        tw.assign((size_t)R * S, make_float2(0.f, 0.f));
+        for (int ll = 0; ll < R; ++ll)
+            for (int m1 = 0; m1 < R; ++m1) {
+                const int q = ((R - 1 - ll) * m1) % N;
+                const double a = 2.0 * M_PI * (double)q / (double)N;
+                tw[(size_t)ll * S + m1] = make_float2((float)cos(a), (float)sin(a));
+            }
+        s.taps_smem = ((size_t)P * N * sizeof(float) <= 16384);
+    } else {
+        tperm = hp;
+        tw.resize(N);
+        for (int q = 0; q < N; ++q) {
+            const double a = 2.0 * M_PI * (double)q / (double)N;
+            tw[q] = make_float2((float)cos(a), (float)sin(a));
+        }
+        if (2 * (size_t)N * sizeof(float2) > 48 * 1024) return RCB_EUNSUPPORTED;
+    }
+    CK(cudaMalloc(&s.d_taps, tperm.size() * sizeof(float)));
+    CK(cudaMalloc(&s.d_tw, tw.size() * sizeof(float2)));
+    CK(cudaMemcpyAsync(s.d_taps, tperm.data(), tperm.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(s.d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+    for (int b = 0; b < 2; ++b) {
+        CK(cudaMalloc(&s.d_hist[b], (size_t)P * N * sizeof(float2)));
+        CK(cudaMemsetAsync(s.d_hist[b], 0, (size_t)P * N * sizeof(float2), h->stream));
+    }
+    s.hist_cur = 0;
+    CK(cudaStreamSynchronize(h->stream));
+    if (R) {
+        PfbParams p{};
+        p.P = P;
+        p.N = N;
+        int rc = pfb_launch_fast(h, p, true);
+        if (rc) return rc;
+    }
+    s.configured = true;
+    return RCB_OK;
+}
+
+extern "C" int rcb_pfb_reset(rcb_t* h) {
+    if (!h) return RCB_EINVAL;
+    auto& s = h->pfb;
+    if (!s.configured) return RCB_ESTATE;
+    CK(cudaSetDevice(h->device));
+    for (int b = 0; b < 2; ++b) CK(cudaMemsetAsync(s.d_hist[b], 0, (size_t)s.P * s.N * sizeof(float2), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RCB_OK;
+}
+
+extern "C" int rcb_pfb_process(rcb_t* h, const void* iq, size_t nsamples, int in_mem, void* out_iq, void* out_fm,
+                               size_t out_stride, int out_mem, size_t* nout) {
+    if (!h) return RCB_EINVAL;
+    auto& s = h->pfb;
+    if (!s.configured) return RCB_ESTATE;
+    if (nout) *nout = 0;
+    if ((!iq && nsamples) || nsamples % (size_t)s.N) return RCB_EINVAL;
+    const size_t frames = nsamples / (size_t)s.N;
+    if (frames > 0x7fffff00u) return RCB_ERANGE;
+    if ((s.mode & RCB_OUT_IQ) && !out_iq) return RCB_EINVAL;
+    if ((s.mode & RCB_OUT_FM) && !out_fm) return RCB_EINVAL;
+    if (out_stride < frames) return RCB_EINVAL;
+    if ((in_mem != RCB_MEM_HOST && in_mem != RCB_MEM_DEVICE) || (out_mem != RCB_MEM_HOST && out_mem != RCB_MEM_DEVICE))
+        return RCB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    if (frames == 0) return RCB_OK;
+
+    if (in_mem == RCB_MEM_DEVICE && out_mem == RCB_MEM_DEVICE) {
+        int rc = pfb_run_device(h, (const float2*)iq, frames, (float2*)out_iq, (float*)out_fm, out_stride);
+        if (rc) return rc;
+        if (nout) *nout = frames;
+        return RCB_OK;
+    }
+
+    // host-facing path: chunked 3-stage pipeline  H2D (s_in) | kernel (stream) | D2H (s_out)
+    int rc = pfb_ensure_stages(h);
+    if (rc) return rc;
+    const size_t cf = s.chunk_frames;
+    size_t done = 0;
+    int si = 0;
+    while (done < frames) {
+        const size_t f = std::min(cf, frames - done);
+        Stage& st = s.st[si];
+        const float2* d_x;
+        if (in_mem == RCB_MEM_HOST) {
+            if (st.used) CK(cudaStreamWaitEvent(h->s_in, st.ev_k, 0));  // previous kernel finished reading d_in
+            CK(cudaMemcpyAsync(st.d_in, (const float2*)iq + done * s.N, f * s.N * sizeof(float2),
+                               cudaMemcpyHostToDevice, h->s_in));
+            h->stats.h2d_bytes += f * s.N * sizeof(float2);
+            CK(cudaEventRecord(st.ev_in, h->s_in));
+            CK(cudaStreamWaitEvent(h->stream, st.ev_in, 0));
+            d_x = st.d_in;
+        } else {
+            d_x = (const float2*)iq + done * s.N;
+        }
+        float2* d_iq;
+        float* d_fm;
+        size_t dstride;
+        if (out_mem == RCB_MEM_HOST) {
+            if (st.used) CK(cudaStreamWaitEvent(h->stream, st.ev_out, 0));  // previous D2H of this stage done
+            d_iq = st.d_iq;
+            d_fm = st.d_fm;
+            dstride = cf;
+        } else {
+            d_iq = out_iq ? (float2*)out_iq + done : nullptr;
+            d_fm = out_fm ? (float*)out_fm + done : nullptr;
+            dstride = out_stride;
+        }
+        rc = pfb_run_device(h, d_x, f, d_iq, d_fm, dstride);
+        if (rc) return rc;
+        CK(cudaEventRecord(st.ev_k, h->stream));
+        if (out_mem == RCB_MEM_HOST) {
+            CK(cudaStreamWaitEvent(h->s_out, st.ev_k, 0));
+            if (s.mode & RCB_OUT_FM) {
+                CK(cudaMemcpy2DAsync((float*)out_fm + done, out_stride * sizeof(float), st.d_fm, cf * sizeof(float),
+                                     f * sizeof(float), s.N, cudaMemcpyDeviceToHost, h->s_out));
+                h->stats.d2h_bytes += f * s.N * sizeof(float);
+            }
+            if (s.mode & RCB_OUT_IQ) {
+                CK(cudaMemcpy2DAsync((float2*)out_iq + done, out_stride * sizeof(float2), st.d_iq, cf * sizeof(float2),
+                                     f * sizeof(float2), s.N, cudaMemcpyDeviceToHost, h->s_out));
+                h->stats.d2h_bytes += f * s.N * sizeof(float2);
+            }
+            CK(cudaEventRecord(st.ev_out, h->s_out));
+        }
+        st.used = true;
+        done += f;
+        si = (si + 1) % kStages;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaStreamSynchronize(h->s_out));
+    if (nout) *nout = frames;
+    return RCB_OK;
+}
+
+// =================================================================================================
+// K2  DDC bank
+// =================================================================================================
+namespace {
+int ddc_upload_taps(rcb_t* h, DdcChan& c) {
+    const double w = 2.0 * M_PI * c.center_freq / c.samp_rate;
+    std::vector<float2> rev(c.ntaps);
+    for (int r = 0; r < c.ntaps; ++r) {
+        const int k = c.ntaps - 1 - r;
+        const double a = fmod(w * (double)k, 2.0 * M_PI);
+        rev[r] = make_float2((float)((double)c.taps[k] * cos(a)), (float)((double)c.taps[k] * sin(a)));
+    }
+    if (c.d_ctaps_rev) cudaFree(c.d_ctaps_rev);
+    c.d_ctaps_rev = nullptr;
+    CK(cudaMalloc(&c.d_ctaps_rev, sizeof(float2) * c.ntaps));
+    CK(cudaMemcpyAsync(c.d_ctaps_rev, rev.data(), sizeof(float2) * c.ntaps, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    double cyc = c.center_freq * (double)c.decim / c.samp_rate;
+    cyc -= floor(cyc);
+    c.cyc = cyc;
+    return RCB_OK;
+}
+int ddc_ensure_hist(rcb_t* h) {
+    auto& d = h->ddc;
+    if (d.d_hist[0]) return RCB_OK;
+    for (int b = 0; b < 2; ++b) {
+        CK(cudaMalloc(&d.d_hist[b], sizeof(float2) * kDdcHistCap));
+        CK(cudaMemsetAsync(d.d_hist[b], 0, sizeof(float2) * kDdcHistCap, h->stream));
+    }
+    return RCB_OK;
+}
+double ddc_phase_at(const DdcChan& c, uint64_t i) {
+    double p = c.phase_base + frac_mul(c.cyc, i - c.i_base);
+    p -= floor(p);
+    return p;
+}
+}  // namespace
+
+extern "C" int rcb_ddc_open(rcb_t* h, int decim, const float* taps, int ntaps, double center_freq, double samp_rate,
+                            int out_mask, float fm_gain, int* chan_id) {
+    if (!h || !taps || !chan_id || decim < 1 || ntaps < 1 || !(samp_rate > 0)) return RCB_EINVAL;
+    if (!(out_mask & (RCB_OUT_IQ | RCB_OUT_FM)) || (out_mask & ~(RCB_OUT_IQ | RCB_OUT_FM))) return RCB_EINVAL;
+    if (ntaps - 1 > kDdcHistCap) return RCB_EUNSUPPORTED;
+    CK(cudaSetDevice(h->device));
+    int rc = ddc_ensure_hist(h);
+    if (rc) return rc;
+    DdcChan c;
+    c.id = h->ddc.next_id++;
+    c.decim = decim;
+    c.ntaps = ntaps;
+    c.out_mask = out_mask;
+    c.gain = fm_gain;
+    c.center_freq = center_freq;
+    c.samp_rate = samp_rate;
+    c.taps.assign(taps, taps + ntaps);
+    c.start_sample = h->ddc.n_consumed;
+    rc = ddc_upload_taps(h, c);
+    if (rc) return rc;
+    CK(cudaMalloc(&c.d_prev, sizeof(float2)));
+    CK(cudaMemsetAsync(c.d_prev, 0, sizeof(float2), h->stream));
+    h->ddc.chans[c.id] = c;
+    *chan_id = c.id;
+    return RCB_OK;
+}
+
+extern "C" int rcb_ddc_retune(rcb_t* h, int chan_id, double center_freq) {
+    if (!h) return RCB_EINVAL;
+    auto it = h->ddc.chans.find(chan_id);
+    if (it == h->ddc.chans.end()) return RCB_ERANGE;
+    CK(cudaSetDevice(h->device));
+    DdcChan& c = it->second;
+    // keep the rotator phase continuous, like set_center_freq -> rotator::set_phase_incr
+    c.phase_base = ddc_phase_at(c, c.i_next);
+    c.i_base = c.i_next;
+    c.center_freq = center_freq;
+    return ddc_upload_taps(h, c);
+}
+
+extern "C" int rcb_ddc_set_taps(rcb_t* h, int chan_id, const float* taps, int ntaps) {
+    if (!h || !taps || ntaps < 1) return RCB_EINVAL;
+    if (ntaps - 1 > kDdcHistCap) return RCB_EUNSUPPORTED;
+    auto it = h->ddc.chans.find(chan_id);
+    if (it == h->ddc.chans.end()) return RCB_ERANGE;
+    CK(cudaSetDevice(h->device));
+    DdcChan& c = it->second;
+    c.taps.assign(taps, taps + ntaps);
+    c.ntaps = ntaps;
+    return ddc_upload_taps(h, c);
+}
+
+extern "C" int rcb_ddc_close(rcb_t* h, int chan_id) {
+    if (!h) return RCB_EINVAL;
+    auto it = h->ddc.chans.find(chan_id);
+    if (it == h->ddc.chans.end()) return RCB_ERANGE;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(it->second.d_ctaps_rev);
+    cudaFree(it->second.d_out_iq);
+    cudaFree(it->second.d_out_fm);
+    cudaFree(it->second.d_prev);
+    h->ddc.chans.erase(it);
+    return RCB_OK;
+}
+
+extern "C" int rcb_ddc_process(rcb_t* h, const void* iq, size_t nsamples, int in_mem) {
+    if (!h || (!iq && nsamples)) return RCB_EINVAL;
+    if (in_mem != RCB_MEM_HOST && in_mem != RCB_MEM_DEVICE) return RCB_EINVAL;
+    if (nsamples > ((size_t)1 << 31)) return RCB_ERANGE;
+    CK(cudaSetDevice(h->device));
+    auto& d = h->ddc;
+    int rc = ddc_ensure_hist(h);
+    if (rc) return rc;
+    if (nsamples == 0) {
+        for (auto& kv : d.chans) kv.second.nout_last = 0;
+        return RCB_OK;
+    }
+    const float2* d_x;
+    if (in_mem == RCB_MEM_HOST) {
+        if (d.in_cap < nsamples) {
+            cudaFree(d.d_in);
+            d.d_in = nullptr;
+            d.in_cap = 0;
+            CK(cudaMalloc(&d.d_in, nsamples * sizeof(float2)));
+            d.in_cap = nsamples;
+        }
+        CK(cudaMemcpyAsync(d.d_in, iq, nsamples * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+        h->stats.h2d_bytes += nsamples * sizeof(float2);
+        d_x = d.d_in;
+    } else {
+        d_x = (const float2*)iq;
+    }
+    const size_t M = d.chans.size();
+    if (M) {
+        if (d.chans_cap < M) {
+            cudaFree(d.d_chans);
+            if (d.h_chans) cudaFreeHost(d.h_chans);
+            d.d_chans = nullptr;
+            d.h_chans = nullptr;
+            d.chans_cap = 0;
+            const size_t cap = std::max<size_t>(16, M * 2);
+            CK(cudaMalloc(&d.d_chans, cap * sizeof(DdcChanDev)));
+            CK(cudaHostAlloc(&d.h_chans, cap * sizeof(DdcChanDev), cudaHostAllocDefault));
+            d.chans_cap = cap;
+        }
+        CK(cudaStreamSynchronize(h->stream));  // h_chans reuse + previous outputs consumed
+        const uint64_t n0 = d.n_consumed, n1 = d.n_consumed + nsamples;
+        size_t max_nout = 0;
+        size_t ci = 0;
+        bool any_fm = false;
+        for (auto& kv : d.chans) {
+            DdcChan& c = kv.second;
+            // outputs i with newest sample  start + i*D  in [n0, n1)
+            const uint64_t s_next = c.start_sample + c.i_next * (uint64_t)c.decim;
+            size_t nout = 0;
+            if (s_next < n1) nout = (size_t)((n1 - 1 - s_next) / (uint64_t)c.decim) + 1;
+            if (c.out_cap < nout) {
+                cudaFree(c.d_out_iq);
+                cudaFree(c.d_out_fm);
+                c.d_out_iq = nullptr;
+                c.d_out_fm = nullptr;
+                c.out_cap = 0;
+                const size_t cap = nout + nout / 4 + 16;
+                CK(cudaMalloc(&c.d_out_iq, cap * sizeof(float2)));
+                CK(cudaMalloc(&c.d_out_fm, cap * sizeof(float)));
+                c.out_cap = cap;
+            }
+            DdcChanDev& dv = d.h_chans[ci++];
+            dv.ctaps_rev = c.d_ctaps_rev;
+            dv.out_iq = c.d_out_iq;
+            dv.out_fm = (c.out_mask & RCB_OUT_FM) ? c.d_out_fm : nullptr;
+            dv.prev = c.d_prev;
+            dv.cyc = c.cyc;
+            dv.phase0 = ddc_phase_at(c, c.i_next);
+            dv.s_first = (long long)s_next - (long long)n0;
+            dv.s_open = (long long)c.start_sample - (long long)n0;
+            dv.ntaps = c.ntaps;
+            dv.decim = c.decim;
+            dv.nout = (int)nout;
+            dv.gain = c.gain;
+            c.nout_last = nout;
+            c.i_next += nout;
+            max_nout = std::max(max_nout, nout);
+            any_fm |= (dv.out_fm != nullptr);
+            h->stats.channel_samples += nout;
+        }
+        CK(cudaMemcpyAsync(d.d_chans, d.h_chans, M * sizeof(DdcChanDev), cudaMemcpyHostToDevice, h->stream));
+        if (max_nout) {
+            dim3 grid((unsigned)((max_nout + 8 * kDdcOutPerWarp - 1) / (8 * kDdcOutPerWarp)), (unsigned)M);
+            ddc_bank_kernel<<<grid, 256, 0, h->stream>>>(d.d_chans, d_x, (long long)nsamples, d.d_hist[d.hist_cur],
+                                                        kDdcHistCap);
+            CKL(h);
+            if (any_fm) {
+                dim3 g2((unsigned)((max_nout + 255) / 256), (unsigned)M);
+                ddc_fm_kernel<<<g2, 256, 0, h->stream>>>(d.d_chans);
+                CKL(h);
+            }
+            ddc_carry_kernel<<<(unsigned)((M + 127) / 128), 128, 0, h->stream>>>(d.d_chans, (int)M);
+            CKL(h);
+        }
+    }
+    const int nxt = d.hist_cur ^ 1;
+    hist_update_kernel<<<(kDdcHistCap + 255) / 256, 256, 0, h->stream>>>(d.d_hist[d.hist_cur], d_x, (long long)nsamples,
+                                                                        d.d_hist[nxt], kDdcHistCap);
+    CKL(h);
+    d.hist_cur = nxt;
+    d.n_consumed += nsamples;
+    h->stats.samples_in += nsamples;
+    return RCB_OK;
+}
+
+extern "C" int rcb_ddc_pull(rcb_t* h, int chan_id, int which, void* dst, size_t cap_items, int dst_mem, size_t* nitems) {
+    if (!h || !nitems) return RCB_EINVAL;
+    auto it = h->ddc.chans.find(chan_id);
+    if (it == h->ddc.chans.end()) return RCB_ERANGE;
+    DdcChan& c = it->second;
+    if (which != RCB_OUT_IQ && which != RCB_OUT_FM) return RCB_EINVAL;
+    if (which == RCB_OUT_FM && !(c.out_mask & RCB_OUT_FM)) return RCB_ESTATE;
+    *nitems = c.nout_last;
+    if (c.nout_last == 0) return RCB_OK;
+    if (!dst || cap_items < c.nout_last) return RCB_ERANGE;
+    CK(cudaSetDevice(h->device));
+    const size_t bytes = c.nout_last * (which == RCB_OUT_IQ ? sizeof(float2) : sizeof(float));
+    const void* src = (which == RCB_OUT_IQ) ? (const void*)c.d_out_iq : (const void*)c.d_out_fm;
+    CK(cudaMemcpyAsync(dst, src, bytes, dst_mem == RCB_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice,
+                       h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (dst_mem == RCB_MEM_HOST) h->stats.d2h_bytes += bytes;
+    return RCB_OK;
+}
+
+// =================================================================================================
+// K4  stand-alone demod / probe
+// =================================================================================================
+extern "C" int rcb_quad_demod(rcb_t* h, const void* iq, size_t rows, size_t n, size_t in_stride, float gain, void* prev,
+                              void* out_fm, size_t out_stride, int mem) {
+    if (!h || !iq || !out_fm || rows == 0 || in_stride < n || out_stride < n) return RCB_EINVAL;
+    if (rows > 65535) return RCB_ERANGE;
+    CK(cudaSetDevice(h->device));
+    if (n == 0) return RCB_OK;
+    const float2* d_x = (const float2*)iq;
+    float* d_o = (float*)out_fm;
+    float2* d_prev = (float2*)prev;
+    if (mem == RCB_MEM_HOST) {
+        const size_t inb = rows * in_stride * sizeof(float2), outb = rows * out_stride * sizeof(float);
+        int rc = ensure_tmp(h, 0, inb + rows * sizeof(float2));
+        if (rc) return rc;
+        rc = ensure_tmp(h, 1, outb);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(h->d_tmp[0], iq, inb, cudaMemcpyHostToDevice, h->stream));
+        d_x = (const float2*)h->d_tmp[0];
+        d_o = (float*)h->d_tmp[1];
+        d_prev = (float2*)((char*)h->d_tmp[0] + inb);
+        if (prev)
+            CK(cudaMemcpyAsync(d_prev, prev, rows * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+        else
+            CK(cudaMemsetAsync(d_prev, 0, rows * sizeof(float2), h->stream));
+        h->stats.h2d_bytes += inb;
+    } else if (mem != RCB_MEM_DEVICE) {
+        return RCB_EINVAL;
+    }
+    dim3 grid((unsigned)((n + 1023) / 1024), (unsigned)rows);
+    quad_demod_rows_kernel<<<grid, 256, 0, h->stream>>>(d_x, (long long)in_stride, d_prev, d_o, (long long)out_stride,
+                                                       (long long)n, gain, 0);
+    CKL(h);
+    if (d_prev) {
+        save_last_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, h->stream>>>(d_x, (long long)in_stride,
+                                                                              (long long)n - 1, d_prev, (int)rows);
+        CKL(h);
+    }
+    if (mem == RCB_MEM_HOST) {
+        CK(cudaMemcpyAsync(out_fm, d_o, rows * out_stride * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        if (prev) CK(cudaMemcpyAsync(prev, d_prev, rows * sizeof(float2), cudaMemcpyDeviceToHost, h->stream));
+        h->stats.d2h_bytes += rows * out_stride * sizeof(float);
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    h->stats.channel_samples += rows * n;
+    return RCB_OK;
+}
+
+extern "C" int rcb_probe_mean(rcb_t* h, const void* x, size_t rows, size_t n, size_t stride, size_t length, float scale,
+                              void* out, int mem) {
+    if (!h || !x || !out || rows == 0 || stride < n || length == 0) return RCB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    const float* d_x = (const float*)x;
+    float* d_o = (float*)out;
+    if (mem == RCB_MEM_HOST) {
+        int rc = ensure_tmp(h, 0, rows * stride * sizeof(float));
+        if (rc) return rc;
+        rc = ensure_tmp(h, 1, rows * sizeof(float));
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(h->d_tmp[0], x, rows * stride * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        d_x = (const float*)h->d_tmp[0];
+        d_o = (float*)h->d_tmp[1];
+    } else if (mem != RCB_MEM_DEVICE) {
+        return RCB_EINVAL;
+    }
+    window_sum_rows_kernel<<<(unsigned)rows, 256, 0, h->stream>>>(d_x, (long long)stride, (long long)n, (long long)length,
+                                                                 scale, d_o);
+    CKL(h);
+    if (mem == RCB_MEM_HOST) CK(cudaMemcpyAsync(out, d_o, rows * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return RCB_OK;
+}
+
+// =================================================================================================
+// K3  streaming FFT + log power
+// =================================================================================================
+extern "C" int rcb_fft_config(rcb_t* h, int length, const float* window, int avg_frames) {
+    if (!h || !window || avg_frames < 1) return RCB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    int rc = fft_config(h->fft, length, window, avg_frames, h->stream, h->sm_count);
+    if (rc == RCB_ECUDA) return fail_cuda(h, cudaGetLastError(), "fft_config");
+    return rc;
+}
+extern "C" int rcb_fft_reset(rcb_t* h) {
+    if (!h) return RCB_EINVAL;
+    if (!h->fft.configured) return RCB_ESTATE;
+    CK(cudaSetDevice(h->device));
+    int rc = fft_reset(h->fft, h->stream);
+    if (rc == RCB_ECUDA) return fail_cuda(h, cudaGetLastError(), "fft_reset");
+    return rc;
+}
+extern "C" int rcb_fft_process(rcb_t* h, const void* iq, size_t nsamples, int in_mem, void* out_sums, size_t cap_vectors,
+                               int out_mem, size_t* nvec) {
+    if (!h || (!iq && nsamples) || !nvec) return RCB_EINVAL;
+    if (!h->fft.configured) return RCB_ESTATE;
+    if (nsamples % (size_t)h->fft.L) return RCB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    uint64_t launches = 0, h2d = 0, d2h = 0;
+    int rc = fft_process(h->fft, (const float2*)iq, nsamples, in_mem, (float*)out_sums, cap_vectors, out_mem, nvec,
+                         h->stream, &launches, &h2d, &d2h);
+    h->stats.kernel_launches += launches;
+    h->stats.h2d_bytes += h2d;
+    h->stats.d2h_bytes += d2h;
+    if (rc == RCB_ECUDA) return fail_cuda(h, cudaGetLastError(), "fft_process");
+    if (rc == RCB_OK) h->stats.samples_in += nsamples;
+    return rc;
+}

@@ -1,0 +1,87 @@
+// K4  quadrature FM demod over already-channelised complex streams, and the AFC mean probe.
+//
+// quad_demod_rows: out[r][n] = gain * atan2(Im p, Re p), p = x[r][n] conj(x[r][n-1]), x[r][-1] = prev[r]
+//   = analog.quadrature_demod_cf(gain)  (gr-analog quadrature_demod_cf_impl.cc; reference call sites
+//   moto_control_demod.py:105, edacs_control_demod.py:82-84, p25_control_demod.py:120-121,
+//   logging_receiver.py:214,234,336,346), one row per channel.  12 algorithmic bytes / sample.
+// window_sum_rows: scale * sum of the last `length` samples of each row = what
+//   moving_average_ff(length, 1, ...) -> multiply_const(scale) -> probe_signal_f holds after the block
+//   (p25_control_demod.py:123-127, moto_control_demod.py:121-125, edacs_control_demod.py:98-101).
+#pragma once
+#include "common.cuh"
+
+namespace rcb {
+
+// grid: (ceil(n / (256*4)), rows).  x row stride xs (complex), out row stride os (float).
+__global__ void __launch_bounds__(256) quad_demod_rows_kernel(const float2* __restrict__ x, long long xs,
+                                                              const float2* __restrict__ prev,
+                                                              float* __restrict__ out, long long os,
+                                                              long long n, float gain, long long x_col0) {
+    const int r = blockIdx.y;
+    const float2* xr = x + (long long)r * xs + x_col0;
+    float* orow = out + (long long)r * os;
+    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= n) return;
+    float2 p = (i0 == 0) ? (prev ? prev[r] : make_float2(0.f, 0.f)) : xr[i0 - 1];
+    float o[4];
+    int cnt = (int)min((long long)4, n - i0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j < cnt) {
+            const float2 c = xr[i0 + j];
+            const float2 pr = cmul_conj(c, p);
+            o[j] = gain * atan2_fast(pr.y, pr.x);
+            p = c;
+        }
+    }
+    if (cnt == 4 && ((os & 3) == 0) && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0)) {
+        *reinterpret_cast<float4*>(orow + i0) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+        for (int j = 0; j < cnt; ++j) orow[i0 + j] = o[j];
+    }
+}
+
+// last sample of every row -> prev[r]  (streaming carry for the next block)
+__global__ void save_last_kernel(const float2* __restrict__ x, long long xs, long long last_col,
+                                 float2* __restrict__ prev, int rows) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows) prev[r] = x[(long long)r * xs + last_col];
+}
+
+// generic-PFB emit: ys is [N][T+1] (column 0 = frame -1).  Writes IQ and / or FM channel-major.
+__global__ void __launch_bounds__(256) pfb_generic_emit_kernel(const float2* __restrict__ ys, long long ystride,
+                                                               float2* __restrict__ out_iq,
+                                                               float* __restrict__ out_fm, long long ostride,
+                                                               int T, float gain) {
+    const int m = blockIdx.y;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const float2 c = ys[(long long)m * ystride + t + 1];
+    if (out_iq) out_iq[(long long)m * ostride + t] = c;
+    if (out_fm) {
+        const float2 pv = ys[(long long)m * ystride + t];
+        const float2 pr = cmul_conj(c, pv);
+        out_fm[(long long)m * ostride + t] = gain * atan2_fast(pr.y, pr.x);
+    }
+}
+
+// one CTA per row: scale * sum of x[r][n-length .. n-1] (clamped at 0), double accumulate.
+__global__ void __launch_bounds__(256) window_sum_rows_kernel(const float* __restrict__ x, long long xs,
+                                                              long long n, long long length, float scale,
+                                                              float* __restrict__ out) {
+    const int r = blockIdx.x;
+    const float* xr = x + (long long)r * xs;
+    const long long lo = (n > length) ? n - length : 0;
+    double acc = 0.0;
+    for (long long i = lo + threadIdx.x; i < n; i += blockDim.x) acc += (double)xr[i];
+    __shared__ double sh[256];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[r] = (float)(sh[0] * (double)scale);
+}
+
+}  // namespace rcb

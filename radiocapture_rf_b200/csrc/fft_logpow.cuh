@@ -1,0 +1,405 @@
+// K3  fft_logpow : streaming windowed FFT + |.|^2 + log10 + frame accumulation (the scan path).
+//
+// Replaces the GNU Radio chain of fft_vector.py:37-60:
+//   stream_to_vector(L) -> fft.fft_vcc(L, forward, window, shift=True) -> complex_to_mag_squared
+//   -> nlog10_ff(1, L, 1) -> moving_average_ff(avg, 1, ...)
+// (gr-fft fft_vcc_fftw.cc, gr-blocks complex_to_mag_squared / nlog10_ff / moving_average impl).
+//
+// L = L1*L2 (L1 <= L2, each R*R with R in {8,16,32}: L = 2^12, 2^14, 2^16, 2^18, 2^20) is done as a
+// four-step FFT in two kernels whose 8 MB-per-frame intermediate stays L2-resident (126 MB L2), so HBM
+// sees ~8 B per input sample:
+//   A  fft_cols : CTA = 8*F adjacent columns n2 of one frame.  Coalesced (CB*8-byte row segments)
+//                 window-multiplied load -> smem transpose -> per-warp L1-point FFT (two in-register
+//                 radix-R passes, warp_fft_2pass) -> W_L^{-n2 k1} twiddle from a two-level smem table
+//                 -> smem transpose -> coalesced store of B[k1][n2] to the L2-resident scratch.
+//   B  fft_rows : CTA = 8*F adjacent rows k1.  Per-warp L2-point FFT of a contiguous row -> power ->
+//                 log10 + 1 -> smem transpose -> 32 B-sector stores of vals[frame][fftshift(k)],
+//                 k = k1 + L1*k2 (8 consecutive k1 per store).
+//   C  fold     : acc[k] += sum over the frames of the sub-batch (fixed order => deterministic);
+//                 when an averaging block of `avg` frames completes the vector is emitted.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+#include "fft_inreg.cuh"
+
+namespace rcb {
+
+struct FftParams {
+    const float2* x;       // frames of this sub-batch, frame f at x + f*L
+    const float* window;   // [L]
+    float2* scratch;       // [SB][L1][L2]
+    float* vals;           // [SB][L]
+    const float2* tw1;     // [R1][R1+2]  W_{L1}^{-ll m1}
+    const float2* tw2;     // [R2][R2+2]  W_{L2}^{-ll m1}
+    const float2* t_lo;    // [min(L,1024)] W_L^{-q}
+    const float2* t_hi;    // [max(1,L/1024)] W_L^{-1024 q}
+    int L, L1, L2;
+};
+
+template <int R>
+struct FftGeom {
+    static constexpr int N = R * R;
+    static constexpr int F = 32 / R;
+    static constexpr int CB = 8 * F;                        // columns (A) / rows (B) per CTA
+    static constexpr int S = R + 2;
+    static constexpr int FS = (R == 8) ? 88 : R * S;        // per-frame FFT scratch (complex)
+    static constexpr int CS = (R == 32) ? (N + 66) : (N + 1);  // column stride of the input tile (A)
+    static constexpr int OS = CB + 1;                       // row stride of the output tile (A)
+    // A: region0 = max(input tile CB*CS, out tile N*OS, per-frame scratch CB*FS)
+    static constexpr int A_REGION = (CB * CS > N * OS ? (CB * CS > CB * FS ? CB * CS : CB * FS)
+                                                     : (N * OS > CB * FS ? N * OS : CB * FS));
+    static constexpr size_t a_smem(int L) {
+        return (size_t)A_REGION * 8 + (size_t)R * S * 8 + (size_t)(L < 1024 ? L : 1024) * 8 +
+               (size_t)(L / 1024 > 0 ? L / 1024 : 1) * 8;
+    }
+    static constexpr size_t b_smem() { return (size_t)CB * FS * 8 + (size_t)R * S * 8; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// A: column FFTs.  grid (L2/CB, SB), block 256.
+// ---------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(256, 2) fft_cols_kernel(const FftParams p) {
+    using G = FftGeom<R>;
+    constexpr int N = G::N, F = G::F, CB = G::CB, S = G::S, FS = G::FS, CS = G::CS, OS = G::OS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* region = reinterpret_cast<float2*>(smem_raw);
+    float2* tws = region + G::A_REGION;
+    float2* tlo = tws + R * S;
+    const int nlo = p.L < 1024 ? p.L : 1024;
+    float2* thi = tlo + nlo;
+    const int nhi = p.L / 1024 > 0 ? p.L / 1024 : 1;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int fr = lane / R, ll = lane % R;
+    const int c0 = blockIdx.x * CB;
+    const int f = blockIdx.y;
+    const float2* xf = p.x + (size_t)f * p.L;
+
+    for (int i = tid; i < R * S; i += 256) tws[i] = p.tw1[i];
+    for (int i = tid; i < nlo; i += 256) tlo[i] = p.t_lo[i];
+    for (int i = tid; i < nhi; i += 256) thi[i] = p.t_hi[i];
+    // coalesced, window-multiplied load of the [N rows][CB cols] tile, transposed into region[c*CS + n1]
+#pragma unroll 4
+    for (int idx = tid; idx < N * CB; idx += 256) {
+        const int n1 = idx / CB, c = idx % CB;
+        const size_t g = (size_t)n1 * p.L2 + c0 + c;
+        const float2 xv = ld_stream_f2(xf + g);
+        const float w = __ldg(p.window + g);
+        region[c * CS + n1] = make_float2(xv.x * w, xv.y * w);
+    }
+    __syncthreads();
+    const int col = warp * F + fr;  // this lane's column within the CTA
+    float2 v[R];
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) v[jj] = region[col * CS + jj * R + ll];
+    __syncthreads();  // everyone holds its column in registers: the region can be reused
+    float2* buf = region + col * FS;
+    warp_fft_2pass<R, -1, false>(v, buf, tws, ll);  // v[m2] = A[k1 = ll + R*m2] for column c0+col
+    __syncthreads();  // all per-frame scratch dead: region becomes the [k1][CB] output tile
+    {
+        const int n2 = c0 + col;
+#pragma unroll
+        for (int m2 = 0; m2 < R; ++m2) {
+            const int k1 = ll + R * m2;
+            const int q = n2 * k1;  // < L1*L2 = L
+            const float2 wl = tlo[q & 1023];
+            const float2 wh = thi[q >> 10];
+            const float2 w = cmul(wl, wh);
+            region[k1 * OS + col] = cmul(v[m2], w);
+        }
+    }
+    __syncthreads();
+    float2* out = p.scratch + (size_t)f * p.L;
+#pragma unroll 4
+    for (int idx = tid; idx < N * CB; idx += 256) {
+        const int k1 = idx / CB, c = idx % CB;
+        out[(size_t)k1 * p.L2 + c0 + c] = region[k1 * OS + c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// B: row FFTs + log power.  grid (L1/CB, SB), block 256.
+// ---------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(256, 2) fft_rows_kernel(const FftParams p) {
+    using G = FftGeom<R>;
+    constexpr int N = G::N, F = G::F, CB = G::CB, S = G::S, FS = G::FS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* bufs = reinterpret_cast<float2*>(smem_raw);
+    float2* tws = bufs + CB * FS;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int fr = lane / R, ll = lane % R;
+    const int r0 = blockIdx.x * CB;
+    const int f = blockIdx.y;
+    for (int i = tid; i < R * S; i += 256) tws[i] = p.tw2[i];
+    __syncthreads();
+    const int row = warp * F + fr;
+    const float2* src = p.scratch + (size_t)f * p.L + (size_t)(r0 + row) * N;
+    float2 v[R];
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) v[jj] = __ldcg(src + jj * R + ll);
+    float2* buf = bufs + row * FS;
+    warp_fft_2pass<R, -1, false>(v, buf, tws, ll);  // v[m2] = X[k1 + L1*k2], k2 = ll + R*m2
+    float* fb = reinterpret_cast<float*>(buf);
+#pragma unroll
+    for (int m2 = 0; m2 < R; ++m2) {
+        const float pw = fmaf(v[m2].x, v[m2].x, v[m2].y * v[m2].y);
+        // nlog10_ff(1, L, 1): log10(max(p, 1e-18)) + 1
+        fb[m2 * S + ll] = fmaf(log2f(fmaxf(pw, 1e-18f)), 0.30102999566398120f, 1.0f);
+    }
+    __syncthreads();
+    // thread item = (k2, group of 8 consecutive rows): one 32 B store into vals[f][fftshift(k)]
+    constexpr int ITEMS = N * (CB / 8) / 256;
+    float* vf = p.vals + (size_t)f * p.L;
+#pragma unroll
+    for (int q = 0; q < ITEMS; ++q) {
+        const int item = q * 256 + tid;
+        const int k2 = item % N, g = item / N;
+        const int pos = (k2 / R) * S + (k2 % R);
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = reinterpret_cast<const float*>(bufs + (8 * g + j) * FS)[pos];
+        const int k2s = (k2 + N / 2) % N;  // fftshift: only k2 moves since L/2 = L1*(L2/2)
+        st_global_v8(vf + (size_t)k2s * p.L1 + r0 + 8 * g, o);
+    }
+}
+
+// C: acc[k] += sum_f vals[f][k] (f ascending).  If emit != null the block is complete: emit and clear.
+__global__ void __launch_bounds__(256) fft_fold_kernel(const float* __restrict__ vals, int nframes, int L,
+                                                       float* __restrict__ acc, float* __restrict__ emit) {
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (k >= L) return;
+    float4 a = *reinterpret_cast<const float4*>(acc + k);
+    for (int f = 0; f < nframes; ++f) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(vals + (size_t)f * L + k));
+        a.x += v.x;
+        a.y += v.y;
+        a.z += v.z;
+        a.w += v.w;
+    }
+    if (emit) {
+        *reinterpret_cast<float4*>(emit + k) = a;
+        a = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    *reinterpret_cast<float4*>(acc + k) = a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct FftState {
+    bool configured = false;
+    int L = 0, L1 = 0, L2 = 0, R1 = 0, R2 = 0, avg = 0;
+    int sb = 0;               // frames per sub-batch (scratch kept L2 resident)
+    int in_block = 0;         // frames already folded into the current averaging block
+    float* d_window = nullptr;
+    float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_tlo = nullptr, *d_thi = nullptr;
+    float2* d_scratch = nullptr;
+    float* d_vals = nullptr;
+    float* d_acc = nullptr;
+    float* d_emit = nullptr;  // staging for vectors when the caller's buffer is host memory
+    size_t emit_cap = 0;
+    float2* d_in = nullptr;   // staging for host input
+    size_t in_cap = 0;
+};
+
+inline void fft_free(FftState& s) {
+    cudaFree(s.d_window);
+    cudaFree(s.d_tw1);
+    cudaFree(s.d_tw2);
+    cudaFree(s.d_tlo);
+    cudaFree(s.d_thi);
+    cudaFree(s.d_scratch);
+    cudaFree(s.d_vals);
+    cudaFree(s.d_acc);
+    cudaFree(s.d_emit);
+    cudaFree(s.d_in);
+    s = FftState{};
+}
+
+inline std::vector<float2> fft_tw_table(int R, int N) {
+    const int S = R + 2;
+    std::vector<float2> t((size_t)R * S, make_float2(0.f, 0.f));
+    for (int ll = 0; ll < R; ++ll)
+        for (int m1 = 0; m1 < R; ++m1) {
+            const double a = -2.0 * M_PI * (double)((ll * m1) % N) / (double)N;
+            t[(size_t)ll * S + m1] = make_float2((float)cos(a), (float)sin(a));
+        }
+    return t;
+}
+
+#define FCK(call)                              \
+    do {                                       \
+        if ((call) != cudaSuccess) return -3;  \
+    } while (0)
+
+inline int fft_config(FftState& s, int L, const float* window, int avg, cudaStream_t st, int sm_count) {
+    (void)sm_count;
+    fft_free(s);
+    int r1 = 0, r2 = 0;
+    switch (L) {
+        case 1 << 12: r1 = 8; r2 = 8; break;
+        case 1 << 14: r1 = 8; r2 = 16; break;
+        case 1 << 16: r1 = 16; r2 = 16; break;
+        case 1 << 18: r1 = 16; r2 = 32; break;
+        case 1 << 20: r1 = 32; r2 = 32; break;
+        default: return -7;  // RCB_EUNSUPPORTED
+    }
+    s.L = L;
+    s.R1 = r1;
+    s.R2 = r2;
+    s.L1 = r1 * r1;
+    s.L2 = r2 * r2;
+    s.avg = avg;
+    // sub-batch: keep scratch (8 B) + vals (4 B) per sample under ~48 MB so they stay in L2
+    s.sb = (int)std::max<size_t>(1, std::min<size_t>(((size_t)48 << 20) / ((size_t)L * 12), 4096));
+    FCK(cudaMalloc(&s.d_window, sizeof(float) * L));
+    FCK(cudaMemcpyAsync(s.d_window, window, sizeof(float) * L, cudaMemcpyHostToDevice, st));
+    auto t1 = fft_tw_table(r1, s.L1), t2 = fft_tw_table(r2, s.L2);
+    const int nlo = L < 1024 ? L : 1024, nhi = L / 1024 > 0 ? L / 1024 : 1;
+    std::vector<float2> lo(nlo), hi(nhi);
+    for (int q = 0; q < nlo; ++q) {
+        const double a = -2.0 * M_PI * (double)q / (double)L;
+        lo[q] = make_float2((float)cos(a), (float)sin(a));
+    }
+    for (int q = 0; q < nhi; ++q) {
+        const double a = -2.0 * M_PI * (double)q * 1024.0 / (double)L;
+        hi[q] = make_float2((float)cos(a), (float)sin(a));
+    }
+    FCK(cudaMalloc(&s.d_tw1, t1.size() * sizeof(float2)));
+    FCK(cudaMalloc(&s.d_tw2, t2.size() * sizeof(float2)));
+    FCK(cudaMalloc(&s.d_tlo, lo.size() * sizeof(float2)));
+    FCK(cudaMalloc(&s.d_thi, hi.size() * sizeof(float2)));
+    FCK(cudaMemcpyAsync(s.d_tw1, t1.data(), t1.size() * sizeof(float2), cudaMemcpyHostToDevice, st));
+    FCK(cudaMemcpyAsync(s.d_tw2, t2.data(), t2.size() * sizeof(float2), cudaMemcpyHostToDevice, st));
+    FCK(cudaMemcpyAsync(s.d_tlo, lo.data(), lo.size() * sizeof(float2), cudaMemcpyHostToDevice, st));
+    FCK(cudaMemcpyAsync(s.d_thi, hi.data(), hi.size() * sizeof(float2), cudaMemcpyHostToDevice, st));
+    FCK(cudaMalloc(&s.d_scratch, (size_t)s.sb * L * sizeof(float2)));
+    FCK(cudaMalloc(&s.d_vals, (size_t)s.sb * L * sizeof(float)));
+    FCK(cudaMalloc(&s.d_acc, (size_t)L * sizeof(float)));
+    FCK(cudaMemsetAsync(s.d_acc, 0, (size_t)L * sizeof(float), st));
+    FCK(cudaStreamSynchronize(st));
+    s.in_block = 0;
+    s.configured = true;
+    return 0;
+}
+
+inline int fft_reset(FftState& s, cudaStream_t st) {
+    FCK(cudaMemsetAsync(s.d_acc, 0, (size_t)s.L * sizeof(float), st));
+    FCK(cudaStreamSynchronize(st));
+    s.in_block = 0;
+    return 0;
+}
+
+template <int R>
+inline int fft_launch_cols(const FftParams& p, int nfr, cudaStream_t st) {
+    using G = FftGeom<R>;
+    const size_t smem = G::a_smem(p.L);
+    static size_t attr = 0;  // the opt-in limit must cover the largest L used with this R
+    if (smem > attr) {
+        FCK(cudaFuncSetAttribute(fft_cols_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    dim3 grid(p.L2 / G::CB, nfr);
+    fft_cols_kernel<R><<<grid, 256, smem, st>>>(p);
+    FCK(cudaGetLastError());
+    return 0;
+}
+template <int R>
+inline int fft_launch_rows(const FftParams& p, int nfr, cudaStream_t st) {
+    using G = FftGeom<R>;
+    const size_t smem = G::b_smem();
+    static size_t attr = 0;
+    if (smem > attr) {
+        FCK(cudaFuncSetAttribute(fft_rows_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    dim3 grid(p.L1 / G::CB, nfr);
+    fft_rows_kernel<R><<<grid, 256, smem, st>>>(p);
+    FCK(cudaGetLastError());
+    return 0;
+}
+
+inline int fft_process(FftState& s, const float2* iq, size_t nsamples, int in_mem, float* out, size_t cap_vec,
+                       int out_mem, size_t* nvec, cudaStream_t st, uint64_t* launches, uint64_t* h2d, uint64_t* d2h) {
+    *nvec = 0;
+    const size_t L = (size_t)s.L;
+    size_t nframes = nsamples / L;
+    // vectors this call will complete
+    const size_t will_emit = (s.in_block + nframes) / (size_t)s.avg;
+    if (will_emit > cap_vec || (will_emit && !out)) return -6;  // RCB_ERANGE
+    const float2* d_x = iq;
+    if (in_mem == 0) {  // host: stage one sub-batch at a time
+        const size_t need = (size_t)s.sb * L;
+        if (s.in_cap < need) {
+            cudaFree(s.d_in);
+            s.d_in = nullptr;
+            s.in_cap = 0;
+            FCK(cudaMalloc(&s.d_in, need * sizeof(float2)));
+            s.in_cap = need;
+        }
+    }
+    if (out_mem == 0 && will_emit) {
+        if (s.emit_cap < will_emit * L) {
+            cudaFree(s.d_emit);
+            s.d_emit = nullptr;
+            s.emit_cap = 0;
+            FCK(cudaMalloc(&s.d_emit, will_emit * L * sizeof(float)));
+            s.emit_cap = will_emit * L;
+        }
+    }
+    float* d_out = (out_mem == 0) ? s.d_emit : out;
+    size_t done = 0, emitted = 0;
+    while (done < nframes) {
+        const int room = s.avg - s.in_block;
+        const int nfr = (int)std::min<size_t>(std::min<size_t>(s.sb, nframes - done), (size_t)room);
+        if (in_mem == 0) {
+            FCK(cudaMemcpyAsync(s.d_in, iq + done * L, (size_t)nfr * L * sizeof(float2), cudaMemcpyHostToDevice, st));
+            *h2d += (size_t)nfr * L * sizeof(float2);
+            d_x = s.d_in;
+        } else {
+            d_x = iq + done * L;
+        }
+        FftParams p{};
+        p.x = d_x;
+        p.window = s.d_window;
+        p.scratch = s.d_scratch;
+        p.vals = s.d_vals;
+        p.tw1 = s.d_tw1;
+        p.tw2 = s.d_tw2;
+        p.t_lo = s.d_tlo;
+        p.t_hi = s.d_thi;
+        p.L = s.L;
+        p.L1 = s.L1;
+        p.L2 = s.L2;
+        int rc = (s.R1 == 8) ? fft_launch_cols<8>(p, nfr, st) : (s.R1 == 16) ? fft_launch_cols<16>(p, nfr, st)
+                                                                            : fft_launch_cols<32>(p, nfr, st);
+        if (rc) return rc;
+        rc = (s.R2 == 8) ? fft_launch_rows<8>(p, nfr, st) : (s.R2 == 16) ? fft_launch_rows<16>(p, nfr, st)
+                                                                        : fft_launch_rows<32>(p, nfr, st);
+        if (rc) return rc;
+        const bool complete = (s.in_block + nfr == s.avg);
+        float* emit = complete ? d_out + emitted * L : nullptr;
+        fft_fold_kernel<<<(unsigned)((L / 4 + 255) / 256), 256, 0, st>>>(s.d_vals, nfr, s.L, s.d_acc, emit);
+        FCK(cudaGetLastError());
+        *launches += 3;
+        s.in_block += nfr;
+        if (complete) {
+            s.in_block = 0;
+            ++emitted;
+        }
+        done += nfr;
+    }
+    if (out_mem == 0 && emitted) {
+        FCK(cudaMemcpyAsync(out, s.d_emit, emitted * L * sizeof(float), cudaMemcpyDeviceToHost, st));
+        *d2h += emitted * L * sizeof(float);
+    }
+    if (in_mem == 0 || out_mem == 0) FCK(cudaStreamSynchronize(st));
+    *nvec = emitted;
+    return 0;
+}
+#undef FCK
+
+}  // namespace rcb

@@ -1,0 +1,274 @@
+"""Python host over the C ABI (ctypes, numpy only).  One ``Engine`` = one rcb handle = one wideband
+stream on one GPU (rc_frontend/receiver.py runs one frontend process per SDR source, :67-70).
+
+Classes
+  Engine          handle, device/pinned memory, timers
+  PfbChannelizer  K1  (pfb.channelizer_ccf + per-bin quadrature_demod_cf; rc_frontend/receiver.py:249-261)
+  DdcBank         K2  (freq_xlating_fir_filter_ccc per channel; rc_frontend/channel.py:35)
+  FftScanner      K3  (fft_vector.py:37-60)
+  Engine.quad_demod / Engine.probe_mean  K4
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (MEM_DEVICE, MEM_HOST, OUT_FM, OUT_IQ, COPY_D2D, COPY_D2H, COPY_H2D, B200ChanError, check)
+
+
+def device_count():
+    n = C.c_int(0)
+    st = _lib.load().rcb_device_count(C.byref(n))
+    return n.value if st == 0 else 0
+
+
+class DeviceBuffer(object):
+    """Raw device allocation owned by an Engine."""
+
+    def __init__(self, engine, nbytes):
+        self.engine = engine
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        check(engine.lib.rcb_dev_alloc(engine.h, self.nbytes, C.byref(p)), "rcb_dev_alloc", engine.h)
+        self.ptr = p.value
+
+    def free(self):
+        if self.ptr:
+            self.engine.lib.rcb_dev_free(self.engine.h, self.ptr)
+            self.ptr = None
+
+    def offset(self, nbytes):
+        return self.ptr + int(nbytes)
+
+
+class Engine(object):
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        check(self.lib.rcb_open(int(device), C.byref(h)), "rcb_open(device=%d)" % device)
+        self.h = h
+        self.device = device
+        self._pinned = []
+
+    # ---- lifecycle -------------------------------------------------------------------------------
+    def close(self):
+        if self.h:
+            for p in self._pinned:
+                self.lib.rcb_host_free(self.h, p)
+            self._pinned = []
+            self.lib.rcb_close(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def sync(self):
+        check(self.lib.rcb_sync(self.h), "rcb_sync", self.h)
+
+    def device_name(self):
+        buf = C.create_string_buffer(256)
+        sm = C.c_int(0)
+        check(self.lib.rcb_device_name(self.h, buf, 256, C.byref(sm)), "rcb_device_name", self.h)
+        return buf.value.decode(), sm.value
+
+    def stats(self):
+        s = _lib.rcb_stats_t()
+        check(self.lib.rcb_stats(self.h, C.byref(s)), "rcb_stats", self.h)
+        return {k: int(getattr(s, k)) for k, _ in s._fields_}
+
+    # ---- memory ----------------------------------------------------------------------------------
+    def dev_alloc(self, nbytes):
+        return DeviceBuffer(self, nbytes)
+
+    def pinned(self, shape, dtype):
+        """numpy array backed by pinned host memory (freed with the engine)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        check(self.lib.rcb_host_alloc(self.h, max(n, 1), C.byref(p)), "rcb_host_alloc", self.h)
+        self._pinned.append(p.value)
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def to_device(self, arr):
+        arr = np.ascontiguousarray(arr)
+        d = self.dev_alloc(max(arr.nbytes, 1))
+        check(self.lib.rcb_memcpy(self.h, d.ptr, arr.ctypes.data, arr.nbytes, COPY_H2D), "rcb_memcpy h2d", self.h)
+        return d
+
+    def to_host(self, dev_ptr, shape, dtype):
+        out = np.empty(shape, dtype=dtype)
+        ptr = dev_ptr.ptr if isinstance(dev_ptr, DeviceBuffer) else dev_ptr
+        check(self.lib.rcb_memcpy(self.h, out.ctypes.data, ptr, out.nbytes, COPY_D2H), "rcb_memcpy d2h", self.h)
+        return out
+
+    def copy_d2d(self, dst_ptr, src_ptr, nbytes):
+        check(self.lib.rcb_memcpy(self.h, dst_ptr, src_ptr, nbytes, COPY_D2D), "rcb_memcpy d2d", self.h)
+
+    def l2_flush(self):
+        check(self.lib.rcb_l2_flush(self.h), "rcb_l2_flush", self.h)
+
+    def timer_start(self):
+        check(self.lib.rcb_timer_start(self.h), "rcb_timer_start", self.h)
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        check(self.lib.rcb_timer_stop(self.h, C.byref(ms)), "rcb_timer_stop", self.h)
+        return ms.value
+
+    # ---- K4 --------------------------------------------------------------------------------------
+    def quad_demod(self, x, gain, prev=None):
+        """analog.quadrature_demod_cf(gain) over rows of x (complex64 [rows][n] or [n]).
+        Returns (fm float32 same shape, last samples per row)."""
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        one = (x.ndim == 1)
+        x2 = x.reshape(1, -1) if one else x
+        rows, n = x2.shape
+        out = np.empty((rows, n), dtype=np.float32)
+        pv = np.zeros(rows, dtype=np.complex64) if prev is None else np.ascontiguousarray(
+            np.broadcast_to(np.asarray(prev, np.complex64), (rows,)))
+        pv = pv.copy()
+        if n:
+            check(self.lib.rcb_quad_demod(self.h, x2.ctypes.data, rows, n, n, float(gain), pv.ctypes.data,
+                                          out.ctypes.data, n, MEM_HOST), "rcb_quad_demod", self.h)
+        return (out[0] if one else out), (pv[0] if one else pv)
+
+    def probe_mean(self, x, length, scale):
+        """moving_average_ff(length,1,..) -> multiply_const(scale) -> probe value after the block."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        x2 = x.reshape(1, -1) if x.ndim == 1 else x
+        rows, n = x2.shape
+        out = np.empty(rows, dtype=np.float32)
+        check(self.lib.rcb_probe_mean(self.h, x2.ctypes.data, rows, n, n, int(length), float(scale),
+                                      out.ctypes.data, MEM_HOST), "rcb_probe_mean", self.h)
+        return out[0] if x.ndim == 1 else out
+
+
+class PfbChannelizer(object):
+    """K1: N-channel critically sampled polyphase channelizer with fused FM demod."""
+
+    def __init__(self, engine, nchans, taps, out_mask=OUT_IQ, fm_gain=1.0):
+        self.e = engine
+        self.nchans = int(nchans)
+        self.out_mask = int(out_mask)
+        taps = np.ascontiguousarray(taps, dtype=np.float32)
+        self.ntaps = len(taps)
+        check(engine.lib.rcb_pfb_config(engine.h, self.nchans, taps.ctypes.data, len(taps), self.out_mask,
+                                        float(fm_gain)), "rcb_pfb_config", engine.h)
+
+    def reset(self):
+        check(self.e.lib.rcb_pfb_reset(self.e.h), "rcb_pfb_reset", self.e.h)
+
+    def process(self, iq, out_iq=None, out_fm=None):
+        """iq: complex64 host array, len multiple of nchans.  Returns (iq_out [N][T] or None, fm_out or None)."""
+        iq = np.ascontiguousarray(iq, dtype=np.complex64)
+        if len(iq) % self.nchans:
+            raise ValueError("nsamples must be a multiple of nchans")
+        t = len(iq) // self.nchans
+        if (self.out_mask & OUT_IQ) and out_iq is None:
+            out_iq = np.empty((self.nchans, t), dtype=np.complex64)
+        if (self.out_mask & OUT_FM) and out_fm is None:
+            out_fm = np.empty((self.nchans, t), dtype=np.float32)
+        nout = C.c_size_t(0)
+        check(self.e.lib.rcb_pfb_process(
+            self.e.h, iq.ctypes.data, len(iq), MEM_HOST,
+            out_iq.ctypes.data if out_iq is not None else None,
+            out_fm.ctypes.data if out_fm is not None else None,
+            max(t, 1), MEM_HOST, C.byref(nout)), "rcb_pfb_process", self.e.h)
+        return out_iq, out_fm
+
+    def process_device(self, d_in, nsamples, d_iq, d_fm, out_stride):
+        """All pointers device resident (ints / DeviceBuffer).  Asynchronous: returns after the launch."""
+        def _p(x):
+            return x.ptr if isinstance(x, DeviceBuffer) else x
+        nout = C.c_size_t(0)
+        check(self.e.lib.rcb_pfb_process(self.e.h, _p(d_in), int(nsamples), MEM_DEVICE, _p(d_iq), _p(d_fm),
+                                         int(out_stride), MEM_DEVICE, C.byref(nout)), "rcb_pfb_process", self.e.h)
+        return nout.value
+
+
+class DdcBank(object):
+    """K2: bank of freq_xlating_fir_filter_ccc channels over one wideband stream."""
+
+    def __init__(self, engine):
+        self.e = engine
+
+    def open(self, decim, taps, center_freq, samp_rate, out_mask=OUT_IQ, fm_gain=1.0):
+        taps = np.ascontiguousarray(taps, dtype=np.float32)
+        cid = C.c_int(0)
+        check(self.e.lib.rcb_ddc_open(self.e.h, int(decim), taps.ctypes.data, len(taps), float(center_freq),
+                                      float(samp_rate), int(out_mask), float(fm_gain), C.byref(cid)),
+              "rcb_ddc_open", self.e.h)
+        return cid.value
+
+    def retune(self, chan, center_freq):
+        check(self.e.lib.rcb_ddc_retune(self.e.h, int(chan), float(center_freq)), "rcb_ddc_retune", self.e.h)
+
+    def set_taps(self, chan, taps):
+        taps = np.ascontiguousarray(taps, dtype=np.float32)
+        check(self.e.lib.rcb_ddc_set_taps(self.e.h, int(chan), taps.ctypes.data, len(taps)), "rcb_ddc_set_taps",
+              self.e.h)
+
+    def close(self, chan):
+        check(self.e.lib.rcb_ddc_close(self.e.h, int(chan)), "rcb_ddc_close", self.e.h)
+
+    def process(self, iq):
+        iq = np.ascontiguousarray(iq, dtype=np.complex64)
+        check(self.e.lib.rcb_ddc_process(self.e.h, iq.ctypes.data, len(iq), MEM_HOST), "rcb_ddc_process", self.e.h)
+
+    def process_device(self, d_in, nsamples):
+        p = d_in.ptr if isinstance(d_in, DeviceBuffer) else d_in
+        check(self.e.lib.rcb_ddc_process(self.e.h, p, int(nsamples), MEM_DEVICE), "rcb_ddc_process", self.e.h)
+
+    def pull(self, chan, which=OUT_IQ):
+        n = C.c_size_t(0)
+        # first ask for the size (dst NULL is only legal when there is nothing to fetch)
+        st = self.e.lib.rcb_ddc_pull(self.e.h, int(chan), int(which), None, 0, MEM_HOST, C.byref(n))
+        if st not in (0, _lib.RCB_ERANGE):
+            check(st, "rcb_ddc_pull", self.e.h)
+        dt = np.complex64 if which == OUT_IQ else np.float32
+        out = np.empty(n.value, dtype=dt)
+        if n.value:
+            check(self.e.lib.rcb_ddc_pull(self.e.h, int(chan), int(which), out.ctypes.data, n.value, MEM_HOST,
+                                          C.byref(n)), "rcb_ddc_pull", self.e.h)
+        return out
+
+
+class FftScanner(object):
+    """K3: windowed streaming FFT + log-power block sums (fft_vector.py flowgraph)."""
+
+    def __init__(self, engine, length, window, avg_frames=100):
+        self.e = engine
+        self.length = int(length)
+        self.avg = int(avg_frames)
+        window = np.ascontiguousarray(window, dtype=np.float32)
+        if len(window) != self.length:
+            raise ValueError("window length != fft length")
+        check(engine.lib.rcb_fft_config(engine.h, self.length, window.ctypes.data, self.avg), "rcb_fft_config",
+              engine.h)
+
+    def reset(self):
+        check(self.e.lib.rcb_fft_reset(self.e.h), "rcb_fft_reset", self.e.h)
+
+    def process(self, iq):
+        """Returns float32 [nvec][L]: one vector per completed block of avg frames."""
+        iq = np.ascontiguousarray(iq, dtype=np.complex64)
+        if len(iq) % self.length:
+            raise ValueError("nsamples must be a multiple of the FFT length")
+        cap = len(iq) // self.length // self.avg + 1
+        out = np.empty((cap, self.length), dtype=np.float32)
+        n = C.c_size_t(0)
+        check(self.e.lib.rcb_fft_process(self.e.h, iq.ctypes.data, len(iq), MEM_HOST, out.ctypes.data, cap, MEM_HOST,
+                                         C.byref(n)), "rcb_fft_process", self.e.h)
+        return out[:n.value]
+
+    def process_device(self, d_in, nsamples, d_out, cap_vectors):
+        def _p(x):
+            return x.ptr if isinstance(x, DeviceBuffer) else x
+        n = C.c_size_t(0)
+        check(self.e.lib.rcb_fft_process(self.e.h, _p(d_in), int(nsamples), MEM_DEVICE, _p(d_out), int(cap_vectors),
+                                         MEM_DEVICE, C.byref(n)), "rcb_fft_process", self.e.h)
+        return n.value

@@ -1,0 +1,181 @@
+"""K2 / K4 parity: DDC bank (freq_xlating_fir_filter_ccc per channel) + quad demod vs the float64 oracle."""
+import numpy as np
+import pytest
+
+from oracle import gr_blocks as gb, gr_firdes as fd, synth
+from radiocapture_rf_b200.engine import DdcBank, OUT_FM, OUT_IQ
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _fm_err(fm, ref, gain):
+    d = (fm.astype(np.float64) - ref) / gain
+    d = (d + np.pi) % (2 * np.pi) - np.pi
+    return np.linalg.norm(d) / max(np.linalg.norm(ref / gain), 1e-30)
+
+
+def test_cfg1_single_channel_xlat_fm(engine):
+    """BASELINE config 1: fs 2.4 Msps, offset -62.5 kHz, rate 12500 -> D 96, 349 taps, gains 5 and 6.6315."""
+    x, fs, offs = synth.cfg1(1 << 20, seed=1)
+    decim, taps = fd.channel_taps(fs, 12500)
+    assert decim == 96 and len(taps) == 349
+    bank = DdcBank(engine)
+    g2 = 25000.0 / (2 * np.pi * 600.0)
+    c1 = bank.open(decim, taps, -62500.0, fs, OUT_IQ | OUT_FM, 5.0)
+    c2 = bank.open(decim, taps, -62500.0, fs, OUT_IQ | OUT_FM, g2)
+    bank.process(x)
+    y1 = bank.pull(c1, OUT_IQ)
+    f1 = bank.pull(c1, OUT_FM)
+    f2 = bank.pull(c2, OUT_FM)
+    ref = gb.freq_xlating_fir(x, taps, decim, -62500.0, fs)
+    assert len(y1) == len(ref) == (1 << 20) // 96 + 1 - (1 if ((1 << 20) % 96 == 0) else 0) or len(y1) == len(ref) + 1
+    n = min(len(y1), len(ref))
+    assert gb.rel_l2(y1[:n], ref[:n]) <= TOL
+    fref = gb.quadrature_demod(ref[:n], 1.0)
+    assert _fm_err(f1[:n], 5.0 * fref, 5.0) <= TOL
+    assert _fm_err(f2[:n], g2 * fref, g2) <= TOL
+
+
+def test_ddc_output_count_and_decimation_phase(engine):
+    """Output i's newest sample is x[i*D]: a block of n samples yields ceil(n/D) outputs from a fresh channel."""
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal(1000) + 1j * rng.standard_normal(1000)).astype(np.complex64)
+    taps = fd.low_pass(1, 8.0, 1.0, 1.0)
+    bank = DdcBank(engine)
+    c = bank.open(7, taps, 0.3, 8.0)
+    bank.process(x)
+    y = bank.pull(c)
+    assert len(y) == (1000 + 6) // 7
+    # oracle convention: one output per D inputs, first output uses x[0] as newest sample
+    xr = np.concatenate([x, np.zeros(6, np.complex64)])
+    ref = gb.freq_xlating_fir(xr, taps, 7, 0.3, 8.0)
+    assert gb.rel_l2(y, ref[:len(y)]) <= TOL
+
+
+def test_ddc_many_channels_share_one_block(engine):
+    x, fs, offs = synth.cfg1(1 << 18, seed=11)
+    decim, taps = fd.channel_taps(fs, 12500)
+    bank = DdcBank(engine)
+    ids = [bank.open(decim, taps, f, fs, OUT_IQ | OUT_FM, 5.0) for f in offs]
+    bank.process(x)
+    for cid, f in zip(ids, offs):
+        y = bank.pull(cid)
+        ref = gb.freq_xlating_fir(x, taps, decim, f, fs)
+        n = min(len(y), len(ref))
+        assert gb.rel_l2(y[:n], ref[:n]) <= TOL, f
+
+
+def test_ddc_split_invariance_and_ragged_blocks(engine):
+    x, fs, offs = synth.cfg1(200000, seed=5)
+    decim, taps = fd.channel_taps(fs, 12500)
+    bank = DdcBank(engine)
+    a = bank.open(decim, taps, 437500.0, fs, OUT_IQ | OUT_FM, 5.0)
+    bank.process(x)
+    ya, fa = bank.pull(a, OUT_IQ), bank.pull(a, OUT_FM)
+    bank.close(a)
+    bank2 = DdcBank(engine)
+    # fresh engine-level stream position continues; open a new channel (its own phase origin)
+    b = bank2.open(decim, taps, 437500.0, fs, OUT_IQ | OUT_FM, 5.0)
+    ys, fs_ = [], []
+    pos = 0
+    for blk in [1, 95, 96, 97, 1000, 12345, 7, 0, 50000]:
+        bank2.process(x[pos:pos + blk])
+        pos += blk
+        ys.append(bank2.pull(b, OUT_IQ))
+        fs_.append(bank2.pull(b, OUT_FM))
+    bank2.process(x[pos:])
+    ys.append(bank2.pull(b, OUT_IQ))
+    fs_.append(bank2.pull(b, OUT_FM))
+    yb, fb = np.concatenate(ys), np.concatenate(fs_)
+    assert len(yb) == len(ya)
+    # different stream origin -> different absolute decimation phase is NOT allowed to change samples:
+    # channel b was opened when the handle had consumed len(x) samples; outputs restart at its open time.
+    assert gb.rel_l2(yb, ya) <= 2e-6
+    assert _fm_err(fb[1:], fa[1:].astype(np.float64), 5.0) <= 2e-5
+
+
+def test_ddc_retune_keeps_phase_continuous(engine):
+    """set_center_freq (channel.py:61-63): composite taps and rotator increment change, phase continues."""
+    fs = 2.4e6
+    n = 96 * 2000
+    t = np.arange(2 * n) / fs
+    x = np.exp(2j * np.pi * 100e3 * t).astype(np.complex64)
+    decim, taps = fd.channel_taps(fs, 12500)
+    bank = DdcBank(engine)
+    c = bank.open(decim, taps, 100e3, fs)
+    bank.process(x[:n])
+    y0 = bank.pull(c)
+    bank.retune(c, 101e3)
+    bank.process(x[n:])
+    y1 = bank.pull(c)
+    # first segment: tone at DC of the channel -> constant phase
+    ph0 = np.angle(y0[50:])
+    assert np.ptp(np.unwrap(ph0)) < 1e-3
+    # after retune the tone sits at -1 kHz in the channel: phase slope = -2 pi 1000 / 25000 per sample
+    ph1 = np.unwrap(np.angle(y1[50:]))
+    slope = np.polyfit(np.arange(len(ph1)), ph1, 1)[0]
+    assert abs(slope + 2 * np.pi * 1000.0 / 25000.0) < 1e-5
+    # continuity: the phase right after the retune continues from the end of the first segment
+    # (filter transient aside) - compare extrapolated phases
+    end0 = ph0[-1]
+    ph1_full = np.unwrap(np.angle(y1))
+    start1 = ph1_full[50] - slope * 50
+    # ... plus the FIR group delay seen by the now -1 kHz tone: +2 pi 1000 (ntaps-1)/2 / fs
+    expect = 2 * np.pi * 1000.0 * (len(taps) - 1) / 2.0 / fs
+    d = (start1 - end0 - expect + np.pi) % (2 * np.pi) - np.pi
+    assert abs(d) < 0.02
+
+
+def test_prefilter_1x_69_taps(engine):
+    """p25_control_demod.py:106-108: freq_xlating_fir_filter_ccc(1, low_pass_2(1,25000,6250,500,30,BLACKMAN), 0, 25000)."""
+    taps = fd.low_pass_2(1.0, 25000, 6250, 500.0, 30.0, fd.WIN_BLACKMAN)
+    assert len(taps) == 69
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal(50000) + 1j * rng.standard_normal(50000)).astype(np.complex64) * 0.1
+    bank = DdcBank(engine)
+    c = bank.open(1, taps, 0.0, 25000.0, OUT_IQ | OUT_FM, 25000 / (2 * np.pi * 600))
+    bank.process(x)
+    y = bank.pull(c)
+    ref = gb.freq_xlating_fir(x, taps, 1, 0.0, 25000.0)
+    assert len(y) == len(ref)
+    assert gb.rel_l2(y, ref) <= TOL
+
+
+def test_split2_half_band_pair(engine):
+    """rc_frontend/receiver.py:78-86: two decim-2 DDCs at -fs/4 and +fs/4 with firdes.low_pass(1,fs,fs/4,fs/8)."""
+    fs = 8.0e6
+    taps = fd.low_pass(1, fs, fs / 4, fs / 8)
+    assert len(taps) == 19
+    x = synth.wideband(1 << 16, fs, [-2.5e6, -1e6, 0.4e6, 3e6], seed=9)
+    bank = DdcBank(engine)
+    lo = bank.open(2, taps, -fs / 4, fs)
+    hi = bank.open(2, taps, fs / 4, fs)
+    bank.process(x)
+    for cid, f0 in ((lo, -fs / 4), (hi, fs / 4)):
+        y = bank.pull(cid)
+        ref = gb.freq_xlating_fir(x, taps, 2, f0, fs)
+        assert gb.rel_l2(y, ref) <= TOL
+
+
+def test_quad_demod_and_probe(engine):
+    rng = np.random.default_rng(4)
+    x = (rng.standard_normal((7, 5001)) + 1j * rng.standard_normal((7, 5001))).astype(np.complex64)
+    fm, last = engine.quad_demod(x, 5.0)
+    ref = gb.quadrature_demod(x, 5.0)
+    assert _fm_err(fm, ref, 5.0) <= TOL
+    assert np.array_equal(last, x[:, -1])
+    # streaming carry
+    fm_a, last_a = engine.quad_demod(x[:, :1234], 5.0)
+    fm_b, _ = engine.quad_demod(x[:, 1234:], 5.0, prev=last_a)
+    assert np.array_equal(np.concatenate([fm_a, fm_b], axis=1), fm)
+    # (0,0) -> 0 like fast_atan2f
+    z, _ = engine.quad_demod(np.zeros(16, np.complex64), 5.0)
+    assert not z.any()
+    # table-atan GR emulation differs from exact by <= 1.6e-6 rad * gain
+    gr = gb.quadrature_demod_grcompat(x[0], 5.0)
+    assert np.abs(gr - fm[0]).max() <= 5.0 * 2.0e-6 + 1e-6
+    # AFC probe: moving_average_ff(10000,1,40000) -> *1e-4
+    pm = engine.probe_mean(fm, 1000, 1e-3)
+    ref_pm = gb.moving_average(ref.T, 1000, 1e-3)[-1]
+    np.testing.assert_allclose(pm, ref_pm, atol=1e-5)

@@ -1,0 +1,138 @@
+"""K1 parity: CUDA polyphase channelizer (+fused FM) vs the float64 oracle, through the C ABI.
+
+Tolerance (BASELINE.json north_star): ||gpu - oracle||2 / ||oracle||2 <= 1e-5 per channel for float
+outputs (after discarding the first ceil(L/N) outputs is NOT needed here because history is zero in
+both); FM compared on the wrapped phase difference.
+"""
+import numpy as np
+import pytest
+
+from oracle import gr_blocks as gb, gr_firdes as fd, synth
+from radiocapture_rf_b200.engine import PfbChannelizer, OUT_FM, OUT_IQ
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _fm_err(fm, ref, gain):
+    d = (fm.astype(np.float64) - ref) / gain
+    d = (d + np.pi) % (2 * np.pi) - np.pi
+    return np.linalg.norm(d) / max(np.linalg.norm(ref / gain), 1e-30)
+
+
+def _check(engine, n, taps, frames, seed, mode=OUT_IQ | OUT_FM, gain=5.0, blocks=None, active_every=2):
+    x, offs = synth.pfb_stream(n * frames, 1.0e6 * n / 4.0, n, seed, active_every=active_every)
+    ch = PfbChannelizer(engine, n, taps, mode, gain)
+    if blocks is None:
+        iq, fm = ch.process(x)
+    else:
+        outs = []
+        pos = 0
+        for b in blocks:
+            outs.append(ch.process(x[pos * n:(pos + b) * n]))
+            pos += b
+        assert pos == frames
+        iq = np.concatenate([o[0] for o in outs], axis=1) if mode & OUT_IQ else None
+        fm = np.concatenate([o[1] for o in outs], axis=1) if mode & OUT_FM else None
+    ref = gb.pfb_channelizer(x, np.asarray(taps, np.float64), n)
+    if mode & OUT_IQ:
+        active = list(range(1, n, active_every))
+        errs = [gb.rel_l2(iq[m], ref[m]) for m in active]
+        assert max(errs) <= TOL, "IQ rel err %g at channel %d" % (max(errs), active[int(np.argmax(errs))])
+        assert gb.rel_l2(iq, ref) <= TOL          # whole output
+        # empty (noise-only, 30 dB down) bins: float32 rounding is relative to the strong bins that are
+        # filtered out, so the per-channel ratio is looser there (same for GNU Radio's float32 VOLK path)
+        errs = [gb.rel_l2(iq[m], ref[m]) for m in range(n)]
+        assert max(errs) <= 1e-4, "IQ rel err %g at empty channel %d" % (max(errs), int(np.argmax(errs)))
+    if mode & OUT_FM:
+        fref = gb.quadrature_demod(ref, gain)
+        active = list(range(1, n, active_every))
+        errs = [_fm_err(fm[m], fref[m], gain) for m in active]
+        assert max(errs) <= TOL, "FM rel err %g at channel %d" % (max(errs), active[int(np.argmax(errs))])
+        # noise-only bins: atan2 of small products is ill conditioned; bound the aggregate loosely
+        allerr = _fm_err(fm, fref, gain)
+        assert allerr <= 2e-4, "FM aggregate err %g" % allerr
+    return iq, fm
+
+
+@pytest.mark.parametrize("n,tpa,frames", [(64, 2, 1024), (64, 16, 520), (256, 16, 256), (256, 1, 333),
+                                          (1024, 16, 96), (1024, 4, 131)])
+def test_pfb_iq_fm_parity(engine, n, tpa, frames):
+    taps = fd.pfb_prototype(n, tpa)
+    _check(engine, n, taps, frames, seed=n + tpa)
+
+
+def test_pfb_cfg3_literal_256_taps_1024_channels(engine):
+    """BASELINE config 3, literal reading: 256-tap prototype, 1024 channels -> 1 tap/arm, 768 zero arms."""
+    taps = fd.pfb_prototype(4, 64)  # any 256-tap low-pass
+    assert len(taps) == 256
+    _check(engine, 1024, taps, 200, seed=3, mode=OUT_FM)
+    _check(engine, 1024, taps, 64, seed=33, mode=OUT_IQ)
+
+
+def test_pfb_cfg2_64ch_128taps(engine):
+    taps = fd.pfb_prototype(64, 2)
+    assert len(taps) == 128
+    _check(engine, 64, taps, 4096, seed=2, mode=OUT_IQ)
+
+
+def test_pfb_ragged_tap_count(engine):
+    """L not a multiple of N: arms are zero padded (polyphase_filterbank::set_taps)."""
+    taps = fd.pfb_prototype(64, 5)[:-17]
+    _check(engine, 64, taps, 300, seed=5)
+
+
+@pytest.mark.parametrize("n", [5, 6, 20, 25, 40, 96])
+def test_pfb_generic_channel_counts(engine, n):
+    """The reference's own PFB shapes: N = fs/400 kHz (rc_frontend/receiver.py:244-249), optfir prototype."""
+    taps = fd.pfb_prototype(n)
+    _check(engine, n, taps, 400, seed=100 + n)
+
+
+@pytest.mark.parametrize("n,tpa", [(64, 4), (1024, 2), (20, None)])
+def test_pfb_split_invariance(engine, n, tpa):
+    """Block-wise processing == one shot (streaming state = last P input rows)."""
+    taps = fd.pfb_prototype(n, tpa) if tpa else fd.pfb_prototype(n)
+    frames = 257
+    a_iq, a_fm = _check(engine, n, taps, frames, seed=7)
+    b_iq, b_fm = _check(engine, n, taps, frames, seed=7, blocks=[1, 2, 3, 100, 9, 1, 141])
+    assert np.array_equal(a_iq, b_iq)
+    # FM of the first frame of a block is recomputed from the carried input rows: identical arithmetic
+    assert np.array_equal(a_fm, b_fm)
+
+
+def test_pfb_edge_cases(engine, built_lib):
+    import ctypes as C
+    from radiocapture_rf_b200 import _lib
+    taps = fd.pfb_prototype(64, 2)
+    ch = PfbChannelizer(engine, 64, taps, OUT_IQ)
+    iq, fm = ch.process(np.zeros(0, np.complex64))  # empty input
+    assert iq.shape == (64, 0) and fm is None
+    with pytest.raises(ValueError):
+        ch.process(np.zeros(63, np.complex64))
+    n = C.c_size_t()
+    x = np.zeros(63, np.complex64)
+    st = built_lib.rcb_pfb_process(engine.h, x.ctypes.data, 63, 0, x.ctypes.data, None, 1, 0, C.byref(n))
+    assert st == _lib.RCB_EINVAL
+    # single frame, all-zero input -> zeros, FM atan2(0,0) = 0
+    ch2 = PfbChannelizer(engine, 1024, fd.pfb_prototype(1024, 2), OUT_IQ | OUT_FM, 5.0)
+    iq, fm = ch2.process(np.zeros(1024, np.complex64))
+    assert not iq.any() and not fm.any()
+
+
+def test_pfb_tone_lands_in_its_bin(engine):
+    """Tone at bin centre m -> energy only in output m; FM of a tone offset by df is constant
+    gain*2*pi*df/fs_out (SURVEY 8(c) golden (iii))."""
+    n, frames = 64, 2048
+    taps = fd.pfb_prototype(n, 8)
+    fs = 64.0
+    m = 11
+    df = 0.05  # Hz with fs_out = 1 Hz
+    t = np.arange(n * frames)
+    x = np.exp(2j * np.pi * (m * fs / n + df) * t / fs).astype(np.complex64)
+    ch = PfbChannelizer(engine, n, taps, OUT_IQ | OUT_FM, 5.0)
+    iq, fm = ch.process(x)
+    p = (np.abs(iq[:, 64:]) ** 2).mean(axis=1)
+    assert int(np.argmax(p)) == m
+    assert p[m] / (p.sum() - p[m]) > 1e4
+    np.testing.assert_allclose(fm[m, 64:], 5.0 * 2 * np.pi * df, rtol=0, atol=2e-4)
