@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py - wideband IQ Msps channelised + FM-demodulated on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg3|cfg2|cfg5|cfg4]
+
+A "step" is one pass of the hot path over one batch of synthetic wideband IQ.  Default workload =
+BASELINE config 3 (the one the 70 %-of-HBM-roofline target is quoted on): ONE 1024-channel polyphase
+channelizer with a 256-tap prototype (GNU Radio API reading: pfb.channelizer_ccf(1024, taps[256])) and
+the fused quadrature FM demod, 2^28 complex64 samples per step resident in HBM (2 GiB in, 1 GiB FM out
+=> inputs far larger than the 126 MB L2, no flush needed).  Reported on one JSON line:
+  value      whole-job Msps-in with inputs resident in HBM (device timed, CUDA events, max over ranks)
+  e2e        same metric through the C ABI with pinned HOST buffers (H2D + kernel + D2H pipelined inside)
+  roofline   algorithmic bytes (12 B/sample: 8 read + 4 FM written) / kernel time vs measured HBM peak
+  cpu_baseline  the GR-semantics C restatement (oracle/gr_cpu.c, kind "port") on a bounded sample
+  also       the same kernel at 16 taps/arm (reference-like prototype) for context
+N > 1: one process per GPU (torchrun), independent streams per rank, no data-path collective ("weak").
+`--impl reference` times the CPU restatement only (GNU Radio itself is not installable here).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "wideband_iq_msps_channelized_demodulated"
+
+WORKLOADS = {
+    # name: nchans, ntaps, out (fm/iq), log2 samples per step per stream, streams per GPU, fs label
+    "cfg3": dict(nchans=1024, ntaps=256, out="fm", log2n=28, streams=1,
+                 desc="cfg3: 1024-channel PFB, 256-tap prototype, fused FM demod, one 200 Msps stream"),
+    "cfg3_p16": dict(nchans=1024, ntaps=16384, out="fm", log2n=28, streams=1,
+                     desc="cfg3 variant: 1024-channel PFB, 16 taps/arm (16384-tap prototype), fused FM demod"),
+    "cfg2": dict(nchans=64, ntaps=128, out="iq", log2n=27, streams=1,
+                 desc="cfg2: 64-channel PFB, 128-tap prototype, IQ out, one 25 Msps stream"),
+    "cfg5": dict(nchans=256, ntaps=4096, out="fm", log2n=25, streams=8,
+                 desc="cfg5: 8 independent 100 Msps streams per GPU x 256 channels, 16 taps/arm, fused FM demod"),
+}
+
+
+def load_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic(workload):
+    """dram bytes per input sample from the committed ncu --set full capture (profiles/traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return float(json.load(open(p))[workload]["dram_bytes_per_sample"])
+    except Exception:
+        return None
+
+
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self):
+        if self.proc is None:
+            return
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+
+    def summary(self, t0, t1):
+        sm, smax, reasons = [], 0.0, set()
+        for ts, ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk, mx = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            smax = max(smax, mx)
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(clk)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # region shorter than the sampling period: take everything we saw
+            for ts, ln in self.lines:
+                f = [x.strip() for x in ln.split(",")]
+                try:
+                    sm.append(float(f[1]))
+                except Exception:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_taps(nchans, ntaps):
+    """Blackman-Harris windowed-sinc prototype of exactly `ntaps` taps, cutoff half a bin."""
+    n = np.arange(ntaps, dtype=np.float64) - (ntaps - 1) / 2.0
+    fc = 0.5 / nchans
+    h = 2 * fc * np.sinc(2 * fc * n)
+    k = np.arange(ntaps, dtype=np.float64)
+    m = max(ntaps - 1, 1)
+    w = 0.35875 - 0.48829 * np.cos(2 * np.pi * k / m) + 0.14128 * np.cos(4 * np.pi * k / m) - 0.01168 * np.cos(6 * np.pi * k / m)
+    h = h * w
+    return (h / h.sum()).astype(np.float32)
+
+
+def synth_block(n, nchans, seed):
+    """Seeded synthetic IQ: tones in 1/4 of the bins + AWGN, RMS 0.25 (arithmetic cost is data independent)."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal(2 * n, dtype=np.float32).view(np.complex64) * np.float32(0.02)
+    t = np.arange(n, dtype=np.float64)
+    for b in rng.choice(nchans, size=min(16, nchans // 4), replace=False):
+        f = (b + rng.uniform(-0.1, 0.1)) / nchans
+        x += (0.05 * np.exp(2j * np.pi * f * t)).astype(np.complex64)
+    x *= np.float32(0.25 / np.sqrt(np.mean(np.abs(x) ** 2)))
+    return x
+
+
+def dist_setup(ngpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    return world, rank, local, dist
+
+
+def barrier(dist, local):
+    if dist is not None:
+        import torch
+        dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+
+def allreduce_max(dist, local, v):
+    if dist is None:
+        return v
+    import torch
+    t = torch.tensor([v], dtype=torch.float64, device="cuda:%d" % local)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# -------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: GR-semantics C restatement on the host cores
+# -------------------------------------------------------------------------------------------------
+def cpu_run(wl, steps, warmup, log2n_cpu=None, budget_s=None):
+    from oracle import gr_cpu
+    cfg = WORKLOADS[wl]
+    nch, ntaps = cfg["nchans"], cfg["ntaps"]
+    taps = make_taps(nch, ntaps)
+    log2n = log2n_cpu or 22
+    n = 1 << log2n
+    x = synth_block(n, nch, 3)
+    want_fm = cfg["out"] == "fm"
+    threads = gr_cpu.num_threads()
+    hist = None
+    for _ in range(max(warmup, 1)):
+        _, _, hist = gr_cpu.pfb_fm(x, nch, taps, 5.0, want_iq=not want_fm, want_fm=want_fm, hist=hist)
+    t0 = time.perf_counter()
+    done = 0
+    for s in range(steps):
+        _, _, hist = gr_cpu.pfb_fm(x, nch, taps, 5.0, want_iq=not want_fm, want_fm=want_fm, hist=hist)
+        done += 1
+        if budget_s and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    msps = done * n / dt / 1e6
+    return msps, threads, done, n, dt
+
+
+def run_reference(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cfg = WORKLOADS[args.workload]
+    msps, threads, done, n, dt = cpu_run(args.workload, args.steps, args.warmup)
+    sample = "%d steps x 2^%d samples of the %s stream (oracle/gr_cpu.c, OpenMP over frames)" % (
+        done, int(np.log2(n)), args.workload)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": msps, "unit": "Msps", "n_gpus": args.gpus,
+        "steps": done, "warmup": args.warmup, "ms_per_step": dt / max(done, 1) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["desc"], "nchans": cfg["nchans"], "ntaps": cfg["ntaps"], "out": cfg["out"],
+                   "note": "GNU Radio 3.8 is not installable here; GR-semantics C restatement of its blocks"},
+        "cpu_baseline": {"value": msps, "unit": "Msps", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": msps, "unit": "Msps", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# -------------------------------------------------------------------------------------------------
+# B200 arm
+# -------------------------------------------------------------------------------------------------
+class StreamCtx(object):
+    """One wideband stream resident on the GPU: engine + channelizer + device buffers."""
+
+    def __init__(self, device, wl, seed, log2n=None, ntaps=None):
+        from radiocapture_rf_b200.engine import Engine, PfbChannelizer, OUT_FM, OUT_IQ
+        cfg = WORKLOADS[wl]
+        self.cfg = cfg
+        self.nch = cfg["nchans"]
+        self.ntaps = ntaps or cfg["ntaps"]
+        self.n = 1 << (log2n or cfg["log2n"])
+        self.frames = self.n // self.nch
+        self.fm = cfg["out"] == "fm"
+        self.e = Engine(device)
+        self.ch = PfbChannelizer(self.e, self.nch, make_taps(self.nch, self.ntaps), OUT_FM if self.fm else OUT_IQ, 5.0)
+        base_n = min(self.n, 1 << 24)
+        base = synth_block(base_n, self.nch, seed)
+        self.d_in = self.e.dev_alloc(self.n * 8)
+        check_copy = self.e.lib.rcb_memcpy
+        from radiocapture_rf_b200._lib import COPY_H2D, check
+        check(check_copy(self.e.h, self.d_in.ptr, base.ctypes.data, base.nbytes, COPY_H2D), "h2d", self.e.h)
+        filled = base_n
+        while filled < self.n:  # replicate on device
+            c = min(filled, self.n - filled)
+            self.e.copy_d2d(self.d_in.ptr + filled * 8, self.d_in.ptr, c * 8)
+            filled += c
+        self.base = base
+        self.d_out = self.e.dev_alloc(self.n * (4 if self.fm else 8))
+        self.bytes_per_sample = 8 + (4 if self.fm else 8)
+
+    def step(self):
+        if self.fm:
+            self.ch.process_device(self.d_in, self.n, None, self.d_out, self.frames)
+        else:
+            self.ch.process_device(self.d_in, self.n, self.d_out, None, self.frames)
+
+    def close(self):
+        self.e.close()
+
+
+def timed_loop(ctxs, steps, warmup, dist, local):
+    for _ in range(warmup):
+        for c in ctxs:
+            c.step()
+    for c in ctxs:
+        c.e.sync()
+    barrier(dist, local)
+    l0 = sum(c.e.stats()["kernel_launches"] for c in ctxs)
+    for c in ctxs:
+        c.e.timer_start()
+    t0 = time.time()
+    for _ in range(steps):
+        for c in ctxs:
+            c.step()
+    ms = max(c.e.timer_stop() for c in ctxs)   # events on each stream's own CUDA stream; streams run concurrently
+    t1 = time.time()
+    for c in ctxs:
+        c.e.sync()
+    barrier(dist, local)
+    launches = sum(c.e.stats()["kernel_launches"] for c in ctxs) - l0
+    return ms, launches, t0, t1
+
+
+def run_e2e(device, wl, steps, warmup, dist, local, log2n=26):
+    """Same metric through the public host-buffer call: pinned host in -> H2D -> kernel -> D2H -> pinned host out."""
+    from radiocapture_rf_b200.engine import Engine, PfbChannelizer, OUT_FM, OUT_IQ
+    cfg = WORKLOADS[wl]
+    nch = cfg["nchans"]
+    fm = cfg["out"] == "fm"
+    n = 1 << log2n
+    frames = n // nch
+    e = Engine(device)
+    ch = PfbChannelizer(e, nch, make_taps(nch, cfg["ntaps"]), OUT_FM if fm else OUT_IQ, 5.0)
+    hin = e.pinned((n,), np.complex64)
+    base = synth_block(min(n, 1 << 22), nch, 5)
+    for i in range(0, n, len(base)):
+        hin[i:i + len(base)] = base[:min(len(base), n - i)]
+    hout = e.pinned((nch, frames), np.float32 if fm else np.complex64)
+    for _ in range(warmup):
+        ch.process(hin, out_iq=None if fm else hout, out_fm=hout if fm else None)
+    barrier(dist, local)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ch.process(hin, out_iq=None if fm else hout, out_fm=hout if fm else None)   # returns after the D2H completed
+    dt = time.perf_counter() - t0
+    barrier(dist, local)
+    chk = float(np.abs(hout[:, -8:]).sum())   # the result is really on the host
+    e.close()
+    return n * steps / dt / 1e6, n * 8, hout.nbytes, chk
+
+
+def run_b200(args):
+    world, rank, local, dist = dist_setup(args.gpus)
+    device = local if world > 1 else 0
+    wl = args.workload
+    cfg = WORKLOADS[wl]
+    peak, peak_src = load_peak()
+
+    ctxs = [StreamCtx(device, wl, seed=3 + 100 * rank + i, log2n=args.log2n) for i in range(cfg["streams"])]
+    sampler = ClockSampler(device)
+    sampler.start()
+    time.sleep(0.3)
+    ms, launches, t0, t1 = timed_loop(ctxs, args.steps, args.warmup, dist, local)
+    sampler.stop()
+    clocks = sampler.summary(t0, t1)
+    ms = allreduce_max(dist, local, ms)
+    samples_rank = sum(c.n for c in ctxs) * args.steps
+    total = samples_rank * world
+    msps = total / (ms * 1e-3) / 1e6
+    bps = ctxs[0].bytes_per_sample
+    # dominant kernel = pfb_fm_kernel: one launch per stream per step (the other launch is a ~2 us history copy)
+    n_launch_samples = ctxs[0].n
+    kern_ms = ms / args.steps if cfg["streams"] == 1 else None
+    achieved = (samples_rank * bps) / (ms * 1e-3) / 1e9
+    tr = load_traffic(wl)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": (tr * n_launch_samples) if tr else None, "peak_source": peak_src,
+                "kernel": "pfb_fm_kernel", "algorithmic_bytes_per_launch": n_launch_samples * bps,
+                "kernel_ms_per_launch": kern_ms}
+    for c in ctxs:
+        c.close()
+
+    also = None
+    if wl == "cfg3" and not args.no_also:
+        c16 = StreamCtx(device, "cfg3_p16", seed=3, log2n=args.log2n)
+        ms16, _, _, _ = timed_loop([c16], max(3, args.steps // 2), 2, dist, local)
+        ms16 = allreduce_max(dist, local, ms16)
+        st16 = max(3, args.steps // 2)
+        a16 = c16.n * st16 * 12 / (ms16 * 1e-3) / 1e9
+        also = {"workload": WORKLOADS["cfg3_p16"]["desc"], "value": c16.n * st16 * world / (ms16 * 1e-3) / 1e6,
+                "unit": "Msps", "roofline_frac": a16 / peak}
+        c16.close()
+
+    e2e_v, h2d, d2h, chk = run_e2e(device, wl, args.e2e_steps, 1, dist, local)
+    e2e_v = e2e_v * world if dist is None else allreduce_sum_min(dist, local, e2e_v, world)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cm, threads, done, n, dt = cpu_run(wl, 64, 1, budget_s=12.0)
+        cpu = {"value": cm, "unit": "Msps", "cores": threads, "kind": "port",
+               "sample": "%d x 2^%d samples of the same workload (oracle/gr_cpu.c, %.1f s)" % (done, int(np.log2(n)), dt)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": msps, "unit": "Msps", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["desc"], "nchans": cfg["nchans"], "ntaps": cfg["ntaps"], "out": cfg["out"],
+                       "samples_per_step_per_gpu": sum(c.n for c in ctxs), "streams_per_gpu": cfg["streams"],
+                       "channels_out": cfg["nchans"] * cfg["streams"] * world,
+                       "l2": "inputs (%d MiB/step) larger than L2, no flush" % (sum(c.n for c in ctxs) * 8 >> 20),
+                       "parallelism": "independent streams, %d GPU(s), no collective" % world},
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_v, "unit": "Msps", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "rcb_pfb_process(host pinned in, host pinned out)", "checksum": chk},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "also": also,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def allreduce_sum_min(dist, local, v, world):
+    """whole-job e2e = world * min over ranks (ranks run concurrently, each bounded by its own PCIe link)."""
+    import torch
+    t = torch.tensor([v], dtype=torch.float64, device="cuda:%d" % local)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return float(t.item()) * world
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--log2n", type=int, default=None, help="override samples per step per stream (log2)")
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-also", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -196,7 +196,16 @@ class DdcBank(object):
     def __init__(self, engine):
         self.e = engine
 
-    def open(self, decim, taps, center_freq, samp_rate, out_mask=OUT_IQ, fm_gain=1.0):
+    @staticmethod
+    def gr_float_omega(center_freq, samp_rate):
+        """GNU Radio 3.8 holds w = 2*pi*f0/fs in a C float (freq_xlating_fir_filter_impl.cc): return the
+        frequency whose exact w equals that float32 value, for bit-level studies against GNU Radio."""
+        w = float(np.float32(2.0 * np.pi * float(center_freq) / float(samp_rate)))
+        return w * float(samp_rate) / (2.0 * np.pi)
+
+    def open(self, decim, taps, center_freq, samp_rate, out_mask=OUT_IQ, fm_gain=1.0, gr_float_omega=False):
+        if gr_float_omega:
+            center_freq = self.gr_float_omega(center_freq, samp_rate)
         taps = np.ascontiguousarray(taps, dtype=np.float32)
         cid = C.c_int(0)
         check(self.e.lib.rcb_ddc_open(self.e.h, int(decim), taps.ctypes.data, len(taps), float(center_freq),

@@ -179,3 +179,16 @@ def test_quad_demod_and_probe(engine):
     pm = engine.probe_mean(fm, 1000, 1e-3)
     ref_pm = gb.moving_average(ref.T, 1000, 1e-3)[-1]
     np.testing.assert_allclose(pm, ref_pm, atol=1e-5)
+
+
+def test_gr_float_omega_mode_matches_gnuradio_emulation(engine):
+    """With w rounded to float32 like GNU Radio, the GPU (exact phase) matches a float32 emulation of the
+    GNU Radio block (complex64 taps, recursive rotator renormalised every 512) to 1e-5."""
+    x, fs, _ = synth.cfg1(96 * 1200, seed=1)
+    decim, taps = fd.channel_taps(fs, 12500)
+    bank = DdcBank(engine)
+    c = bank.open(decim, taps, -62500.0, fs, gr_float_omega=True)
+    bank.process(x)
+    y = bank.pull(c)
+    gr = gb.freq_xlating_fir_grcompat(x, taps, decim, -62500.0, fs)
+    assert gb.rel_l2(y[:len(gr)], gr) <= TOL

@@ -104,10 +104,15 @@ def test_quadrature_demod_zero_and_table_atan():
 def test_grcompat_rotator_drift_is_what_survey_says():
     x, fs, _ = synth.cfg1(96 * 1200, seed=1)
     decim, taps = fd.channel_taps(fs, 12500)
-    exact = gb.freq_xlating_fir(x, taps, decim, -62500.0, fs, omega_f32=True)
+    e32 = gb.freq_xlating_fir(x, taps, decim, -62500.0, fs, omega_f32=True)
+    e64 = gb.freq_xlating_fir(x, taps, decim, -62500.0, fs)
     gr = gb.freq_xlating_fir_grcompat(x, taps, decim, -62500.0, fs)
-    # float32 recursive rotator drifts ~1e-7..1e-6 rad per output (SURVEY 7 "hard parts"): not 1e-5-exact
-    assert 1e-6 < gb.rel_l2(gr, exact) < 5e-3
+    # GNU Radio's float32 recursive rotator + float32 dot products stay within 1e-5 of exact arithmetic
+    # done with the SAME float32-rounded w ...
+    assert gb.rel_l2(gr, e32) < 1e-5
+    # ... but holding w in a C float is itself a ~2e-4 departure from ideal math after 1200 outputs
+    # (48 ms): GNU Radio is not 1e-5-exact against float64 ideal, hence the gr_float_omega option.
+    assert 1e-5 < gb.rel_l2(e64, e32) < 5e-3
 
 
 def test_moving_average_forms_agree():
