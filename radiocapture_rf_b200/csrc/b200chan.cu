@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -17,6 +18,7 @@
 #include "demod.cuh"
 #include "fft_logpow.cuh"
 #include "pfb_fm.cuh"
+#include "pfb_fm_tma.cuh"
 
 using namespace rcb;
 
@@ -73,13 +75,18 @@ struct rcb_ctx {
         float gain = 1.f;
         float* d_taps = nullptr;
         float2* d_tw = nullptr;
+        float2* d_tw_tma = nullptr;  // dense swizzled table for pfb_fm_tma_kernel
+        bool use_tma = false;
         float2* d_hist[2] = {nullptr, nullptr};
         int hist_cur = 0;
+        float2* d_zeros = nullptr;  // one all-zero row
+        int* d_counter = nullptr;   // dynamic work counter of the TMA kernel
         float2* d_ys = nullptr;  // generic path scratch [N][T+1]
         size_t ys_cap = 0;
         int blocks_per_sm = 0;
         size_t smem = 0;
         bool taps_smem = true;
+        int variant = 0;  // RCB_PFB_VARIANT (tuning experiments)
         Stage st[kStages];
         size_t chunk_frames = 0;
     } pfb;
@@ -155,10 +162,10 @@ double frac_mul(double cyc, uint64_t k) {
 // ------------------------------------------------------------------------------------------------
 // PFB kernel dispatch
 // ------------------------------------------------------------------------------------------------
-template <int R, int MODE, bool TS, int PT>
+template <int R, int MODE, bool TS, int PT, int PF = 0>
 int pfb_launch_t(rcb_t* h, const PfbParams& p, bool query_only) {
     using G = PfbGeom<R>;
-    auto kern = pfb_fm_kernel<R, MODE, TS, PT>;
+    auto kern = pfb_fm_kernel<R, MODE, TS, PT, PF>;
     const size_t smem = G::smem_bytes(p.P, TS);
     if (query_only) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -176,7 +183,10 @@ int pfb_launch_t(rcb_t* h, const PfbParams& p, bool query_only) {
 }
 template <int R, int MODE>
 int pfb_launch_rm(rcb_t* h, const PfbParams& p, bool q) {
-    if (p.P == 1) return pfb_launch_t<R, MODE, true, 1>(h, p, q);
+    if (p.P == 1) {
+        if (h->pfb.variant == 1 && R == 32 && MODE == PFB_OUT_FM) return pfb_launch_t<R, MODE, true, 1, 1>(h, p, q);
+        return pfb_launch_t<R, MODE, true, 1>(h, p, q);
+    }
     if (h->pfb.taps_smem) return pfb_launch_t<R, MODE, true, 0>(h, p, q);
     return pfb_launch_t<R, MODE, false, 0>(h, p, q);
 }
@@ -188,7 +198,38 @@ int pfb_launch_r(rcb_t* h, const PfbParams& p, bool q) {
         default: return pfb_launch_rm<R, PFB_OUT_IQ | PFB_OUT_FM>(h, p, q);
     }
 }
+template <int R>
+int pfb_launch_tma(rcb_t* h, const PfbParams& p, bool query_only) {
+    using G = PfbTmaGeom<R>;
+    auto kern = pfb_fm_tma_kernel<R>;
+    const size_t smem = G::smem_bytes;
+    if (query_only) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, G::THREADS, smem));
+        h->pfb.blocks_per_sm = std::max(nb, 1);
+        h->pfb.smem = smem;
+        return RCB_OK;
+    }
+    const int NI = (p.T + G::FPI - 1) / G::FPI;
+    const int grid = std::max(1, std::min(NI, h->pfb.blocks_per_sm * h->sm_count));
+    PfbParams q = p;
+    q.twiddle = h->pfb.d_tw_tma;
+    q.work_counter = h->pfb.d_counter;
+    CK(cudaMemsetAsync(h->pfb.d_counter, 0, sizeof(int), h->stream));
+    kern<<<grid, G::THREADS, smem, h->stream>>>(q);
+    CKL(h);
+    return RCB_OK;
+}
+
 int pfb_launch_fast(rcb_t* h, const PfbParams& p, bool q) {
+    if (h->pfb.use_tma) {
+        switch (h->pfb.R) {
+            case 8: return pfb_launch_tma<8>(h, p, q);
+            case 16: return pfb_launch_tma<16>(h, p, q);
+            case 32: return pfb_launch_tma<32>(h, p, q);
+        }
+    }
     switch (h->pfb.R) {
         case 8: return pfb_launch_r<8>(h, p, q);
         case 16: return pfb_launch_r<16>(h, p, q);
@@ -201,9 +242,15 @@ void pfb_free(rcb_t* h) {
     auto& s = h->pfb;
     cudaFree(s.d_taps);
     cudaFree(s.d_tw);
+    cudaFree(s.d_tw_tma);
+    s.d_tw_tma = nullptr;
     cudaFree(s.d_hist[0]);
     cudaFree(s.d_hist[1]);
     cudaFree(s.d_ys);
+    cudaFree(s.d_zeros);
+    s.d_zeros = nullptr;
+    cudaFree(s.d_counter);
+    s.d_counter = nullptr;
     for (auto& st : s.st) {
         cudaFree(st.d_in);
         cudaFree(st.d_fm);
@@ -231,6 +278,7 @@ int pfb_run_device(rcb_t* h, const float2* d_x, size_t frames, float2* d_iq, flo
     p.hist = s.d_hist[s.hist_cur];
     p.taps = s.d_taps;
     p.twiddle = s.d_tw;
+    p.zeros = s.d_zeros;
     p.out_fm = (s.mode & RCB_OUT_FM) ? d_fm : nullptr;
     p.out_iq = (s.mode & RCB_OUT_IQ) ? d_iq : nullptr;
     p.ostride = (long long)ostride;
@@ -507,6 +555,10 @@ extern "C" int rcb_pfb_config(rcb_t* h, int nchans, const float* taps, int ntaps
     s.mode = out_mask;
     s.gain = fm_gain;
     s.R = (nchans == 64) ? 8 : (nchans == 256) ? 16 : (nchans == 1024) ? 32 : 0;
+    {
+        const char* v = getenv("RCB_PFB_VARIANT");
+        s.variant = v ? atoi(v) : 0;
+    }
     const int N = s.N, P = s.P, R = s.R;
     std::vector<float> hp((size_t)P * N, 0.f);
     for (int i = 0; i < ntaps; ++i) hp[i] = taps[i];
@@ -516,7 +568,8 @@ extern "C" int rcb_pfb_config(rcb_t* h, int nchans, const float* taps, int ntaps
         for (int k = 0; k < P; ++k)
             for (int jj = 0; jj < R; ++jj)
                 for (int ll = 0; ll < R; ++ll)
-                    tperm[((size_t)k * R + jj) * R + ll] = hp[(size_t)R * (R - 1 - jj) + (R - 1 - ll) + (size_t)k * N];
+                    tperm[(((size_t)k * (R / 4) + jj / 4) * R + ll) * 4 + (jj % 4)] =
+                        hp[(size_t)R * (R - 1 - jj) + (R - 1 - ll) + (size_t)k * N];
         const int S = R + 2;
         tw.assign((size_t)R * S, make_float2(0.f, 0.f));
         for (int ll = 0; ll < R; ++ll)
@@ -526,6 +579,21 @@ extern "C" int rcb_pfb_config(rcb_t* h, int nchans, const float* taps, int ntaps
                 tw[(size_t)ll * S + m1] = make_float2((float)cos(a), (float)sin(a));
             }
         s.taps_smem = ((size_t)P * N * sizeof(float) <= 16384);
+        // FM-only, one tap per arm: the TMA-staged kernel (RCB_PFB_VARIANT=9 keeps the register-prefetch one)
+        s.use_tma = (P == 1 && out_mask == RCB_OUT_FM && s.variant != 9);
+        if (s.use_tma) {
+            std::vector<float2> tt((size_t)N);
+            for (int ll = 0; ll < R; ++ll) {
+                const int sw = (R == 8) ? ((ll >> 1) & 3) : (ll & (R / 2 - 1));
+                for (int m1 = 0; m1 < R; ++m1) {
+                    const int q = ((R - 1 - ll) * m1) % N;
+                    const double a = 2.0 * M_PI * (double)q / (double)N;
+                    tt[(size_t)ll * R + ((((m1 >> 1) ^ sw) << 1) | (m1 & 1))] = make_float2((float)cos(a), (float)sin(a));
+                }
+            }
+            CK(cudaMalloc(&s.d_tw_tma, tt.size() * sizeof(float2)));
+            CK(cudaMemcpy(s.d_tw_tma, tt.data(), tt.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        }
     } else {
         tperm = hp;
         tw.resize(N);
@@ -544,6 +612,9 @@ extern "C" int rcb_pfb_config(rcb_t* h, int nchans, const float* taps, int ntaps
         CK(cudaMemsetAsync(s.d_hist[b], 0, (size_t)P * N * sizeof(float2), h->stream));
     }
     s.hist_cur = 0;
+    CK(cudaMalloc(&s.d_counter, sizeof(int)));
+    CK(cudaMalloc(&s.d_zeros, (size_t)N * sizeof(float2)));
+    CK(cudaMemsetAsync(s.d_zeros, 0, (size_t)N * sizeof(float2), h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (R) {
         PfbParams p{};

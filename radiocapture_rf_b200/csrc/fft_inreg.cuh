@@ -135,11 +135,11 @@ namespace rcb {
 //   buf: this frame's private R*(R+2) complex scratch (row stride R+2 => STS.128 / LDS.64 conflict free)
 //   tws: shared twiddle table tws[ll*(R+2) + m1] = W_N^{SIGN * l * m1}
 // Only __syncwarp() is used; buf may be reused by the warp as soon as the call returns.
+// second half: twiddle, transpose through buf, second radix-R pass (first pass already done in v)
 template <int R, int SIGN, bool REV>
-__device__ __forceinline__ void warp_fft_2pass(float2 (&v)[R], float2* __restrict__ buf,
-                                               const float2* __restrict__ tws, const int ll) {
+__device__ __forceinline__ void warp_fft_xpose_pass2(float2 (&v)[R], float2* __restrict__ buf,
+                                                     const float2* __restrict__ tws, const int ll) {
     constexpr int S = R + 2;
-    fft_inreg<R, SIGN>(v);  // v[m1] = sum_j u[R j + l] W_R^{j m1}
     {
         const float4* twp = reinterpret_cast<const float4*>(tws + ll * S);
         float4* bp = reinterpret_cast<float4*>(buf + ll * S);
@@ -157,6 +157,13 @@ __device__ __forceinline__ void warp_fft_2pass(float2 (&v)[R], float2* __restric
     for (int l2 = 0; l2 < R; ++l2) v[REV ? (R - 1 - l2) : l2] = buf[l2 * S + ll];
     fft_inreg<R, SIGN>(v);  // v[m2] = X[ll + R*m2]
     __syncwarp();
+}
+
+template <int R, int SIGN, bool REV>
+__device__ __forceinline__ void warp_fft_2pass(float2 (&v)[R], float2* __restrict__ buf,
+                                               const float2* __restrict__ tws, const int ll) {
+    fft_inreg<R, SIGN>(v);  // v[m1] = sum_j u[R j + l] W_R^{j m1}
+    warp_fft_xpose_pass2<R, SIGN, REV>(v, buf, tws, ll);
 }
 
 }  // namespace rcb

@@ -37,8 +37,10 @@ enum { PFB_OUT_IQ = 1, PFB_OUT_FM = 2 };
 struct PfbParams {
     const float2* x;        // T*N new samples (row n = frame n)
     const float2* hist;     // P*N samples preceding x (rows -P .. -1)
-    const float* taps;      // permuted: taps[(k*R + jj)*R + ll] = h[R*(R-1-jj) + (R-1-ll) + k*N]  (fast path)
-                            // generic path: taps[k*N + i] = h[i + k*N]
+    const float* taps;      // fast path, float4 groups: taps[((k*(R/4) + jj/4)*R + ll)*4 + jj%4] =
+                            //   h[R*(R-1-jj) + (R-1-ll) + k*N];  generic path: taps[k*N + i] = h[i + k*N]
+    const float2* zeros;    // N complex zeros (rows outside the stream)
+    int* work_counter;      // zeroed before each launch: dynamic tail-chunk counter (pfb_fm_tma_kernel)
     const float2* twiddle;  // fast: [R][R+2]: tw[ll*(R+2) + m1] = W_N^{+(R-1-ll) m1};  generic: [N] W_N^{+q}
     float* out_fm;          // [N][ostride] floats (or null)
     float2* out_iq;         // [N][ostride] complex (or null)
@@ -62,25 +64,70 @@ struct PfbGeom {
     static constexpr size_t ring_bytes = (size_t)NSLOT * FS * sizeof(float2);
     static constexpr size_t tw_bytes = (size_t)R * S * sizeof(float2);
     static size_t smem_bytes(int P, bool taps_smem) {
-        return ring_bytes + tw_bytes + (taps_smem ? (size_t)P * N * sizeof(float) : 0);
+        return ring_bytes + tw_bytes + 16 /* mbarrier */ + (taps_smem ? (size_t)P * N * sizeof(float) : 0);
     }
 };
 
 template <int R>
 __device__ __forceinline__ const float2* pfb_row_ptr(const PfbParams& p, long long r) {
+    // rows outside [-P, T) read an all-zero row (p.zeros) so the loads stay unconditional
     constexpr int N = R * R;
-    if (r >= 0) return (r < p.T) ? p.x + r * N : nullptr;
-    return (r >= -(long long)p.P) ? p.hist + (r + p.P) * N : nullptr;
+    if (r >= 0) return (r < p.T) ? p.x + r * N : p.zeros;
+    return (r >= -(long long)p.P) ? p.hist + (r + p.P) * N : p.zeros;
 }
 
-template <int R, int MODE, bool TAPS_SMEM, int PT /* compile-time P, 0 = runtime */>
+// ---- mbarrier (arrive early / wait late) used to overlap the next frame's FIR + first FFT pass with the
+// ---- tail of the other warps' demod phase -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 t;\n\tmbarrier.arrive.shared::cta.b64 t, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// atan2 variant for the phase ring: (0,0) -> NaN (0/0), which the demod turns into the reference's 0
+__device__ __forceinline__ float atan2_nan(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float z = __fdividef(mn, mx);
+    const float s = z * z;
+    float r = -0.004370174370706081f;
+    r = fmaf(r, s, 0.023092154413461685f);
+    r = fmaf(r, s, -0.05784549191594124f);
+    r = fmaf(r, s, 0.0979914739727974f);
+    r = fmaf(r, s, -0.13978290557861328f);
+    r = fmaf(r, s, 0.1996297985315323f);
+    r = fmaf(r, s, -0.33331674337387085f);
+    r = r * s;
+    r = fmaf(r, z, z);
+    r = (ay > ax) ? (1.57079632679489661923f - r) : r;
+    r = (x < 0.0f) ? (3.14159265358979323846f - r) : r;
+    return copysignf(r, y);
+}
+
+template <int R, int MODE, bool TAPS_SMEM, int PT /* compile-time P, 0 = runtime */, int PF = 0 /* 0: register prefetch, 1: L2 prefetch */>
 __global__ void __launch_bounds__(256, 2) pfb_fm_kernel(const PfbParams p) {
     using G = PfbGeom<R>;
     constexpr int N = G::N, F = G::F, FPI = G::FPI, S = G::S, FS = G::FS, NSLOT = G::NSLOT;
+    constexpr bool PHI = (MODE == PFB_OUT_FM);  // FM only: the ring holds angle(Y) (4 B) instead of Y (8 B)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* ring = reinterpret_cast<float2*>(smem_raw);
     float2* tws = ring + NSLOT * FS;
-    float* taps_s = reinterpret_cast<float*>(tws + R * S);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tws + R * S);
+    float* taps_s = reinterpret_cast<float*>(bar + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane / R, ll = lane % R;
@@ -89,8 +136,9 @@ __global__ void __launch_bounds__(256, 2) pfb_fm_kernel(const PfbParams p) {
     for (int i = tid; i < R * S; i += G::THREADS) tws[i] = p.twiddle[i];
     if (TAPS_SMEM)
         for (int i = tid; i < P * N; i += G::THREADS) taps_s[i] = p.taps[i];
+    if (tid == 0) mbar_init(bar, G::THREADS);
     __syncthreads();
-    const float* tap_base = TAPS_SMEM ? taps_s : p.taps;
+    const float4* tap4 = reinterpret_cast<const float4*>(TAPS_SMEM ? taps_s : p.taps);
 
     // contiguous run of iterations for this CTA
     const int NI = (p.T + FPI - 1) / FPI;
@@ -103,102 +151,193 @@ __global__ void __launch_bounds__(256, 2) pfb_fm_kernel(const PfbParams p) {
     float2 xr[R];
     long long frame = (long long)(it0 - 1) * FPI + warp * F + fr;
     {
-        const float2* rp = pfb_row_ptr<R>(p, frame);
+        const float2* rp = pfb_row_ptr<R>(p, frame) + ll;
 #pragma unroll
-        for (int jj = 0; jj < R; ++jj)
-            xr[jj] = rp ? (PT == 1 ? ld_stream_f2(rp + jj * R + ll) : __ldg(rp + jj * R + ll)) : make_float2(0.f, 0.f);
+        for (int jj = 0; jj < R; ++jj) xr[jj] = (PT == 1) ? ld_stream_f2(rp + jj * R) : __ldg(rp + jj * R);
     }
 
-    int c = 0;
-    for (int it = it0 - 1; it < it1; ++it, ++c) {
+    int base_slot = 0;  // slot of the frame before this iteration's first frame; frame f -> base_slot + f + 1
+    uint32_t parity = 0;
+#pragma unroll 1
+    for (int it = it0 - 1; it < it1; ++it) {
         // ---------------- phase 1: arm FIR + N-point backward DFT for this warp's F frames -------------
+        if constexpr (PF == 1) {
+            if (it > it0 - 1) {  // the row was pulled into L2 before the demod phase: load it now
+                const float2* rp = pfb_row_ptr<R>(p, frame) + ll;
+#pragma unroll
+                for (int jj = 0; jj < R; ++jj) xr[jj] = (PT == 1) ? ld_stream_f2(rp + jj * R) : __ldg(rp + jj * R);
+            }
+        }
         float2 v[R];  // v[j], j = R-1-jj  (DFT input index i = R*j + (R-1-ll))
 #pragma unroll
-        for (int jj = 0; jj < R; ++jj) {
-            const float h = tap_base[jj * R + ll];
-            v[R - 1 - jj] = make_float2(h * xr[jj].x, h * xr[jj].y);
+        for (int jq = 0; jq < R / 4; ++jq) {
+            const float4 h = tap4[jq * R + ll];
+            v[R - 1 - (4 * jq + 0)] = make_float2(h.x * xr[4 * jq + 0].x, h.x * xr[4 * jq + 0].y);
+            v[R - 1 - (4 * jq + 1)] = make_float2(h.y * xr[4 * jq + 1].x, h.y * xr[4 * jq + 1].y);
+            v[R - 1 - (4 * jq + 2)] = make_float2(h.z * xr[4 * jq + 2].x, h.z * xr[4 * jq + 2].y);
+            v[R - 1 - (4 * jq + 3)] = make_float2(h.w * xr[4 * jq + 3].x, h.w * xr[4 * jq + 3].y);
         }
+#pragma unroll 1
         for (int k = 1; k < P; ++k) {
-            const float2* rp = pfb_row_ptr<R>(p, frame - k);
-            if (rp) {
-                const float* tk = tap_base + k * N;
+            const float2* rp = pfb_row_ptr<R>(p, frame - k) + ll;
+            const float4* tk = tap4 + k * (N / 4);
 #pragma unroll
-                for (int jj = 0; jj < R; ++jj) {
-                    const float2 xv = __ldg(rp + jj * R + ll);
-                    const float h = tk[jj * R + ll];
-                    v[R - 1 - jj].x = fmaf(h, xv.x, v[R - 1 - jj].x);
-                    v[R - 1 - jj].y = fmaf(h, xv.y, v[R - 1 - jj].y);
+            for (int jq = 0; jq < R / 4; ++jq) {
+                const float4 h = tk[jq * R + ll];
+                const float hh[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float2 xv = __ldg(rp + (4 * jq + u) * R);
+                    v[R - 1 - (4 * jq + u)].x = fmaf(hh[u], xv.x, v[R - 1 - (4 * jq + u)].x);
+                    v[R - 1 - (4 * jq + u)].y = fmaf(hh[u], xv.y, v[R - 1 - (4 * jq + u)].y);
                 }
             }
         }
-        const int slot = (c * FPI + warp * F + fr + 1) % NSLOT;
-        float2* buf = ring + slot * FS;
-        warp_fft_2pass<R, +1, true>(v, buf, tws, ll);  // v[m2] = Y[ll + R*m2]
-#pragma unroll
-        for (int m2 = 0; m2 < R; ++m2) buf[m2 * S + ll] = v[m2];
+        fft_inreg<R, +1>(v);  // pass 1 needs no shared memory: overlaps the other warps' demod tail
 
-        // prefetch the k = 0 row of this warp's next frame; the loads fly during phase 2
+        int slot = base_slot + warp * F + fr + 1;
+        slot = (slot >= NSLOT) ? slot - NSLOT : slot;
+        float2* buf = ring + slot * FS;
+        if (it > it0 - 1) {  // everyone finished reading the ring in the previous demod phase?
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+        }
+        warp_fft_xpose_pass2<R, +1, true>(v, buf, tws, ll);  // v[m2] = Y[ll + R*m2]
+        if constexpr (PHI) {
+            float* fb = reinterpret_cast<float*>(buf);
+#pragma unroll
+            for (int m2 = 0; m2 < R; ++m2) {
+                fb[m2 * R + ll] = atan2_nan(v[m2].y, v[m2].x);
+                if ((m2 & 3) == 3) asm volatile("" ::: "memory");  // bound the atan2 ILP (register pressure)
+            }
+        } else {
+#pragma unroll
+            for (int m2 = 0; m2 < R; ++m2) buf[m2 * S + ll] = v[m2];
+        }
+
+        // prefetch the k = 0 row of this warp's next frame; the loads fly during the demod phase
         frame += FPI;
         if (it + 1 < it1) {
-            const float2* rp = pfb_row_ptr<R>(p, frame);
+            if constexpr (PF == 1) {
+                // one prefetch per 128 B line of the F*N*8-byte chunk this warp reads next
+                const char* base = reinterpret_cast<const char*>(pfb_row_ptr<R>(p, frame - fr)) ;
+                if (frame - fr >= 0 && frame - fr + F <= p.T) {
 #pragma unroll
-            for (int jj = 0; jj < R; ++jj)
-                xr[jj] = rp ? (PT == 1 ? ld_stream_f2(rp + jj * R + ll) : __ldg(rp + jj * R + ll)) : make_float2(0.f, 0.f);
+                    for (int q = 0; q < (F * N * 8) / (128 * 32); ++q)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (q * 32 + lane) * 128));
+                }
+            } else {
+                const float2* rp = pfb_row_ptr<R>(p, frame) + ll;
+#pragma unroll
+                for (int jj = 0; jj < R; ++jj) xr[jj] = (PT == 1) ? ld_stream_f2(rp + jj * R) : __ldg(rp + jj * R);
+            }
         }
         __syncthreads();
 
-        // ---------------- phase 2: demod 8 consecutive frames of one channel, 32 B store ---------------
+        // ---------------- phase 2: 8 consecutive frames of CPT channels per thread, 32 B stores --------
         if (it >= it0) {
-            constexpr int ITEMS = N * (FPI / 8) / G::THREADS;
-#pragma unroll
-            for (int q = 0; q < ITEMS; ++q) {
-                const int item = q * G::THREADS + tid;
-                const int m = item % N, g = item / N;
-                const int pos = (m / R) * S + (m % R);
-                const int base = c * FPI + 8 * g;  // slot of frame f is (base + j + 1) % NSLOT, j = f - 8g
+            if constexpr (PHI) {
+                constexpr int CPT = N * (FPI / 8) / G::THREADS;  // 4, 2, 1 for R = 32, 16, 8
+                const int g = tid / (N / CPT);
+                const int m0 = (tid % (N / CPT)) * CPT;
                 const long long t0 = (long long)it * FPI + 8 * g;
-                float2 y[9];
-#pragma unroll
-                for (int j = 0; j < 9; ++j) y[j] = ring[((base + j) % NSLOT) * FS + pos];
+                int s = base_slot + 8 * g;
+                s = (s >= NSLOT) ? s - NSLOT : s;
                 const bool full = (t0 + 8 <= p.T);
-                if (MODE & PFB_OUT_FM) {
-                    float o[8];
+                constexpr int W = (CPT >= 2) ? 2 : 1;  // channels handled together (register footprint)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float2 pr = cmul_conj(y[j + 1], y[j]);
-                        o[j] = p.gain * atan2_fast(pr.y, pr.x);
-                    }
-                    float* dst = p.out_fm + (long long)m * p.ostride + t0;
-                    if (full) {
-                        st_global_v8(dst, o);
-                    } else {
+                for (int hq = 0; hq < CPT / W; ++hq) {
+                    float ph[9][W];
+                    int sj = s;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (t0 + j < p.T) dst[j] = o[j];
+                    for (int j = 0; j < 9; ++j) {
+                        const float* src = reinterpret_cast<const float*>(ring + sj * FS) + m0 + hq * W;
+                        if constexpr (W == 2) {
+                            const float2 t = *reinterpret_cast<const float2*>(src);
+                            ph[j][0] = t.x; ph[j][1] = t.y;
+                        } else {
+                            ph[j][0] = *src;
+                        }
+                        sj = (sj + 1 == NSLOT) ? 0 : sj + 1;
                     }
-                }
-                if (MODE & PFB_OUT_IQ) {
-                    float2* dst = p.out_iq + (long long)m * p.ostride + t0;
-                    if (full) {
+#pragma unroll
+                    for (int q = 0; q < W; ++q) {
                         float o[8];
 #pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                o[2 * j] = y[1 + 4 * hh + j].x;
-                                o[2 * j + 1] = y[1 + 4 * hh + j].y;
-                            }
-                            st_global_v8(reinterpret_cast<float*>(dst + 4 * hh), o);
+                        for (int j = 0; j < 8; ++j) {
+                            float d = ph[j + 1][q] - ph[j][q];                       // in (-2pi, 2pi)
+                            const float k = (d * 0.15915494309189535f + 12582912.0f) - 12582912.0f;  // rint(d/2pi)
+                            d = fmaf(k, -6.283185307179586f, d);
+                            d *= p.gain;
+                            o[j] = (d != d) ? 0.0f : d;                             // Y == 0 -> 0 like fast_atan2f
                         }
-                    } else {
+                        float* dst = p.out_fm + (long long)(m0 + hq * W + q) * p.ostride + t0;
+                        if (full) {
+                            st_global_v8(dst, o);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (t0 + j < p.T) dst[j] = y[j + 1];
+                            for (int j = 0; j < 8; ++j)
+                                if (t0 + j < p.T) dst[j] = o[j];
+                        }
+                    }
+                }
+            } else {
+                constexpr int ITEMS = N * (FPI / 8) / G::THREADS;
+#pragma unroll 1
+                for (int q = 0; q < ITEMS; ++q) {
+                    const int item = q * G::THREADS + tid;
+                    const int m = item % N, g = item / N;
+                    const int pos = (m / R) * S + (m % R);
+                    const long long t0 = (long long)it * FPI + 8 * g;
+                    int s = base_slot + 8 * g;
+                    s = (s >= NSLOT) ? s - NSLOT : s;
+                    float2 y[9];
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) {
+                        y[j] = ring[s * FS + pos];
+                        s = (s + 1 == NSLOT) ? 0 : s + 1;
+                    }
+                    const bool full = (t0 + 8 <= p.T);
+                    if (MODE & PFB_OUT_FM) {
+                        float o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float2 pr = cmul_conj(y[j + 1], y[j]);
+                            o[j] = p.gain * atan2_fast(pr.y, pr.x);
+                        }
+                        float* dst = p.out_fm + (long long)m * p.ostride + t0;
+                        if (full) {
+                            st_global_v8(dst, o);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (t0 + j < p.T) dst[j] = o[j];
+                        }
+                    }
+                    if (MODE & PFB_OUT_IQ) {
+                        float2* dst = p.out_iq + (long long)m * p.ostride + t0;
+                        if (full) {
+                            float o[8];
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    o[2 * j] = y[1 + 4 * hh + j].x;
+                                    o[2 * j + 1] = y[1 + 4 * hh + j].y;
+                                }
+                                st_global_v8(reinterpret_cast<float*>(dst + 4 * hh), o);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (t0 + j < p.T) dst[j] = y[j + 1];
+                        }
                     }
                 }
             }
         }
-        __syncthreads();
+        mbar_arrive(bar);  // this thread is done reading the ring
+        base_slot = (base_slot == 0) ? NSLOT - 1 : base_slot - 1;  // FPI == -1 (mod NSLOT)
     }
 }
 

@@ -1,0 +1,260 @@
+// K1 (headline variant)  pfb_fm_tma : FM-only polyphase channelizer, 1 tap per arm (P = 1), N = R*R.
+//
+// Same arithmetic and launch geometry as pfb_fm_kernel (pfb_fm.cuh) but with the input staged by TMA:
+//   * each warp owns an 8 KB shared-memory work buffer.  One elected lane issues cp.async.bulk (1-D TMA,
+//     SASS UBLKCP) copies of the warp's next F frames (8 KB of contiguous wideband samples) into it and the
+//     warp waits on its own mbarrier - no registers are tied up by in-flight loads (the register-prefetch
+//     variant spilled half of its 64 prefetch registers, profiles/r01_pfb_fm_v2_*), and the copy for frame
+//     n+1 is issued as soon as the second FFT pass of frame n has been read out of the buffer, i.e. a full
+//     atan2 + demod phase ahead of its use;
+//   * the same buffer is then reused as the 32x32 transpose scratch between the two in-register radix-R
+//     passes, dense (no padding) with a 16-byte-chunk XOR swizzle so STS.128 / LDS.64 stay conflict free;
+//   * the ring shared by the CTA holds angle(Y) (4 B) instead of Y: atan2 runs once per sample in the FFT
+//     warp, the demod phase is subtract + wrap (magic-number rint) + gain, 32 B sector stores.
+//   * CTA-level ordering uses an mbarrier (arrive after the demod reads, wait just before the next ring
+//     write) so the next frame's FIR + both FFT passes + atan2 overlap the other warps' demod tail.
+// Shared memory: 8 x 8 KB work + 9 x 4 KB phase ring + 8 KB twiddles + 4 KB taps = 112.1 KB -> 2 CTAs/SM.
+#pragma once
+#include "pfb_fm.cuh"
+
+namespace rcb {
+
+template <int R>
+struct PfbTmaGeom {
+    static constexpr int N = R * R;
+    static constexpr int F = 32 / R;
+    static constexpr int WARPS = 8;
+    static constexpr int THREADS = 256;
+    static constexpr int FPI = WARPS * F;
+    static constexpr int NSLOT = FPI + 1;
+    static constexpr int FSW = N + (R == 8 ? 8 : 0);       // frame stride inside a warp's work buffer (complex)
+    static constexpr int WORK = F * FSW;                    // complex per warp
+    static constexpr size_t work_bytes = (size_t)WARPS * WORK * 8;
+    static constexpr size_t ring_bytes = (size_t)NSLOT * N * 4;
+    static constexpr size_t tw_bytes = (size_t)N * 8;
+    static constexpr size_t taps_bytes = (size_t)N * 4;
+    static constexpr size_t smem_bytes = work_bytes + ring_bytes + tw_bytes + taps_bytes + 128;
+};
+
+template <int R>
+__device__ __forceinline__ int pfb_swz(int l) {
+    return (R == 8) ? ((l >> 1) & 3) : (l & (R / 2 - 1));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 t;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// twiddle table layout expected in p.twiddle for this kernel: dense [R][R] complex, 16-byte chunks swizzled:
+//   tw[ll*R + (((m1>>1) ^ swz(ll))<<1 | (m1&1))] = W_N^{+(R-1-ll) m1}
+// taps layout: float4 groups as in pfb_fm.cuh (P = 1).
+template <int R>
+__global__ void __launch_bounds__(256, 2) pfb_fm_tma_kernel(const PfbParams p) {
+    using G = PfbTmaGeom<R>;
+    constexpr int N = G::N, F = G::F, FPI = G::FPI, NSLOT = G::NSLOT, FSW = G::FSW;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* work_all = reinterpret_cast<float2*>(smem_raw);
+    float* ring = reinterpret_cast<float*>(smem_raw + G::work_bytes);
+    float2* tws = reinterpret_cast<float2*>(smem_raw + G::work_bytes + G::ring_bytes);
+    float* taps_s = reinterpret_cast<float*>(smem_raw + G::work_bytes + G::ring_bytes + G::tw_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + G::work_bytes + G::ring_bytes + G::tw_bytes + G::taps_bytes);
+    uint64_t* cta_bar = bars + 8;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int fr = lane / R, ll = lane % R;
+    float2* work = work_all + warp * G::WORK;   // this warp's buffer
+    float2* wf = work + fr * FSW;               // this lane's frame inside it
+    uint64_t* row_bar = bars + warp;
+
+    for (int i = tid; i < N; i += 256) {
+        tws[i] = p.twiddle[i];
+        taps_s[i] = p.taps[i];
+    }
+    if (tid < 8) mbar_init(bars + tid, 1);
+    if (tid == 8) mbar_init(cta_bar, 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const float4* tap4 = reinterpret_cast<const float4*>(taps_s);
+
+    // ---- work distribution: a static contiguous run (7/8 of the even share) per CTA, then the tail of the
+    // ---- launch is handed out dynamically in chunks of kTailChunk iterations (atomic counter).  SMs differ
+    // ---- by up to +-10 % in sustained speed with TMA staging (profiles/r01_pfb_fm_v3_*): a purely static split
+    // ---- leaves the fast SMs idle for 11 % of the launch.  Every range starts with one warm-up iteration
+    // ---- that recomputes the frame before it (no Y / phase state is carried between ranges or launches).
+    constexpr int kTailChunk = 4;
+    const int NI = (p.T + FPI - 1) / FPI;
+    const int stat = (int)(((long long)(NI / (int)gridDim.x) * 7) / 8);
+    const int tail0 = stat * (int)gridDim.x;
+    __shared__ int s_next;
+    int cur0, cur1;
+    if (stat > 0) {
+        cur0 = blockIdx.x * stat;
+        cur1 = cur0 + stat;
+    } else {
+        if (tid == 0) s_next = atomicAdd(p.work_counter, 1);
+        __syncthreads();
+        cur0 = tail0 + s_next * kTailChunk;
+        cur1 = min(cur0 + kTailChunk, NI);
+        __syncthreads();
+        if (cur0 >= NI) return;
+    }
+    int nxt0 = NI, nxt1 = NI;  // following range (nxt0 >= NI: none)
+
+    long long frame0 = (long long)(cur0 - 1) * FPI + warp * F;  // first of this warp's F frames
+    auto issue_rows = [&](long long f0) {
+        if (lane == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(row_bar, (uint32_t)(F * N * 8));
+#pragma unroll
+            for (int q = 0; q < F; ++q)
+                tma_bulk_g2s(work + q * FSW, pfb_row_ptr<R>(p, f0 + q), (uint32_t)(N * 8), row_bar);
+        }
+    };
+    issue_rows(frame0);
+
+    int base_slot = 0;
+    uint32_t row_par = 0, cta_par = 0;
+    bool first_ever = true;
+#pragma unroll 1
+    for (int it = cur0 - 1;; ++it) {
+        const bool range_first = (it == cur0 - 1);
+        if (range_first && tid == 0) {  // reserve the range that follows the current one
+            const int c = atomicAdd(p.work_counter, 1);
+            s_next = tail0 + c * kTailChunk;
+        }
+        // ---- wait for the TMA copy of this warp's frames, FIR, first radix-R pass ----
+        mbar_wait(row_bar, row_par);
+        row_par ^= 1u;
+        float2 v[R];
+#pragma unroll
+        for (int jq = 0; jq < R / 4; ++jq) {
+            const float4 h = tap4[jq * R + ll];
+            const float2 x0 = wf[(4 * jq + 0) * R + ll], x1 = wf[(4 * jq + 1) * R + ll];
+            const float2 x2 = wf[(4 * jq + 2) * R + ll], x3 = wf[(4 * jq + 3) * R + ll];
+            v[R - 1 - (4 * jq + 0)] = make_float2(h.x * x0.x, h.x * x0.y);
+            v[R - 1 - (4 * jq + 1)] = make_float2(h.y * x1.x, h.y * x1.y);
+            v[R - 1 - (4 * jq + 2)] = make_float2(h.z * x2.x, h.z * x2.y);
+            v[R - 1 - (4 * jq + 3)] = make_float2(h.w * x3.x, h.w * x3.y);
+        }
+        fft_inreg<R, +1>(v);
+        __syncwarp();  // every lane has read its samples: the buffer becomes the transpose scratch
+        // ---- twiddle + swizzled transpose + second pass ----
+        {
+            const int sw = pfb_swz<R>(ll);
+            const float4* twp = reinterpret_cast<const float4*>(tws + ll * R);
+            float4* bp = reinterpret_cast<float4*>(wf + ll * R);
+#pragma unroll
+            for (int c = 0; c < R / 2; ++c) {
+                const float4 t = twp[c ^ sw];
+                const int m1 = 2 * c;
+                const float2 b0 = make_float2(fmaf(v[m1].x, t.x, -v[m1].y * t.y), fmaf(v[m1].x, t.y, v[m1].y * t.x));
+                const float2 b1 = make_float2(fmaf(v[m1 + 1].x, t.z, -v[m1 + 1].y * t.w),
+                                              fmaf(v[m1 + 1].x, t.w, v[m1 + 1].y * t.z));
+                bp[c ^ sw] = make_float4(b0.x, b0.y, b1.x, b1.y);
+            }
+        }
+        __syncwarp();
+        {
+            const int ch = ll >> 1, wi = ll & 1;
+#pragma unroll
+            for (int l2 = 0; l2 < R; ++l2) v[R - 1 - l2] = wf[l2 * R + (((ch ^ pfb_swz<R>(l2)) << 1) | wi)];
+        }
+        __syncwarp();  // scratch fully consumed: start the copy of the next frames right away
+        const bool range_last = (it + 1 == cur1);
+        if (!range_last) {
+            frame0 += FPI;
+            issue_rows(frame0);
+        } else if (nxt0 < NI) {  // seamless hand-over: prefetch the warm-up frames of the next range
+            frame0 = (long long)(nxt0 - 1) * FPI + warp * F;
+            issue_rows(frame0);
+        }
+        fft_inreg<R, +1>(v);  // v[m2] = Y[ll + R*m2]
+
+        float ph[R];
+#pragma unroll
+        for (int m2 = 0; m2 < R; ++m2) ph[m2] = atan2_nan(v[m2].y, v[m2].x);
+
+        int slot = base_slot + warp * F + fr + 1;
+        slot = (slot >= NSLOT) ? slot - NSLOT : slot;
+        if (!first_ever) {  // previous demod phase finished reading the ring?
+            mbar_wait(cta_bar, cta_par);
+            cta_par ^= 1u;
+        }
+        first_ever = false;
+        {
+            float* fb = ring + slot * N;
+#pragma unroll
+            for (int m2 = 0; m2 < R; ++m2) fb[m2 * R + ll] = ph[m2];
+        }
+        __syncthreads();
+        if (range_first) {
+            nxt0 = s_next;
+            nxt1 = min(nxt0 + kTailChunk, NI);
+        }
+
+        // ---- demod: 8 consecutive frames of CPT channels per thread ----
+        if (it >= cur0) {
+            constexpr int CPT = N * (FPI / 8) / 256;  // 4, 2, 1 for R = 32, 16, 8
+            const int g = tid / (N / CPT);
+            const int m0 = (tid % (N / CPT)) * CPT;
+            const long long t0 = (long long)it * FPI + 8 * g;
+            int s = base_slot + 8 * g;
+            s = (s >= NSLOT) ? s - NSLOT : s;
+            const bool full = (t0 + 8 <= p.T);
+            float pw[9][CPT];  // all ring loads first (9 vector LDS), then CPT*8 independent wrap chains
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                const float* src = ring + s * N + m0;
+                if constexpr (CPT == 4) {
+                    const float4 t = *reinterpret_cast<const float4*>(src);
+                    pw[j][0] = t.x; pw[j][1] = t.y; pw[j][2] = t.z; pw[j][3] = t.w;
+                } else if constexpr (CPT == 2) {
+                    const float2 t = *reinterpret_cast<const float2*>(src);
+                    pw[j][0] = t.x; pw[j][1] = t.y;
+                } else {
+                    pw[j][0] = *src;
+                }
+                s = (s + 1 == NSLOT) ? 0 : s + 1;
+            }
+#pragma unroll
+            for (int q = 0; q < CPT; ++q) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float d = pw[j + 1][q] - pw[j][q];
+                    const float k = (d * 0.15915494309189535f + 12582912.0f) - 12582912.0f;
+                    d = fmaf(k, -6.283185307179586f, d);
+                    d *= p.gain;
+                    o[j] = (d != d) ? 0.0f : d;
+                }
+                float* dst = p.out_fm + (long long)(m0 + q) * p.ostride + t0;
+                if (full) {
+                    st_global_v8(dst, o);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (t0 + j < p.T) dst[j] = o[j];
+                }
+            }
+        }
+        mbar_arrive(cta_bar);
+        base_slot = (base_slot == 0) ? NSLOT - 1 : base_slot - 1;
+        if (range_last) {
+            if (nxt0 >= NI) break;
+            cur0 = nxt0;
+            cur1 = nxt1;
+            it = cur0 - 2;  // ++it -> warm-up iteration of the new range
+        }
+    }
+}
+
+}  // namespace rcb
