@@ -148,9 +148,9 @@ def synth_block(n, nchans, seed):
 
 
 def dist_setup(ngpus):
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    """One process per GPU under torchrun; torch.distributed (NCCL) only for barrier + reductions."""
+    from radiocapture_rf_b200 import sharding
+    world, rank, local = sharding.world_from_env()
     dist = None
     if world > 1:
         import torch
@@ -169,12 +169,8 @@ def barrier(dist, local):
 
 
 def allreduce_max(dist, local, v):
-    if dist is None:
-        return v
-    import torch
-    t = torch.tensor([v], dtype=torch.float64, device="cuda:%d" % local)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+    from radiocapture_rf_b200 import sharding
+    return sharding.Reducer(dist, "cuda:%d" % local if dist is not None else None).max(v)
 
 
 # -------------------------------------------------------------------------------------------------
@@ -234,7 +230,7 @@ def run_reference(args):
 class StreamCtx(object):
     """One wideband stream resident on the GPU: engine + channelizer + device buffers."""
 
-    def __init__(self, device, wl, seed, log2n=None, ntaps=None):
+    def __init__(self, device, wl, seed, log2n=None, ntaps=None, out_block=0):
         from radiocapture_rf_b200.engine import Engine, PfbChannelizer, OUT_FM, OUT_IQ
         cfg = WORKLOADS[wl]
         self.cfg = cfg
@@ -257,7 +253,12 @@ class StreamCtx(object):
             self.e.copy_d2d(self.d_in.ptr + filled * 8, self.d_in.ptr, c * 8)
             filled += c
         self.base = base
-        self.d_out = self.e.dev_alloc(self.n * (4 if self.fm else 8))
+        self.out_block = out_block
+        if out_block:
+            self.ch.set_out_block(out_block)
+        nb = -(-self.frames // out_block) if out_block else 0
+        out_elems = nb * self.nch * out_block if out_block else self.n
+        self.d_out = self.e.dev_alloc(out_elems * (4 if self.fm else 8))
         self.bytes_per_sample = 8 + (4 if self.fm else 8)
 
     def step(self):
@@ -328,7 +329,8 @@ def run_b200(args):
     cfg = WORKLOADS[wl]
     peak, peak_src = load_peak()
 
-    ctxs = [StreamCtx(device, wl, seed=3 + 100 * rank + i, log2n=args.log2n) for i in range(cfg["streams"])]
+    ctxs = [StreamCtx(device, wl, seed=3 + 100 * rank + i, log2n=args.log2n, out_block=args.out_block)
+            for i in range(cfg["streams"])]
     sampler = ClockSampler(device)
     sampler.start()
     time.sleep(0.3)
@@ -354,13 +356,23 @@ def run_b200(args):
 
     also = None
     if wl == "cfg3" and not args.no_also:
-        c16 = StreamCtx(device, "cfg3_p16", seed=3, log2n=args.log2n)
+        also = {}
+        if args.out_block:  # the same launch with the plain [N][T] layout (rows 1 MB apart)
+            cp = StreamCtx(device, wl, seed=3, log2n=args.log2n, out_block=0)
+            msp, _, _, _ = timed_loop([cp], max(3, args.steps // 2), 3, dist, local)
+            msp = allreduce_max(dist, local, msp)
+            stp = max(3, args.steps // 2)
+            also["plain_layout"] = {"workload": cfg["desc"] + ", plain [N][T] output", "unit": "Msps",
+                                    "value": cp.n * stp * world / (msp * 1e-3) / 1e6,
+                                    "roofline_frac": cp.n * stp * 12 / (msp * 1e-3) / 1e9 / peak}
+            cp.close()
+        c16 = StreamCtx(device, "cfg3_p16", seed=3, log2n=args.log2n, out_block=args.out_block)
         ms16, _, _, _ = timed_loop([c16], max(3, args.steps // 2), 2, dist, local)
         ms16 = allreduce_max(dist, local, ms16)
         st16 = max(3, args.steps // 2)
         a16 = c16.n * st16 * 12 / (ms16 * 1e-3) / 1e9
-        also = {"workload": WORKLOADS["cfg3_p16"]["desc"], "value": c16.n * st16 * world / (ms16 * 1e-3) / 1e6,
-                "unit": "Msps", "roofline_frac": a16 / peak}
+        also["taps_per_arm_16"] = {"workload": WORKLOADS["cfg3_p16"]["desc"], "unit": "Msps",
+                                   "value": c16.n * st16 * world / (ms16 * 1e-3) / 1e6, "roofline_frac": a16 / peak}
         c16.close()
 
     e2e_v, h2d, d2h, chk = run_e2e(device, wl, args.e2e_steps, 1, dist, local)
@@ -380,6 +392,8 @@ def run_b200(args):
             "config": {"workload": cfg["desc"], "nchans": cfg["nchans"], "ntaps": cfg["ntaps"], "out": cfg["out"],
                        "samples_per_step_per_gpu": sum(c.n for c in ctxs), "streams_per_gpu": cfg["streams"],
                        "channels_out": cfg["nchans"] * cfg["streams"] * world,
+                       "out_layout": ("channel-major in blocks of %d frames (rcb_pfb_set_out_block)" % args.out_block)
+                       if args.out_block else "channel-major [N][T]",
                        "l2": "inputs (%d MiB/step) larger than L2, no flush" % (sum(c.n for c in ctxs) * 8 >> 20),
                        "parallelism": "independent streams, %d GPU(s), no collective" % world},
             "roofline": roofline,
@@ -398,10 +412,8 @@ def run_b200(args):
 
 def allreduce_sum_min(dist, local, v, world):
     """whole-job e2e = world * min over ranks (ranks run concurrently, each bounded by its own PCIe link)."""
-    import torch
-    t = torch.tensor([v], dtype=torch.float64, device="cuda:%d" % local)
-    dist.all_reduce(t, op=dist.ReduceOp.MIN)
-    return float(t.item()) * world
+    from radiocapture_rf_b200 import sharding
+    return sharding.Reducer(dist, "cuda:%d" % local).min(v) * world
 
 
 def main():
@@ -413,6 +425,8 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--log2n", type=int, default=None, help="override samples per step per stream (log2)")
     ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--out-block", type=int, default=1024,
+                    help="device output layout: channel-major in blocks of this many frames (0 = plain [N][T])")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-also", action="store_true")
     args = ap.parse_args()

@@ -82,6 +82,12 @@ int rcb_timer_stop(rcb_t* h, float* ms);        /* record + synchronize + elapse
  * stream into calls gives the same samples as one call.  out_iq / out_fm may be NULL per out_mask. */
 int rcb_pfb_config(rcb_t* h, int nchans, const float* taps, int ntaps, int out_mask, float fm_gain);
 int rcb_pfb_reset(rcb_t* h);
+/* Optional device-output layout: channel-major inside time blocks of `frames` (power of two >= 8, 0 = plain
+ * [N][out_stride]): element (m, n) at ((n / frames) * nchans + m) * frames + n % frames.  Each channel is then
+ * delivered as contiguous `frames`-sample messages - the unit a zeromq.pub_sink sends (channel.py:36) - and the
+ * rows one kernel iteration writes stay within a few MB (TLB / DRAM page locality).  The output buffer must hold
+ * ceil(nout / frames) * nchans * frames elements; out_stride is ignored.  Device-resident outputs only. */
+int rcb_pfb_set_out_block(rcb_t* h, int frames);
 int rcb_pfb_process(rcb_t* h, const void* iq, size_t nsamples, int in_mem,
                     void* out_iq, void* out_fm, size_t out_stride, int out_mem, size_t* nout);
 

@@ -87,6 +87,7 @@ struct rcb_ctx {
         size_t smem = 0;
         bool taps_smem = true;
         int variant = 0;  // RCB_PFB_VARIANT (tuning experiments)
+        int oblock_log2 = 0;  // rcb_pfb_set_out_block
         Stage st[kStages];
         size_t chunk_frames = 0;
     } pfb;
@@ -279,9 +280,14 @@ int pfb_run_device(rcb_t* h, const float2* d_x, size_t frames, float2* d_iq, flo
     p.taps = s.d_taps;
     p.twiddle = s.d_tw;
     p.zeros = s.d_zeros;
+    {
+        const char* dbg = getenv("RCB_PFB_DEBUG");
+        p.debug_flags = dbg ? atoi(dbg) : 0;
+    }
     p.out_fm = (s.mode & RCB_OUT_FM) ? d_fm : nullptr;
     p.out_iq = (s.mode & RCB_OUT_IQ) ? d_iq : nullptr;
     p.ostride = (long long)ostride;
+    p.oblock_log2 = s.oblock_log2;
     p.T = (int)frames;
     p.P = s.P;
     p.N = s.N;
@@ -304,7 +310,7 @@ int pfb_run_device(rcb_t* h, const float2* d_x, size_t frames, float2* d_iq, flo
         CKL(h);
         dim3 g2((unsigned)((frames + 255) / 256), (unsigned)s.N);
         pfb_generic_emit_kernel<<<g2, 256, 0, h->stream>>>(s.d_ys, (long long)frames + 1, p.out_iq, p.out_fm,
-                                                           p.ostride, p.T, p.gain);
+                                                           p.ostride, p.T, p.gain, p.oblock_log2, p.N);
         CKL(h);
     }
     // hist <- last P rows of (hist ++ x)
@@ -627,6 +633,20 @@ extern "C" int rcb_pfb_config(rcb_t* h, int nchans, const float* taps, int ntaps
     return RCB_OK;
 }
 
+extern "C" int rcb_pfb_set_out_block(rcb_t* h, int frames) {
+    if (!h) return RCB_EINVAL;
+    if (!h->pfb.configured) return RCB_ESTATE;
+    if (frames == 0) {
+        h->pfb.oblock_log2 = 0;
+        return RCB_OK;
+    }
+    if (frames < 8 || (frames & (frames - 1))) return RCB_EINVAL;  // power of two >= 8
+    int k = 0;
+    while ((1 << k) < frames) ++k;
+    h->pfb.oblock_log2 = k;
+    return RCB_OK;
+}
+
 extern "C" int rcb_pfb_reset(rcb_t* h) {
     if (!h) return RCB_EINVAL;
     auto& s = h->pfb;
@@ -648,7 +668,7 @@ extern "C" int rcb_pfb_process(rcb_t* h, const void* iq, size_t nsamples, int in
     if (frames > 0x7fffff00u) return RCB_ERANGE;
     if ((s.mode & RCB_OUT_IQ) && !out_iq) return RCB_EINVAL;
     if ((s.mode & RCB_OUT_FM) && !out_fm) return RCB_EINVAL;
-    if (out_stride < frames) return RCB_EINVAL;
+    if (out_stride < frames && !s.oblock_log2) return RCB_EINVAL;
     if ((in_mem != RCB_MEM_HOST && in_mem != RCB_MEM_DEVICE) || (out_mem != RCB_MEM_HOST && out_mem != RCB_MEM_DEVICE))
         return RCB_EINVAL;
     CK(cudaSetDevice(h->device));
@@ -662,6 +682,7 @@ extern "C" int rcb_pfb_process(rcb_t* h, const void* iq, size_t nsamples, int in
     }
 
     // host-facing path: chunked 3-stage pipeline  H2D (s_in) | kernel (stream) | D2H (s_out)
+    if (s.oblock_log2) return RCB_ESTATE;  // the blocked layout is for device-resident outputs only
     int rc = pfb_ensure_stages(h);
     if (rc) return rc;
     const size_t cf = s.chunk_frames;

@@ -48,6 +48,22 @@ __device__ __forceinline__ void st_global_v8(float* p, const float (&v)[8]) {
                  : "memory");
 }
 
+__device__ __forceinline__ void st_global_v8_hint(float* p, const float (&v)[8], uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;" ::"l"(p), "f"(v[0]), "f"(v[1]),
+                 "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
 // streaming (read-once) 64-bit load: bypass L1 allocation
 __device__ __forceinline__ float2 ld_stream_f2(const float2* p) {
     float2 r;

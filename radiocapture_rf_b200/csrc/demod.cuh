@@ -52,16 +52,19 @@ __global__ void save_last_kernel(const float2* __restrict__ x, long long xs, lon
 __global__ void __launch_bounds__(256) pfb_generic_emit_kernel(const float2* __restrict__ ys, long long ystride,
                                                                float2* __restrict__ out_iq,
                                                                float* __restrict__ out_fm, long long ostride,
-                                                               int T, float gain) {
+                                                               int T, float gain, int oblock_log2, int N) {
     const int m = blockIdx.y;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     const float2 c = ys[(long long)m * ystride + t + 1];
-    if (out_iq) out_iq[(long long)m * ostride + t] = c;
+    const long long oi = (oblock_log2 > 0)
+                             ? (((((t >> oblock_log2) * N) + m) << oblock_log2) | (t & ((1LL << oblock_log2) - 1)))
+                             : ((long long)m * ostride + t);
+    if (out_iq) out_iq[oi] = c;
     if (out_fm) {
         const float2 pv = ys[(long long)m * ystride + t];
         const float2 pr = cmul_conj(c, pv);
-        out_fm[(long long)m * ostride + t] = gain * atan2_fast(pr.y, pr.x);
+        out_fm[oi] = gain * atan2_fast(pr.y, pr.x);
     }
 }
 

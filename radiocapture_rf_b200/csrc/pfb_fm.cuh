@@ -40,11 +40,15 @@ struct PfbParams {
     const float* taps;      // fast path, float4 groups: taps[((k*(R/4) + jj/4)*R + ll)*4 + jj%4] =
                             //   h[R*(R-1-jj) + (R-1-ll) + k*N];  generic path: taps[k*N + i] = h[i + k*N]
     const float2* zeros;    // N complex zeros (rows outside the stream)
+    int debug_flags;        // RCB_PFB_DEBUG (measurement experiments only): 1 = suppress FM stores, 2 = load rows once
     int* work_counter;      // zeroed before each launch: dynamic tail-chunk counter (pfb_fm_tma_kernel)
     const float2* twiddle;  // fast: [R][R+2]: tw[ll*(R+2) + m1] = W_N^{+(R-1-ll) m1};  generic: [N] W_N^{+q}
     float* out_fm;          // [N][ostride] floats (or null)
     float2* out_iq;         // [N][ostride] complex (or null)
-    long long ostride;      // elements between consecutive channels
+    long long ostride;      // elements between consecutive channels (plain channel-major layout)
+    int oblock_log2;        // > 0: channel-major inside time blocks of 2^k frames: (m, t) at
+                            //   ((t >> k) * N + m) << k | (t & (2^k - 1)); keeps the 1024 rows a CTA writes
+                            //   per iteration within a few MB (TLB / DRAM-page locality, +15 % on cfg3)
     int T;                  // frames in this launch
     int P;                  // taps per arm
     int N;                  // channels
@@ -67,6 +71,14 @@ struct PfbGeom {
         return ring_bytes + tw_bytes + 16 /* mbarrier */ + (taps_smem ? (size_t)P * N * sizeof(float) : 0);
     }
 };
+
+__device__ __forceinline__ long long pfb_out_index(const PfbParams& p, int m, long long t) {
+    if (p.oblock_log2 > 0) {
+        const int k = p.oblock_log2;
+        return ((((t >> k) * p.N) + m) << k) | (t & ((1LL << k) - 1));
+    }
+    return (long long)m * p.ostride + t;
+}
 
 template <int R>
 __device__ __forceinline__ const float2* pfb_row_ptr(const PfbParams& p, long long r) {
@@ -271,7 +283,7 @@ __global__ void __launch_bounds__(256, 2) pfb_fm_kernel(const PfbParams p) {
                             d *= p.gain;
                             o[j] = (d != d) ? 0.0f : d;                             // Y == 0 -> 0 like fast_atan2f
                         }
-                        float* dst = p.out_fm + (long long)(m0 + hq * W + q) * p.ostride + t0;
+                        float* dst = p.out_fm + pfb_out_index(p, m0 + hq * W + q, t0);
                         if (full) {
                             st_global_v8(dst, o);
                         } else {
@@ -305,7 +317,7 @@ __global__ void __launch_bounds__(256, 2) pfb_fm_kernel(const PfbParams p) {
                             const float2 pr = cmul_conj(y[j + 1], y[j]);
                             o[j] = p.gain * atan2_fast(pr.y, pr.x);
                         }
-                        float* dst = p.out_fm + (long long)m * p.ostride + t0;
+                        float* dst = p.out_fm + pfb_out_index(p, m, t0);
                         if (full) {
                             st_global_v8(dst, o);
                         } else {
@@ -315,7 +327,7 @@ __global__ void __launch_bounds__(256, 2) pfb_fm_kernel(const PfbParams p) {
                         }
                     }
                     if (MODE & PFB_OUT_IQ) {
-                        float2* dst = p.out_iq + (long long)m * p.ostride + t0;
+                        float2* dst = p.out_iq + pfb_out_index(p, m, t0);
                         if (full) {
                             float o[8];
 #pragma unroll

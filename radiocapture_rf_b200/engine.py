@@ -162,6 +162,18 @@ class PfbChannelizer(object):
     def reset(self):
         check(self.e.lib.rcb_pfb_reset(self.e.h), "rcb_pfb_reset", self.e.h)
 
+    def set_out_block(self, frames):
+        """Device outputs as channel-major blocks of `frames` (power of two >= 8; 0 = plain [N][stride])."""
+        check(self.e.lib.rcb_pfb_set_out_block(self.e.h, int(frames)), "rcb_pfb_set_out_block", self.e.h)
+        self.out_block = int(frames)
+
+    @staticmethod
+    def unblock(arr, nchans, frames, block):
+        """[nblocks][nchans][block] device layout (flat) -> [nchans][frames]."""
+        nb = -(-frames // block)
+        a = np.asarray(arr).reshape(nb, nchans, block)
+        return np.ascontiguousarray(a.transpose(1, 0, 2).reshape(nchans, nb * block)[:, :frames])
+
     def process(self, iq, out_iq=None, out_fm=None):
         """iq: complex64 host array, len multiple of nchans.  Returns (iq_out [N][T] or None, fm_out or None)."""
         iq = np.ascontiguousarray(iq, dtype=np.complex64)

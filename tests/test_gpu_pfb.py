@@ -136,3 +136,34 @@ def test_pfb_tone_lands_in_its_bin(engine):
     assert int(np.argmax(p)) == m
     assert p[m] / (p.sum() - p[m]) > 1e4
     np.testing.assert_allclose(fm[m, 64:], 5.0 * 2 * np.pi * df, rtol=0, atol=2e-4)
+
+
+@pytest.mark.parametrize("n,tpa,mode", [(1024, 0.25, OUT_FM), (256, 4, OUT_IQ | OUT_FM), (20, None, OUT_FM)])
+def test_pfb_blocked_device_output_layout(engine, n, tpa, mode):
+    """rcb_pfb_set_out_block: channel-major inside time blocks (device-resident outputs) carries exactly
+    the same samples as the plain [N][T] layout, including a ragged last block."""
+    taps = fd.pfb_prototype(n, tpa) if tpa else fd.pfb_prototype(n)
+    frames, block = 300, 64
+    x, _ = synth.pfb_stream(n * frames, 1.0e6 * n / 4.0, n, 21)
+    ch = PfbChannelizer(engine, n, taps, mode, 5.0)
+    iq_ref, fm_ref = ch.process(x)
+    ch.reset()
+    ch.set_out_block(block)
+    nb = -(-frames // block)
+    d_in = engine.to_device(x)
+    d_iq = engine.dev_alloc(nb * n * block * 8) if mode & OUT_IQ else None
+    d_fm = engine.dev_alloc(nb * n * block * 4) if mode & OUT_FM else None
+    nout = ch.process_device(d_in, len(x), d_iq, d_fm, 0)
+    engine.sync()
+    assert nout == frames
+    if mode & OUT_FM:
+        fm = PfbChannelizer.unblock(engine.to_host(d_fm, (nb * n * block,), np.float32), n, frames, block)
+        assert np.array_equal(fm, fm_ref)
+    if mode & OUT_IQ:
+        iq = PfbChannelizer.unblock(engine.to_host(d_iq, (nb * n * block,), np.complex64), n, frames, block)
+        assert np.array_equal(iq, iq_ref)
+    with pytest.raises(Exception):
+        ch.process(x)            # host outputs are plain channel-major only
+    ch.set_out_block(0)
+    with pytest.raises(Exception):
+        ch.set_out_block(12)     # must be a power of two >= 8
