@@ -39,6 +39,10 @@ WORKLOADS = {
                      desc="cfg3 variant: 1024-channel PFB, 16 taps/arm (16384-tap prototype), fused FM demod"),
     "cfg2": dict(nchans=64, ntaps=128, out="iq", log2n=27, streams=1,
                  desc="cfg2: 64-channel PFB, 128-tap prototype, IQ out, one 25 Msps stream"),
+    "cfg4": dict(kind="fft", length=1 << 20, avg=64, log2n=27, streams=1, nchans=0, ntaps=0, out="logpow",
+                 desc="cfg4: 2^20-point streaming FFT (Blackman-Harris) + |.|^2 + log10 + 64-frame sums, 1 Gsps scan"),
+    "cfg4_16k": dict(kind="fft", length=1 << 14, avg=100, log2n=27, streams=1, nchans=0, ntaps=0, out="logpow",
+                     desc="fft_vector.py shape: 16384-point FFT + log-power, 100-frame sums"),
     "cfg5": dict(nchans=256, ntaps=4096, out="fm", log2n=25, streams=8,
                  desc="cfg5: 8 independent 100 Msps streams per GPU x 256 channels, 16 taps/arm, fused FM demod"),
 }
@@ -179,6 +183,23 @@ def allreduce_max(dist, local, v):
 def cpu_run(wl, steps, warmup, log2n_cpu=None, budget_s=None):
     from oracle import gr_cpu
     cfg = WORKLOADS[wl]
+    if cfg.get("kind") == "fft":
+        from oracle import gr_firdes
+        L = cfg["length"]
+        n = max(L * 8, 1 << (log2n_cpu or 23))
+        x = synth_block(n, 1024, 3)
+        w = gr_firdes.blackmanharris(L)
+        threads = gr_cpu.num_threads()
+        gr_cpu.fft_logpow(x[:L * 2], L, w)
+        t0 = time.perf_counter()
+        done = 0
+        for s in range(steps):
+            gr_cpu.fft_logpow(x, L, w)
+            done += 1
+            if budget_s and time.perf_counter() - t0 > budget_s:
+                break
+        dt = time.perf_counter() - t0
+        return done * n / dt / 1e6, threads, done, n, dt
     nch, ntaps = cfg["nchans"], cfg["ntaps"]
     taps = make_taps(nch, ntaps)
     log2n = log2n_cpu or 22
@@ -271,6 +292,38 @@ class StreamCtx(object):
         self.e.close()
 
 
+class FftCtx(object):
+    """Scan path: K3 over a device-resident stream."""
+
+    def __init__(self, device, wl, seed, log2n=None, **kw):
+        from radiocapture_rf_b200.engine import Engine, FftScanner
+        from radiocapture_rf_b200 import firdes
+        cfg = WORKLOADS[wl]
+        self.cfg = cfg
+        self.n = 1 << (log2n or cfg["log2n"])
+        self.L = cfg["length"]
+        self.e = Engine(device)
+        self.sc = FftScanner(self.e, self.L, firdes.blackmanharris(self.L), cfg["avg"])
+        base = synth_block(min(self.n, 1 << 24), 1024, seed)
+        self.d_in = self.e.dev_alloc(self.n * 8)
+        from radiocapture_rf_b200._lib import COPY_H2D, check
+        check(self.e.lib.rcb_memcpy(self.e.h, self.d_in.ptr, base.ctypes.data, base.nbytes, COPY_H2D), "h2d", self.e.h)
+        filled = len(base)
+        while filled < self.n:
+            c = min(filled, self.n - filled)
+            self.e.copy_d2d(self.d_in.ptr + filled * 8, self.d_in.ptr, c * 8)
+            filled += c
+        self.cap = self.n // self.L // cfg["avg"] + 2
+        self.d_out = self.e.dev_alloc(self.cap * self.L * 4)
+        self.bytes_per_sample = 8
+
+    def step(self):
+        self.sc.process_device(self.d_in, self.n, self.d_out, self.cap)
+
+    def close(self):
+        self.e.close()
+
+
 def timed_loop(ctxs, steps, warmup, dist, local):
     for _ in range(warmup):
         for c in ctxs:
@@ -322,6 +375,29 @@ def run_e2e(device, wl, steps, warmup, dist, local, log2n=26):
     return n * steps / dt / 1e6, n * 8, hout.nbytes, chk
 
 
+def run_e2e_fft(device, wl, steps, dist, local, log2n=26):
+    from radiocapture_rf_b200.engine import Engine, FftScanner
+    from radiocapture_rf_b200 import firdes
+    cfg = WORKLOADS[wl]
+    n = 1 << log2n
+    e = Engine(device)
+    sc = FftScanner(e, cfg["length"], firdes.blackmanharris(cfg["length"]), min(cfg["avg"], n // cfg["length"]))
+    hin = e.pinned((n,), np.complex64)
+    base = synth_block(min(n, 1 << 22), 1024, 5)
+    for i in range(0, n, len(base)):
+        hin[i:i + len(base)] = base[:min(len(base), n - i)]
+    out = sc.process(hin)
+    barrier(dist, local)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = sc.process(hin)
+    dt = time.perf_counter() - t0
+    barrier(dist, local)
+    chk = float(out[-1][:8].sum()) if len(out) else 0.0
+    e.close()
+    return n * steps / dt / 1e6, n * 8, int(out.nbytes), chk
+
+
 def run_b200(args):
     world, rank, local, dist = dist_setup(args.gpus)
     device = local if world > 1 else 0
@@ -329,7 +405,9 @@ def run_b200(args):
     cfg = WORKLOADS[wl]
     peak, peak_src = load_peak()
 
-    ctxs = [StreamCtx(device, wl, seed=3 + 100 * rank + i, log2n=args.log2n, out_block=args.out_block)
+    is_fft = cfg.get("kind") == "fft"
+    Ctx = FftCtx if is_fft else StreamCtx
+    ctxs = [Ctx(device, wl, seed=3 + 100 * rank + i, log2n=args.log2n, out_block=args.out_block)
             for i in range(cfg["streams"])]
     sampler = ClockSampler(device)
     sampler.start()
@@ -349,7 +427,7 @@ def run_b200(args):
     tr = load_traffic(wl)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (tr * n_launch_samples) if tr else None, "peak_source": peak_src,
-                "kernel": "pfb_fm_kernel", "algorithmic_bytes_per_launch": n_launch_samples * bps,
+                "kernel": "fft_cols_kernel+fft_rows_kernel" if is_fft else "pfb_fm_tma_kernel", "algorithmic_bytes_per_launch": n_launch_samples * bps,
                 "kernel_ms_per_launch": kern_ms}
     for c in ctxs:
         c.close()
@@ -375,12 +453,15 @@ def run_b200(args):
                                    "value": c16.n * st16 * world / (ms16 * 1e-3) / 1e6, "roofline_frac": a16 / peak}
         c16.close()
 
-    e2e_v, h2d, d2h, chk = run_e2e(device, wl, args.e2e_steps, 1, dist, local)
+    if is_fft:
+        e2e_v, h2d, d2h, chk = run_e2e_fft(device, wl, args.e2e_steps, dist, local)
+    else:
+        e2e_v, h2d, d2h, chk = run_e2e(device, wl, args.e2e_steps, 1, dist, local)
     e2e_v = e2e_v * world if dist is None else allreduce_sum_min(dist, local, e2e_v, world)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cm, threads, done, n, dt = cpu_run(wl, 64, 1, budget_s=12.0)
+        cm, threads, done, n, dt = cpu_run(wl, 100000, 1, budget_s=12.0)
         cpu = {"value": cm, "unit": "Msps", "cores": threads, "kind": "port",
                "sample": "%d x 2^%d samples of the same workload (oracle/gr_cpu.c, %.1f s)" % (done, int(np.log2(n)), dt)}
 

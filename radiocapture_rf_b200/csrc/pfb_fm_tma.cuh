@@ -118,22 +118,13 @@ __global__ void __launch_bounds__(256, 2) pfb_fm_tma_kernel(const PfbParams p) {
     int nxt0 = NI, nxt1 = NI;  // following range (nxt0 >= NI: none)
 
     long long frame0 = (long long)(cur0 - 1) * FPI + warp * F;  // first of this warp's F frames
-    const uint64_t pol_first = l2_policy_evict_first();  // the wideband input is read exactly once
-    const uint64_t pol_last = l2_policy_evict_last();    // output lines are completed by the next 3 iterations
-    bool loaded_once = false;
     auto issue_rows = [&](long long f0) {
-        if ((p.debug_flags & 2) && loaded_once) f0 = -1000000;  // experiment: re-read the (L2 resident) zero row
-        loaded_once = true;
         if (lane == 0) {
             fence_proxy_async();
             mbar_expect_tx(row_bar, (uint32_t)(F * N * 8));
 #pragma unroll
-            for (int q = 0; q < F; ++q) {
-                if (p.debug_flags & 4)
-                    tma_bulk_g2s_hint(work + q * FSW, pfb_row_ptr<R>(p, f0 + q), (uint32_t)(N * 8), row_bar, pol_first);
-                else
-                    tma_bulk_g2s(work + q * FSW, pfb_row_ptr<R>(p, f0 + q), (uint32_t)(N * 8), row_bar);
-            }
+            for (int q = 0; q < F; ++q)
+                tma_bulk_g2s(work + q * FSW, pfb_row_ptr<R>(p, f0 + q), (uint32_t)(N * 8), row_bar);
         }
     };
     issue_rows(frame0);
@@ -226,7 +217,10 @@ __global__ void __launch_bounds__(256, 2) pfb_fm_tma_kernel(const PfbParams p) {
             const long long t0 = (long long)it * FPI + 8 * g;
             int s = base_slot + 8 * g;
             s = (s >= NSLOT) ? s - NSLOT : s;
-            const bool full = (t0 + 8 <= p.T) && !(p.debug_flags & 1);
+            const bool full = (t0 + 8 <= p.T);
+            // (m0, t0) -> element index; consecutive channels are `rowstride` apart in both layouts
+            float* dst0 = p.out_fm + pfb_out_index(p, m0, t0);
+            const long long rowstride = (p.oblock_log2 > 0) ? (1LL << p.oblock_log2) : p.ostride;
             float pw[9][CPT];  // all ring loads first (9 vector LDS), then CPT*8 independent wrap chains
 #pragma unroll
             for (int j = 0; j < 9; ++j) {
@@ -253,13 +247,10 @@ __global__ void __launch_bounds__(256, 2) pfb_fm_tma_kernel(const PfbParams p) {
                     d *= p.gain;
                     o[j] = (d != d) ? 0.0f : d;
                 }
-                float* dst = p.out_fm + pfb_out_index(p, m0 + q, t0);
+                float* dst = dst0 + q * rowstride;
                 if (full) {
-                    if (p.debug_flags & 8)
-                        st_global_v8_hint(dst, o, pol_last);
-                    else
-                        st_global_v8(dst, o);
-                } else if (!(p.debug_flags & 1) || o[0] == 123456.789f) {
+                    st_global_v8(dst, o);
+                } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         if (t0 + j < p.T) dst[j] = o[j];
