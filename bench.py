@@ -189,12 +189,12 @@ def cpu_run(wl, steps, warmup, log2n_cpu=None, budget_s=None):
         n = max(L * 8, 1 << (log2n_cpu or 23))
         x = synth_block(n, 1024, 3)
         w = gr_firdes.blackmanharris(L)
-        threads = gr_cpu.num_threads()
-        gr_cpu.fft_logpow(x[:L * 2], L, w)
+        threads = os.cpu_count() or gr_cpu.num_threads()
+        gr_cpu.fft_logpow(x[:L * 2], L, w, nthreads=threads)
         t0 = time.perf_counter()
         done = 0
         for s in range(steps):
-            gr_cpu.fft_logpow(x, L, w)
+            gr_cpu.fft_logpow(x, L, w, nthreads=threads)
             done += 1
             if budget_s and time.perf_counter() - t0 > budget_s:
                 break
@@ -206,14 +206,14 @@ def cpu_run(wl, steps, warmup, log2n_cpu=None, budget_s=None):
     n = 1 << log2n
     x = synth_block(n, nch, 3)
     want_fm = cfg["out"] == "fm"
-    threads = gr_cpu.num_threads()
+    threads = os.cpu_count() or gr_cpu.num_threads()   # torchrun exports OMP_NUM_THREADS=1: ask explicitly
     hist = None
     for _ in range(max(warmup, 1)):
-        _, _, hist = gr_cpu.pfb_fm(x, nch, taps, 5.0, want_iq=not want_fm, want_fm=want_fm, hist=hist)
+        _, _, hist = gr_cpu.pfb_fm(x, nch, taps, 5.0, want_iq=not want_fm, want_fm=want_fm, hist=hist, nthreads=threads)
     t0 = time.perf_counter()
     done = 0
     for s in range(steps):
-        _, _, hist = gr_cpu.pfb_fm(x, nch, taps, 5.0, want_iq=not want_fm, want_fm=want_fm, hist=hist)
+        _, _, hist = gr_cpu.pfb_fm(x, nch, taps, 5.0, want_iq=not want_fm, want_fm=want_fm, hist=hist, nthreads=threads)
         done += 1
         if budget_s and time.perf_counter() - t0 > budget_s:
             break
@@ -241,7 +241,7 @@ def run_reference(args):
         "e2e": {"value": msps, "unit": "Msps", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -485,7 +485,7 @@ def run_b200(args):
             "clocks": clocks,
             "also": also,
         }
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
@@ -497,7 +497,26 @@ def allreduce_sum_min(dist, local, v, world):
     return sharding.Reducer(dist, "cuda:%d" % local).min(v) * world
 
 
+def _claim_stdout():
+    """Library chatter (NCCL version banners, torchrun notices) must not pollute the one JSON line:
+    fd 1 is pointed at stderr for the whole run and the line is written to the saved original stdout."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
+_OUT = None
+
+
+def emit(line):
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
+
+
 def main():
+    global _OUT
+    _OUT = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

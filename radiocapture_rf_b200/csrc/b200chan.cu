@@ -77,6 +77,7 @@ struct rcb_ctx {
         float2* d_tw = nullptr;
         float2* d_tw_tma = nullptr;  // dense swizzled table for pfb_fm_tma_kernel
         bool use_tma = false;
+
         float2* d_hist[2] = {nullptr, nullptr};
         int hist_cur = 0;
         float2* d_zeros = nullptr;  // one all-zero row
@@ -199,10 +200,10 @@ int pfb_launch_r(rcb_t* h, const PfbParams& p, bool q) {
         default: return pfb_launch_rm<R, PFB_OUT_IQ | PFB_OUT_FM>(h, p, q);
     }
 }
-template <int R>
+template <int R, int W = 8>
 int pfb_launch_tma(rcb_t* h, const PfbParams& p, bool query_only) {
-    using G = PfbTmaGeom<R>;
-    auto kern = pfb_fm_tma_kernel<R>;
+    using G = PfbTmaGeom<R, W>;
+    auto kern = pfb_fm_tma_kernel<R, W>;
     const size_t smem = G::smem_bytes;
     if (query_only) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -228,7 +229,7 @@ int pfb_launch_fast(rcb_t* h, const PfbParams& p, bool q) {
         switch (h->pfb.R) {
             case 8: return pfb_launch_tma<8>(h, p, q);
             case 16: return pfb_launch_tma<16>(h, p, q);
-            case 32: return pfb_launch_tma<32>(h, p, q);
+            case 32: return (h->pfb.variant == 16) ? pfb_launch_tma<32, 16>(h, p, q) : pfb_launch_tma<32>(h, p, q);
         }
     }
     switch (h->pfb.R) {
@@ -245,6 +246,7 @@ void pfb_free(rcb_t* h) {
     cudaFree(s.d_tw);
     cudaFree(s.d_tw_tma);
     s.d_tw_tma = nullptr;
+
     cudaFree(s.d_hist[0]);
     cudaFree(s.d_hist[1]);
     cudaFree(s.d_ys);

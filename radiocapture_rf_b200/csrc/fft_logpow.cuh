@@ -18,6 +18,8 @@
 //   C  fold     : acc[k] += sum over the frames of the sub-batch (fixed order => deterministic);
 //                 when an averaging block of `avg` frames completes the vector is emitted.
 #pragma once
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -51,7 +53,7 @@ struct FftGeom {
                                                      : (N * OS > CB * FS ? N * OS : CB * FS));
     static constexpr size_t a_smem(int L) {
         return (size_t)A_REGION * 8 + (size_t)R * S * 8 + (size_t)(L < 1024 ? L : 1024) * 8 +
-               (size_t)(L / 1024 > 0 ? L / 1024 : 1) * 8;
+               (size_t)(L / 1024 > 0 ? L / 1024 : 1) * 8 + (size_t)CB * R * 8 /* rho */;
     }
     static constexpr size_t b_smem() { return (size_t)CB * FS * 8 + (size_t)R * S * 8; }
 };
@@ -70,6 +72,7 @@ __global__ void __launch_bounds__(256, 2) fft_cols_kernel(const FftParams p) {
     const int nlo = p.L < 1024 ? p.L : 1024;
     float2* thi = tlo + nlo;
     const int nhi = p.L / 1024 > 0 ? p.L / 1024 : 1;
+    float2* rho = thi + nhi;  // [CB][R]: W_L^{-(n2 * R * m2)} per column
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane / R, ll = lane % R;
@@ -91,6 +94,13 @@ __global__ void __launch_bounds__(256, 2) fft_cols_kernel(const FftParams p) {
     }
     __syncthreads();
     const int col = warp * F + fr;  // this lane's column within the CTA
+    // W_L^{-n2 k1}, k1 = ll + R m2, factors as W^{-n2 ll} (per lane) * W^{-n2 R m2} (per column): the
+    // per-column powers go to shared memory once (two-level table, exact), so the per-point twiddle is one
+    // broadcast LDS + one complex multiply instead of two scattered (bank-conflicting) table reads.
+    {
+        const int e = ((c0 + col) * R * ll) & (p.L - 1);
+        rho[col * R + ll] = cmul(tlo[e & 1023], thi[e >> 10]);
+    }
     float2 v[R];
 #pragma unroll
     for (int jj = 0; jj < R; ++jj) v[jj] = region[col * CS + jj * R + ll];
@@ -100,13 +110,13 @@ __global__ void __launch_bounds__(256, 2) fft_cols_kernel(const FftParams p) {
     __syncthreads();  // all per-frame scratch dead: region becomes the [k1][CB] output tile
     {
         const int n2 = c0 + col;
+        const int eb = (n2 * ll) & (p.L - 1);
+        const float2 b = cmul(tlo[eb & 1023], thi[eb >> 10]);
+        const float2* rc = rho + col * R;
 #pragma unroll
         for (int m2 = 0; m2 < R; ++m2) {
             const int k1 = ll + R * m2;
-            const int q = n2 * k1;  // < L1*L2 = L
-            const float2 wl = tlo[q & 1023];
-            const float2 wh = thi[q >> 10];
-            const float2 w = cmul(wl, wh);
+            const float2 w = cmul(b, rc[m2]);
             region[k1 * OS + col] = cmul(v[m2], w);
         }
     }
@@ -254,7 +264,9 @@ inline int fft_config(FftState& s, int L, const float* window, int avg, cudaStre
     s.L2 = r2 * r2;
     s.avg = avg;
     // sub-batch: keep scratch (8 B) + vals (4 B) per sample under ~48 MB so they stay in L2
-    s.sb = (int)std::max<size_t>(1, std::min<size_t>(((size_t)48 << 20) / ((size_t)L * 12), 4096));
+    size_t budget_mb = 48;
+    if (const char* e = getenv("RCB_FFT_SCRATCH_MB")) budget_mb = (size_t)std::max(1, atoi(e));
+    s.sb = (int)std::max<size_t>(1, std::min<size_t>((budget_mb << 20) / ((size_t)L * 12), 4096));
     FCK(cudaMalloc(&s.d_window, sizeof(float) * L));
     FCK(cudaMemcpyAsync(s.d_window, window, sizeof(float) * L, cudaMemcpyHostToDevice, st));
     auto t1 = fft_tw_table(r1, s.L1), t2 = fft_tw_table(r2, s.L2);

@@ -19,12 +19,12 @@
 
 namespace rcb {
 
-template <int R>
+template <int R, int W = 8>
 struct PfbTmaGeom {
     static constexpr int N = R * R;
     static constexpr int F = 32 / R;
-    static constexpr int WARPS = 8;
-    static constexpr int THREADS = 256;
+    static constexpr int WARPS = W;
+    static constexpr int THREADS = 32 * W;
     static constexpr int FPI = WARPS * F;
     static constexpr int NSLOT = FPI + 1;
     static constexpr int FSW = N + (R == 8 ? 8 : 0);       // frame stride inside a warp's work buffer (complex)
@@ -33,7 +33,7 @@ struct PfbTmaGeom {
     static constexpr size_t ring_bytes = (size_t)NSLOT * N * 4;
     static constexpr size_t tw_bytes = (size_t)N * 8;
     static constexpr size_t taps_bytes = (size_t)N * 4;
-    static constexpr size_t smem_bytes = work_bytes + ring_bytes + tw_bytes + taps_bytes + 128;
+    static constexpr size_t smem_bytes = work_bytes + ring_bytes + tw_bytes + taps_bytes + 256;
 };
 
 template <int R>
@@ -65,9 +65,10 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // twiddle table layout expected in p.twiddle for this kernel: dense [R][R] complex, 16-byte chunks swizzled:
 //   tw[ll*R + (((m1>>1) ^ swz(ll))<<1 | (m1&1))] = W_N^{+(R-1-ll) m1}
 // taps layout: float4 groups as in pfb_fm.cuh (P = 1).
-template <int R>
-__global__ void __launch_bounds__(256, 2) pfb_fm_tma_kernel(const PfbParams p) {
-    using G = PfbTmaGeom<R>;
+template <int R, int W = 8>
+__global__ void __launch_bounds__(32 * W, 16 / W) pfb_fm_tma_kernel(const PfbParams p) {
+    using G = PfbTmaGeom<R, W>;
+    constexpr int THREADS = G::THREADS;
     constexpr int N = G::N, F = G::F, FPI = G::FPI, NSLOT = G::NSLOT, FSW = G::FSW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float2* work_all = reinterpret_cast<float2*>(smem_raw);
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(256, 2) pfb_fm_tma_kernel(const PfbParams p) {
     float2* tws = reinterpret_cast<float2*>(smem_raw + G::work_bytes + G::ring_bytes);
     float* taps_s = reinterpret_cast<float*>(smem_raw + G::work_bytes + G::ring_bytes + G::tw_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + G::work_bytes + G::ring_bytes + G::tw_bytes + G::taps_bytes);
-    uint64_t* cta_bar = bars + 8;
+    uint64_t* cta_bar = bars + W;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane / R, ll = lane % R;
@@ -83,12 +84,12 @@ __global__ void __launch_bounds__(256, 2) pfb_fm_tma_kernel(const PfbParams p) {
     float2* wf = work + fr * FSW;               // this lane's frame inside it
     uint64_t* row_bar = bars + warp;
 
-    for (int i = tid; i < N; i += 256) {
+    for (int i = tid; i < N; i += THREADS) {
         tws[i] = p.twiddle[i];
         taps_s[i] = p.taps[i];
     }
-    if (tid < 8) mbar_init(bars + tid, 1);
-    if (tid == 8) mbar_init(cta_bar, 256);
+    if (tid < W) mbar_init(bars + tid, 1);
+    if (tid == W) mbar_init(cta_bar, THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     const float4* tap4 = reinterpret_cast<const float4*>(taps_s);
@@ -211,13 +212,13 @@ __global__ void __launch_bounds__(256, 2) pfb_fm_tma_kernel(const PfbParams p) {
 
         // ---- demod: 8 consecutive frames of CPT channels per thread ----
         if (it >= cur0) {
-            constexpr int CPT = N * (FPI / 8) / 256;  // 4, 2, 1 for R = 32, 16, 8
+            constexpr int CPT = N * (FPI / 8) / THREADS;  // 4, 2, 1 for R = 32, 16, 8
             const int g = tid / (N / CPT);
             const int m0 = (tid % (N / CPT)) * CPT;
             const long long t0 = (long long)it * FPI + 8 * g;
             int s = base_slot + 8 * g;
             s = (s >= NSLOT) ? s - NSLOT : s;
-            const bool full = (t0 + 8 <= p.T);
+            const bool full = (t0 + 8 <= p.T) && !(p.debug_flags & 1);  // RCB_PFB_DEBUG=1: measurement only
             // (m0, t0) -> element index; consecutive channels are `rowstride` apart in both layouts
             float* dst0 = p.out_fm + pfb_out_index(p, m0, t0);
             const long long rowstride = (p.oblock_log2 > 0) ? (1LL << p.oblock_log2) : p.ostride;
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(256, 2) pfb_fm_tma_kernel(const PfbParams p) {
                 float* dst = dst0 + q * rowstride;
                 if (full) {
                     st_global_v8(dst, o);
-                } else {
+                } else if (!(p.debug_flags & 1) || o[0] == 123456.789f) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         if (t0 + j < p.T) dst[j] = o[j];
