@@ -39,6 +39,10 @@ WORKLOADS = {
                      desc="cfg3 variant: 1024-channel PFB, 16 taps/arm (16384-tap prototype), fused FM demod"),
     "cfg2": dict(nchans=64, ntaps=128, out="iq", log2n=27, streams=1,
                  desc="cfg2: 64-channel PFB, 128-tap prototype, IQ out, one 25 Msps stream"),
+    "cfg1": dict(kind="ddc", fs=2.4e6, rate=12500, nchan=1, log2n=24, streams=1, nchans=1, ntaps=349, out="iq+fm",
+                 desc="cfg1: 1-channel freq_xlating_fir (D 96, 349 taps, -62.5 kHz) + FM quad demod on 2.4 Msps IQ"),
+    "ddc64": dict(kind="ddc", fs=16.0e6, rate=12500, nchan=64, log2n=24, streams=1, nchans=64, ntaps=2327, out="iq+fm",
+                  desc="64 simultaneous channel.py channels (D 640, 2327 taps) + FM on one 16 Msps source"),
     "cfg4": dict(kind="fft", length=1 << 20, avg=64, log2n=27, streams=1, nchans=0, ntaps=0, out="logpow",
                  desc="cfg4: 2^20-point streaming FFT (Blackman-Harris) + |.|^2 + log10 + 64-frame sums, 1 Gsps scan"),
     "cfg4_16k": dict(kind="fft", length=1 << 14, avg=100, log2n=27, streams=1, nchans=0, ntaps=0, out="logpow",
@@ -200,6 +204,27 @@ def cpu_run(wl, steps, warmup, log2n_cpu=None, budget_s=None):
                 break
         dt = time.perf_counter() - t0
         return done * n / dt / 1e6, threads, done, n, dt
+    if cfg.get("kind") == "ddc":
+        from oracle import gr_firdes
+        fs, rate = cfg["fs"], cfg["rate"]
+        decim, taps = gr_firdes.channel_taps(fs, rate)
+        n = 1 << (log2n_cpu or 22)
+        x = synth_block(n, 64, 3)
+        threads = os.cpu_count() or gr_cpu.num_threads()
+        rng = np.random.default_rng(3)
+        offs = [-62500.0] if cfg["nchan"] == 1 else list(rng.uniform(-0.45 * fs, 0.45 * fs, cfg["nchan"]))
+        gr_cpu.xlating_fir(x[:1 << 16], taps, decim, offs[0], fs, nthreads=threads)
+        t0 = time.perf_counter()
+        done = 0
+        for s in range(steps):
+            for f in offs:  # GNU Radio: one flowgraph (and one full-rate copy) per channel
+                y = gr_cpu.xlating_fir(x, taps, decim, f, fs, nthreads=threads)
+                gr_cpu.quad_demod(y, 5.0)
+            done += 1
+            if budget_s and time.perf_counter() - t0 > budget_s:
+                break
+        dt = time.perf_counter() - t0
+        return done * n / dt / 1e6, threads, done, n, dt
     nch, ntaps = cfg["nchans"], cfg["ntaps"]
     taps = make_taps(nch, ntaps)
     log2n = log2n_cpu or 22
@@ -324,6 +349,34 @@ class FftCtx(object):
         self.e.close()
 
 
+class DdcCtx(object):
+    """xlat mode: M rc_frontend/channel.py channels over one device-resident wideband block (K2)."""
+
+    def __init__(self, device, wl, seed, log2n=None, **kw):
+        from radiocapture_rf_b200.engine import Engine, DdcBank, OUT_FM, OUT_IQ
+        from radiocapture_rf_b200 import firdes
+        cfg = WORKLOADS[wl]
+        self.cfg = cfg
+        self.n = 1 << (log2n or cfg["log2n"])
+        self.e = Engine(device)
+        self.bank = DdcBank(self.e)
+        fs, rate = cfg["fs"], cfg["rate"]
+        decim = firdes.channel_decimation(fs, rate)
+        taps = firdes.low_pass_2(1.0, fs, rate / 2, rate / 2, 20.0, firdes.WIN_HAMMING)
+        rng = np.random.default_rng(seed)
+        offs = [-62500.0] if cfg["nchan"] == 1 else list(rng.uniform(-0.45 * fs, 0.45 * fs, cfg["nchan"]))
+        self.ids = [self.bank.open(decim, taps, f, fs, OUT_IQ | OUT_FM, 5.0) for f in offs]
+        x = synth_block(self.n, 64, seed)
+        self.d_in = self.e.to_device(x)
+        self.bytes_per_sample = 8.0 + cfg["nchan"] * 12.0 / decim
+
+    def step(self):
+        self.bank.process_device(self.d_in, self.n)
+
+    def close(self):
+        self.e.close()
+
+
 def timed_loop(ctxs, steps, warmup, dist, local):
     for _ in range(warmup):
         for c in ctxs:
@@ -375,6 +428,32 @@ def run_e2e(device, wl, steps, warmup, dist, local, log2n=26):
     return n * steps / dt / 1e6, n * 8, hout.nbytes, chk
 
 
+def run_e2e_ddc(device, wl, steps, dist, local, log2n=24):
+    """Host block in -> all channels' IQ+FM pulled back to the host (what SourceStream.push does)."""
+    from radiocapture_rf_b200.engine import OUT_FM, OUT_IQ
+    ctx = DdcCtx(device, wl, seed=5, log2n=log2n)
+    n = ctx.n
+    hin = ctx.e.pinned((n,), np.complex64)
+    hin[:] = synth_block(n, 64, 5)
+    ctx.bank.process(hin)
+    barrier(dist, local)
+    t0 = time.perf_counter()
+    d2h = 0
+    chk = 0.0
+    for _ in range(steps):
+        ctx.bank.process(hin)
+        d2h = 0
+        for cid in ctx.ids:
+            y = ctx.bank.pull(cid, OUT_IQ)
+            f = ctx.bank.pull(cid, OUT_FM)
+            d2h += y.nbytes + f.nbytes
+            chk += float(f[-1])
+    dt = time.perf_counter() - t0
+    barrier(dist, local)
+    ctx.close()
+    return n * steps / dt / 1e6, n * 8, d2h, chk
+
+
 def run_e2e_fft(device, wl, steps, dist, local, log2n=26):
     from radiocapture_rf_b200.engine import Engine, FftScanner
     from radiocapture_rf_b200 import firdes
@@ -406,7 +485,8 @@ def run_b200(args):
     peak, peak_src = load_peak()
 
     is_fft = cfg.get("kind") == "fft"
-    Ctx = FftCtx if is_fft else StreamCtx
+    is_ddc = cfg.get("kind") == "ddc"
+    Ctx = FftCtx if is_fft else (DdcCtx if is_ddc else StreamCtx)
     ctxs = [Ctx(device, wl, seed=3 + 100 * rank + i, log2n=args.log2n, out_block=args.out_block)
             for i in range(cfg["streams"])]
     sampler = ClockSampler(device)
@@ -427,7 +507,8 @@ def run_b200(args):
     tr = load_traffic(wl)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (tr * n_launch_samples) if tr else None, "peak_source": peak_src,
-                "kernel": "fft_cols_kernel+fft_rows_kernel" if is_fft else "pfb_fm_tma_kernel", "algorithmic_bytes_per_launch": n_launch_samples * bps,
+                "kernel": "fft_cols_kernel+fft_rows_kernel" if is_fft else ("ddc_bank_kernel" if is_ddc else "pfb_fm_tma_kernel"),
+                "algorithmic_bytes_per_launch": n_launch_samples * bps,
                 "kernel_ms_per_launch": kern_ms}
     for c in ctxs:
         c.close()
@@ -455,6 +536,8 @@ def run_b200(args):
 
     if is_fft:
         e2e_v, h2d, d2h, chk = run_e2e_fft(device, wl, args.e2e_steps, dist, local)
+    elif is_ddc:
+        e2e_v, h2d, d2h, chk = run_e2e_ddc(device, wl, args.e2e_steps, dist, local)
     else:
         e2e_v, h2d, d2h, chk = run_e2e(device, wl, args.e2e_steps, 1, dist, local)
     e2e_v = e2e_v * world if dist is None else allreduce_sum_min(dist, local, e2e_v, world)

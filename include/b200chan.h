@@ -119,6 +119,16 @@ int rcb_quad_demod(rcb_t* h, const void* iq, size_t rows, size_t n, size_t in_st
 int rcb_probe_mean(rcb_t* h, const void* x, size_t rows, size_t n, size_t stride, size_t length,
                    float scale, void* out, int mem);
 
+/* ---- K5: ingest conversion -----------------------------------------------------
+ * Interleaved integer I/Q as the SDR delivers it -> complex64: out = (v + offset) * scale.
+ * RCB_FMT_U8 with (offset -127.4, scale 1/128) is gr-osmosdr's rtl_source_c mapping (RTL-SDR sources of every
+ * shipped rtlsdr config), RCB_FMT_S8 / RCB_FMT_S16 are UHD's sc8 / sc16 wire formats
+ * (configs/config_denver_usrp.py:20 otw_format).  src holds 2*nsamples integers; dst nsamples complex64.
+ * src_mem / dst_mem: RCB_MEM_HOST or RCB_MEM_DEVICE (host src = 2-4x fewer PCIe bytes than complex64). */
+enum { RCB_FMT_U8 = 1, RCB_FMT_S8 = 2, RCB_FMT_S16 = 3 };
+int rcb_convert_iq(rcb_t* h, const void* src, int fmt, float offset, float scale, size_t nsamples, int src_mem,
+                   void* dst, int dst_mem);
+
 /* ---- K3: streaming windowed FFT + log-power accumulation ---------------------------------------
  * Replaces stream_to_vector -> fft.fft_vcc(L, True, window, True) -> complex_to_mag_squared ->
  * nlog10_ff(1, L, 1) -> moving_average_ff(avg, 1, ...)             fft_vector.py:37-60.

@@ -23,6 +23,9 @@ MEM_HOST = 0
 MEM_DEVICE = 1
 OUT_IQ = 1
 OUT_FM = 2
+FMT_U8 = 1
+FMT_S8 = 2
+FMT_S16 = 3
 COPY_H2D = 1
 COPY_D2H = 2
 COPY_D2D = 3
@@ -77,6 +80,7 @@ _PROTOTYPES = {
     "rcb_ddc_pull": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _sz, C.c_int, C.POINTER(_sz)]),
     "rcb_quad_demod": (C.c_int, [_vp, _vp, _sz, _sz, _sz, C.c_float, _vp, _vp, _sz, C.c_int]),
     "rcb_probe_mean": (C.c_int, [_vp, _vp, _sz, _sz, _sz, _sz, C.c_float, _vp, C.c_int]),
+    "rcb_convert_iq": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_float, _sz, C.c_int, _vp, C.c_int]),
     "rcb_fft_config": (C.c_int, [_vp, C.c_int, _vp, C.c_int]),
     "rcb_fft_reset": (C.c_int, [_vp]),
     "rcb_fft_process": (C.c_int, [_vp, _vp, _sz, C.c_int, _vp, _sz, C.c_int, C.POINTER(_sz)]),

@@ -105,6 +105,10 @@ struct rcb_ctx {
         DdcChanDev* d_chans = nullptr;
         DdcChanDev* h_chans = nullptr;  // pinned
         size_t chans_cap = 0;
+        DdcGroupDev* d_groups = nullptr;
+        DdcGroupDev* h_groups = nullptr;  // pinned
+        size_t groups_cap = 0;
+        size_t tile_smem_attr = 0;
     } ddc;
 
     // ---- FFT ----
@@ -421,6 +425,8 @@ extern "C" int rcb_close(rcb_t* h) {
     cudaFree(h->ddc.d_in);
     cudaFree(h->ddc.d_chans);
     if (h->ddc.h_chans) cudaFreeHost(h->ddc.h_chans);
+    cudaFree(h->ddc.d_groups);
+    if (h->ddc.h_groups) cudaFreeHost(h->ddc.h_groups);
     fft_free(h->fft);
     cudaFree(h->d_tmp[0]);
     cudaFree(h->d_tmp[1]);
@@ -800,7 +806,10 @@ extern "C" int rcb_ddc_open(rcb_t* h, int decim, const float* taps, int ntaps, d
     c.center_freq = center_freq;
     c.samp_rate = samp_rate;
     c.taps.assign(taps, taps + ntaps);
-    c.start_sample = h->ddc.n_consumed;
+    // all channels of a source with the same decimation share one decimation grid (outputs at stream
+    // positions that are multiples of decim): a channel opened mid-stream starts at the next grid point.
+    // (A GNU Radio channel block starts at whatever sample its ZMQ SUB happens to receive first.)
+    c.start_sample = ((h->ddc.n_consumed + (uint64_t)decim - 1) / (uint64_t)decim) * (uint64_t)decim;
     rc = ddc_upload_taps(h, c);
     if (rc) return rc;
     CK(cudaMalloc(&c.d_prev, sizeof(float2)));
@@ -924,18 +933,91 @@ extern "C" int rcb_ddc_process(rcb_t* h, const void* iq, size_t nsamples, int in
             dv.decim = c.decim;
             dv.nout = (int)nout;
             dv.gain = c.gain;
+            // fast path needs every window sample of this block to lie at / after the channel's first sample
+            dv.fast = (nout > 0 && dv.s_open <= dv.s_first - (long long)(c.ntaps - 1) &&
+                       (size_t)(7 * c.decim + c.ntaps) * sizeof(float2) <= 160 * 1024) ? 1 : 0;
             c.nout_last = nout;
             c.i_next += nout;
             max_nout = std::max(max_nout, nout);
             any_fm |= (dv.out_fm != nullptr);
             h->stats.channel_samples += nout;
         }
+        // group the fast channels by (decim, ntaps, s_first, nout), 16 per work group
+        std::map<std::vector<long long>, std::vector<int>> buckets;
+        bool any_slow = false;
+        for (size_t i = 0; i < M; ++i) {
+            const DdcChanDev& dv = d.h_chans[i];
+            if (dv.fast)
+                buckets[{dv.decim, dv.ntaps, dv.s_first, dv.nout}].push_back((int)i);
+            else if (dv.nout > 0)
+                any_slow = true;
+        }
+        size_t ngroups = 0;
+        for (auto& b : buckets) ngroups += (b.second.size() + 15) / 16;
+        if (ngroups > d.groups_cap) {
+            cudaFree(d.d_groups);
+            if (d.h_groups) cudaFreeHost(d.h_groups);
+            d.d_groups = nullptr;
+            d.h_groups = nullptr;
+            d.groups_cap = 0;
+            const size_t cap = std::max<size_t>(8, ngroups * 2);
+            CK(cudaMalloc(&d.d_groups, cap * sizeof(DdcGroupDev)));
+            CK(cudaHostAlloc(&d.h_groups, cap * sizeof(DdcGroupDev), cudaHostAllocDefault));
+            d.groups_cap = cap;
+        }
         CK(cudaMemcpyAsync(d.d_chans, d.h_chans, M * sizeof(DdcChanDev), cudaMemcpyHostToDevice, h->stream));
         if (max_nout) {
-            dim3 grid((unsigned)((max_nout + 8 * kDdcOutPerWarp - 1) / (8 * kDdcOutPerWarp)), (unsigned)M);
-            ddc_bank_kernel<<<grid, 256, 0, h->stream>>>(d.d_chans, d_x, (long long)nsamples, d.d_hist[d.hist_cur],
-                                                        kDdcHistCap);
-            CKL(h);
+            size_t gi = 0;
+            for (auto& b : buckets) {
+                const size_t first_group = gi;
+                for (size_t off = 0; off < b.second.size(); off += 16) {
+                    DdcGroupDev& g = d.h_groups[gi++];
+                    g.nch = (int)std::min<size_t>(16, b.second.size() - off);
+                    for (int u = 0; u < 16; ++u) g.ch[u] = (u < g.nch) ? b.second[off + u] : -1;
+                    g.decim = (int)b.first[0];
+                    g.ntaps = (int)b.first[1];
+                    g.s_first = b.first[2];
+                    g.nout = (int)b.first[3];
+                }
+                (void)first_group;
+            }
+            if (ngroups) {
+                CK(cudaMemcpyAsync(d.d_groups, d.h_groups, ngroups * sizeof(DdcGroupDev), cudaMemcpyHostToDevice, h->stream));
+                gi = 0;
+                for (auto& b : buckets) {
+                    const size_t ng = (b.second.size() + 15) / 16;
+                    const int decim = (int)b.first[0], ntaps = (int)b.first[1], nout = (int)b.first[3];
+                    // output quads per CTA: as many as the group's channel count leaves warps for and smem allows
+                    const size_t per_group = std::min<size_t>(16, b.second.size());
+                    int oq = per_group <= 4 ? 8 : (per_group <= 8 ? 4 : 2);
+                    while (oq > 2 && (size_t)((4 * oq - 1) * decim + ntaps) * sizeof(float2) > 160 * 1024) oq >>= 1;
+                    const size_t smem = (size_t)((4 * oq - 1) * decim + ntaps) * sizeof(float2);
+                    if (smem > d.tile_smem_attr) {
+                        CK(cudaFuncSetAttribute(ddc_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        CK(cudaFuncSetAttribute(ddc_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        CK(cudaFuncSetAttribute(ddc_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        d.tile_smem_attr = smem;
+                    }
+                    dim3 grid((unsigned)((nout + 4 * oq - 1) / (4 * oq)), (unsigned)ng);
+                    if (oq == 8)
+                        ddc_tile_kernel<8><<<grid, 256, smem, h->stream>>>(d.d_chans, d.d_groups + gi, d_x, (long long)nsamples,
+                                                                           d.d_hist[d.hist_cur], kDdcHistCap);
+                    else if (oq == 4)
+                        ddc_tile_kernel<4><<<grid, 256, smem, h->stream>>>(d.d_chans, d.d_groups + gi, d_x, (long long)nsamples,
+                                                                           d.d_hist[d.hist_cur], kDdcHistCap);
+                    else
+                        ddc_tile_kernel<2><<<grid, 256, smem, h->stream>>>(d.d_chans, d.d_groups + gi, d_x, (long long)nsamples,
+                                                                           d.d_hist[d.hist_cur], kDdcHistCap);
+                    CKL(h);
+                    gi += ng;
+                }
+            }
+            if (any_slow) {
+                dim3 grid((unsigned)((max_nout + 8 * kDdcOutPerWarp - 1) / (8 * kDdcOutPerWarp)), (unsigned)M);
+                ddc_bank_kernel<<<grid, 256, 0, h->stream>>>(d.d_chans, d_x, (long long)nsamples, d.d_hist[d.hist_cur],
+                                                            kDdcHistCap);
+                CKL(h);
+            }
             if (any_fm) {
                 dim3 g2((unsigned)((max_nout + 255) / 256), (unsigned)M);
                 ddc_fm_kernel<<<g2, 256, 0, h->stream>>>(d.d_chans);
@@ -1046,6 +1128,51 @@ extern "C" int rcb_probe_mean(rcb_t* h, const void* x, size_t rows, size_t n, si
     CKL(h);
     if (mem == RCB_MEM_HOST) CK(cudaMemcpyAsync(out, d_o, rows * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return RCB_OK;
+}
+
+// =================================================================================================
+// K5  ingest conversion
+// =================================================================================================
+extern "C" int rcb_convert_iq(rcb_t* h, const void* src, int fmt, float offset, float scale, size_t nsamples,
+                              int src_mem, void* dst, int dst_mem) {
+    if (!h || (!src && nsamples) || (!dst && nsamples)) return RCB_EINVAL;
+    if (fmt != RCB_FMT_U8 && fmt != RCB_FMT_S8 && fmt != RCB_FMT_S16) return RCB_EINVAL;
+    if ((src_mem != RCB_MEM_HOST && src_mem != RCB_MEM_DEVICE) || (dst_mem != RCB_MEM_HOST && dst_mem != RCB_MEM_DEVICE))
+        return RCB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    if (nsamples == 0) return RCB_OK;
+    const size_t esz = (fmt == RCB_FMT_S16) ? 2 : 1;
+    const size_t inb = nsamples * 2 * esz, outb = nsamples * sizeof(float2);
+    const void* d_src = src;
+    float2* d_dst = (float2*)dst;
+    if (src_mem == RCB_MEM_HOST) {
+        int rc = ensure_tmp(h, 0, inb + 16);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(h->d_tmp[0], src, inb, cudaMemcpyHostToDevice, h->stream));
+        h->stats.h2d_bytes += inb;
+        d_src = h->d_tmp[0];
+    } else if (((uintptr_t)src) & 15) {
+        return RCB_EINVAL;  // vector loads need 16-byte aligned device input
+    }
+    if (dst_mem == RCB_MEM_HOST) {
+        int rc = ensure_tmp(h, 1, outb);
+        if (rc) return rc;
+        d_dst = (float2*)h->d_tmp[1];
+    }
+    const unsigned grid = (unsigned)((nsamples + 1023) / 1024);
+    if (fmt == RCB_FMT_U8)
+        convert_iq_kernel<uint8_t><<<grid, 256, 0, h->stream>>>((const uint8_t*)d_src, d_dst, (long long)nsamples, offset, scale);
+    else if (fmt == RCB_FMT_S8)
+        convert_iq_kernel<int8_t><<<grid, 256, 0, h->stream>>>((const int8_t*)d_src, d_dst, (long long)nsamples, offset, scale);
+    else
+        convert_iq_kernel<int16_t><<<grid, 256, 0, h->stream>>>((const int16_t*)d_src, d_dst, (long long)nsamples, offset, scale);
+    CKL(h);
+    if (dst_mem == RCB_MEM_HOST) {
+        CK(cudaMemcpyAsync(dst, d_dst, outb, cudaMemcpyDeviceToHost, h->stream));
+        h->stats.d2h_bytes += outb;
+    }
+    if (src_mem == RCB_MEM_HOST || dst_mem == RCB_MEM_HOST) CK(cudaStreamSynchronize(h->stream));
     return RCB_OK;
 }
 

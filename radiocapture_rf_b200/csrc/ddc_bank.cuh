@@ -33,6 +33,7 @@ struct DdcChanDev {
     int decim;
     int nout;
     float gain;
+    int fast;                 // 1: this block is computed by ddc_tile_kernel, ddc_bank_kernel skips it
 };
 
 __device__ __forceinline__ float2 ddc_x_at(const float2* __restrict__ x, const float2* __restrict__ hist,
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(256) ddc_bank_kernel(const DdcChanDev* __restr
     const DdcChanDev ch = chans[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int o0 = (blockIdx.x * 8 + warp) * kDdcOutPerWarp;
-    if (o0 >= ch.nout) return;
+    if (ch.fast || o0 >= ch.nout) return;
     float2 acc[kDdcOutPerWarp];
 #pragma unroll
     for (int q = 0; q < kDdcOutPerWarp; ++q) acc[q] = make_float2(0.f, 0.f);
@@ -89,6 +90,103 @@ __global__ void __launch_bounds__(256) ddc_bank_kernel(const DdcChanDev* __restr
             sincospi(-2.0 * ph, &s, &c);
             const float cf = (float)c, sf = (float)s;
             ch.out_iq[o] = make_float2(fmaf(a.x, cf, -a.y * sf), fmaf(a.x, sf, a.y * cf));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tiled fast path.  Channels of one source that share (decim, ntaps) sit on a common decimation grid
+// (outputs at stream positions that are multiples of decim), so they need the SAME input windows.
+// A CTA stages the window of 8 consecutive outputs (7*D + K samples) in shared memory once and its 8
+// warps form a 2 x 4 grid of (output quad, channel quad): every lane keeps 4 outputs x 4 channels = 16
+// complex accumulators, so one tap step costs 4 LDS (samples) + 4 LDG (composite taps, coalesced, L1/L2
+// resident) for 64 FMAs - versus 5 loads per 16 FMAs and per-element bounds checks in ddc_bank_kernel,
+// which stays as the path for channels opened inside the current windows (zero-history gating).
+// ------------------------------------------------------------------------------------------------
+struct DdcGroupDev {
+    int ch[16];        // indices into the DdcChanDev array, -1 = unused
+    int nch;
+    int decim, ntaps, nout;
+    long long s_first;
+};
+
+// OQ = output quads per CTA (8 / 4 / 2 for groups of <= 4 / <= 8 / <= 16 channels), 8/OQ channel quads.
+// grid (ceil(nout / (4*OQ)), ngroups), block 256, dynamic smem ((4*OQ-1)*decim + ntaps) * 8 bytes
+template <int OQ>
+__global__ void __launch_bounds__(256) ddc_tile_kernel(const DdcChanDev* __restrict__ chans,
+                                                       const DdcGroupDev* __restrict__ groups,
+                                                       const float2* __restrict__ x, long long nsamp,
+                                                       const float2* __restrict__ hist, int hist_cap) {
+    extern __shared__ __align__(16) float2 ddc_tile[];
+    const DdcGroupDev& g = groups[blockIdx.y];
+    const int o_base = blockIdx.x * (4 * OQ);
+    if (o_base >= g.nout) return;
+    const int D = g.decim, K = g.ntaps;
+    const long long w0 = g.s_first + (long long)o_base * D - (K - 1);
+    const int tile_len = (4 * OQ - 1) * D + K;
+    for (int t = threadIdx.x; t < tile_len; t += 256) {
+        const long long idx = w0 + t;
+        ddc_tile[t] = (idx < nsamp) ? ddc_x_at(x, hist, hist_cap, idx) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int oq = warp % OQ, cq = warp / OQ;
+    if (cq * 4 >= g.nch || o_base + oq * 4 >= g.nout) return;
+    int cidx[4];
+    const float2* tp[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        cidx[i] = g.ch[cq * 4 + i];
+        tp[i] = chans[cidx[i] >= 0 ? cidx[i] : g.ch[cq * 4]].ctaps_rev;
+    }
+    float2 acc[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[q][i] = make_float2(0.f, 0.f);
+    const float2* xt = ddc_tile + (oq * 4) * D;
+    for (int r = lane; r < K; r += 32) {
+        float2 xv[4], tv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) xv[q] = xt[q * D + r];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tv[i] = __ldg(tp[i] + r);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc[q][i].x = fmaf(tv[i].x, xv[q].x, fmaf(-tv[i].y, xv[q].y, acc[q][i].x));
+                acc[q][i].y = fmaf(tv[i].x, xv[q].y, fmaf(tv[i].y, xv[q].x, acc[q][i].y));
+            }
+    }
+    float2 mine = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 a = acc[q][i];
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) {
+                a.x += __shfl_xor_sync(0xffffffffu, a.x, sft);
+                a.y += __shfl_xor_sync(0xffffffffu, a.y, sft);
+            }
+            if (lane == q * 4 + i) mine = a;
+        }
+    if (lane < 16) {
+        const int q = lane >> 2, i = lane & 3;
+        const int o = o_base + oq * 4 + q;
+        int ci = cidx[0];
+#pragma unroll
+        for (int u = 1; u < 4; ++u)
+            if (i == u) ci = cidx[u];
+        if (ci >= 0 && o < g.nout) {
+            const DdcChanDev& ch = chans[ci];
+            double ph = ch.phase0 + ch.cyc * (double)o;
+            ph -= floor(ph);
+            double sn, cs;
+            sincospi(-2.0 * ph, &sn, &cs);
+            const float cf = (float)cs, sf = (float)sn;
+            ch.out_iq[o] = make_float2(fmaf(mine.x, cf, -mine.y * sf), fmaf(mine.x, sf, mine.y * cf));
         }
     }
 }

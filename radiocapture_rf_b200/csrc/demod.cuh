@@ -68,6 +68,36 @@ __global__ void __launch_bounds__(256) pfb_generic_emit_kernel(const float2* __r
     }
 }
 
+// K5  ingest conversion: interleaved integer I/Q as the SDR delivers it over the wire -> complex64.
+//   fmt 1: u8  offset-binary (RTL-SDR; gr-osmosdr rtl_source_c: (v - 127.4) / 128)
+//   fmt 2: s8  (USRP otw_format sc8, configs/config_denver_usrp.py:20)        fmt 3: s16 (sc16)
+// out = (v + offset) * scale, 4 samples per thread (8..16 B in, 32 B out).  SURVEY 8(f) row 4.
+template <typename T>
+__global__ void __launch_bounds__(256) convert_iq_kernel(const T* __restrict__ in, float2* __restrict__ out,
+                                                         long long nsamp, float offset, float scale) {
+    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= nsamp) return;
+    if (i0 + 4 <= nsamp) {
+        T v[8];
+        if constexpr (sizeof(T) == 1) {
+            const uint2 w = *reinterpret_cast<const uint2*>(in + 2 * i0);
+            *reinterpret_cast<uint2*>(v) = w;
+        } else {
+            const uint4 w = *reinterpret_cast<const uint4*>(in + 2 * i0);
+            *reinterpret_cast<uint4*>(v) = w;
+        }
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = ((float)v[j] + offset) * scale;
+        float4* o = reinterpret_cast<float4*>(out + i0);
+        o[0] = make_float4(f[0], f[1], f[2], f[3]);
+        o[1] = make_float4(f[4], f[5], f[6], f[7]);
+    } else {
+        for (long long i = i0; i < nsamp; ++i)
+            out[i] = make_float2(((float)in[2 * i] + offset) * scale, ((float)in[2 * i + 1] + offset) * scale);
+    }
+}
+
 // one CTA per row: scale * sum of x[r][n-length .. n-1] (clamped at 0), double accumulate.
 __global__ void __launch_bounds__(256) window_sum_rows_kernel(const float* __restrict__ x, long long xs,
                                                               long long n, long long length, float scale,

@@ -119,6 +119,28 @@ class Engine(object):
         check(self.lib.rcb_timer_stop(self.h, C.byref(ms)), "rcb_timer_stop", self.h)
         return ms.value
 
+    # ---- K5 --------------------------------------------------------------------------------------
+    _FMT = {"u8": (_lib.FMT_U8, np.uint8, -127.4, 1.0 / 128.0),     # gr-osmosdr rtl_source_c
+            "s8": (_lib.FMT_S8, np.int8, 0.0, 1.0 / 128.0),         # UHD sc8
+            "s16": (_lib.FMT_S16, np.int16, 0.0, 1.0 / 32768.0)}    # UHD sc16
+
+    def convert_iq(self, raw, fmt, offset=None, scale=None, out_device=None):
+        """Interleaved integer I/Q (host array) -> complex64.  Returns a host array, or fills `out_device`."""
+        code, dt, off, sc = self._FMT[fmt]
+        raw = np.ascontiguousarray(raw, dtype=dt)
+        n = raw.size // 2
+        off = off if offset is None else float(offset)
+        sc = sc if scale is None else float(scale)
+        if out_device is not None:
+            ptr = out_device.ptr if isinstance(out_device, DeviceBuffer) else out_device
+            check(self.lib.rcb_convert_iq(self.h, raw.ctypes.data, code, off, sc, n, MEM_HOST, ptr, MEM_DEVICE),
+                  "rcb_convert_iq", self.h)
+            return n
+        out = np.empty(n, dtype=np.complex64)
+        check(self.lib.rcb_convert_iq(self.h, raw.ctypes.data, code, off, sc, n, MEM_HOST, out.ctypes.data, MEM_HOST),
+              "rcb_convert_iq", self.h)
+        return out
+
     # ---- K4 --------------------------------------------------------------------------------------
     def quad_demod(self, x, gain, prev=None):
         """analog.quadrature_demod_cf(gain) over rows of x (complex64 [rows][n] or [n]).

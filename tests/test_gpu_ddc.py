@@ -67,32 +67,61 @@ def test_ddc_many_channels_share_one_block(engine):
 
 
 def test_ddc_split_invariance_and_ragged_blocks(engine):
+    from radiocapture_rf_b200.engine import Engine
     x, fs, offs = synth.cfg1(200000, seed=5)
     decim, taps = fd.channel_taps(fs, 12500)
     bank = DdcBank(engine)
     a = bank.open(decim, taps, 437500.0, fs, OUT_IQ | OUT_FM, 5.0)
     bank.process(x)
     ya, fa = bank.pull(a, OUT_IQ), bank.pull(a, OUT_FM)
-    bank.close(a)
-    bank2 = DdcBank(engine)
-    # fresh engine-level stream position continues; open a new channel (its own phase origin)
-    b = bank2.open(decim, taps, 437500.0, fs, OUT_IQ | OUT_FM, 5.0)
-    ys, fs_ = [], []
-    pos = 0
-    for blk in [1, 95, 96, 97, 1000, 12345, 7, 0, 50000]:
-        bank2.process(x[pos:pos + blk])
-        pos += blk
+    e2 = Engine(0)                      # a fresh stream: same samples fed in ragged blocks
+    try:
+        bank2 = DdcBank(e2)
+        b = bank2.open(decim, taps, 437500.0, fs, OUT_IQ | OUT_FM, 5.0)
+        ys, fs_ = [], []
+        pos = 0
+        for blk in [1, 95, 96, 97, 1000, 12345, 7, 0, 50000]:
+            bank2.process(x[pos:pos + blk])
+            pos += blk
+            ys.append(bank2.pull(b, OUT_IQ))
+            fs_.append(bank2.pull(b, OUT_FM))
+        bank2.process(x[pos:])
         ys.append(bank2.pull(b, OUT_IQ))
         fs_.append(bank2.pull(b, OUT_FM))
-    bank2.process(x[pos:])
-    ys.append(bank2.pull(b, OUT_IQ))
-    fs_.append(bank2.pull(b, OUT_FM))
+    finally:
+        e2.close()
     yb, fb = np.concatenate(ys), np.concatenate(fs_)
     assert len(yb) == len(ya)
-    # different stream origin -> different absolute decimation phase is NOT allowed to change samples:
-    # channel b was opened when the handle had consumed len(x) samples; outputs restart at its open time.
+    # the first outputs of a channel run through the zero-history path, later blocks through the tiled
+    # path: same samples to float32 rounding of a different summation order
     assert gb.rel_l2(yb, ya) <= 2e-6
     assert _fm_err(fb[1:], fa[1:].astype(np.float64), 5.0) <= 2e-5
+
+
+def test_ddc_channel_opened_mid_stream_joins_the_decimation_grid(engine):
+    """Channels of one source share a decimation grid: a channel opened after n samples starts at the next
+    multiple of D with zero filter history (a GNU Radio channel starts at whatever sample its ZMQ SUB sees
+    first), and from then on is computed together with the older channels by the tiled kernel."""
+    x, fs, offs = synth.cfg1(96 * 1500 + 37, seed=6)
+    decim, taps = fd.channel_taps(fs, 12500)
+    bank = DdcBank(engine)
+    a = bank.open(decim, taps, -62500.0, fs)
+    n0 = 96 * 500 + 37
+    bank.process(x[:n0])
+    ya0 = bank.pull(a)
+    b = bank.open(decim, taps, 12500.0, fs, OUT_IQ | OUT_FM, 5.0)
+    bank.process(x[n0:n0 + 96 * 400])
+    ya1, yb1 = bank.pull(a), bank.pull(b)
+    bank.process(x[n0 + 96 * 400:])
+    ya2, yb2 = bank.pull(a), bank.pull(b)
+    ya = np.concatenate([ya0, ya1, ya2])
+    ref_a = gb.freq_xlating_fir(np.concatenate([x, np.zeros(96, np.complex64)]), taps, decim, -62500.0, fs)
+    assert gb.rel_l2(ya, ref_a[:len(ya)]) <= TOL
+    start = -(-n0 // 96) * 96                                  # next grid point
+    yb = np.concatenate([yb1, yb2])
+    ref_b = gb.freq_xlating_fir(np.concatenate([x[start:], np.zeros(96, np.complex64)]), taps, decim, 12500.0, fs)
+    assert len(yb) == len(ya) - start // 96
+    assert gb.rel_l2(yb, ref_b[:len(yb)]) <= TOL
 
 
 def test_ddc_retune_keeps_phase_continuous(engine):
@@ -192,3 +221,23 @@ def test_gr_float_omega_mode_matches_gnuradio_emulation(engine):
     y = bank.pull(c)
     gr = gb.freq_xlating_fir_grcompat(x, taps, decim, -62500.0, fs)
     assert gb.rel_l2(y[:len(gr)], gr) <= TOL
+
+
+@pytest.mark.parametrize("fmt,dt,off,sc", [("u8", np.uint8, -127.4, 1 / 128.0), ("s8", np.int8, 0.0, 1 / 128.0),
+                                           ("s16", np.int16, 0.0, 1 / 32768.0)])
+def test_ingest_conversion_bit_exact(engine, fmt, dt, off, sc):
+    """K5: SDR wire formats -> complex64, bit-exact against (v + offset) * scale in float32
+    (u8: gr-osmosdr rtl_source_c's (v - 127.4)/128 mapping), including a ragged tail and empty input."""
+    rng = np.random.default_rng(7)
+    info = np.iinfo(dt)
+    for n in (0, 1, 5, 4096, 100003):
+        raw = rng.integers(info.min, info.max + 1, size=2 * n).astype(dt)
+        y = engine.convert_iq(raw, fmt)
+        ref = ((raw.astype(np.float32) + np.float32(off)) * np.float32(sc)).astype(np.float32).view(np.complex64)
+        assert y.shape == (n,) and np.array_equal(y, ref)
+    # converted samples feed the channelizer directly from device memory
+    raw = rng.integers(0, 256, size=2 * 96 * 200).astype(np.uint8)
+    d = engine.dev_alloc(96 * 200 * 8)
+    assert engine.convert_iq(raw, "u8", out_device=d) == 96 * 200
+    x = engine.to_host(d, (96 * 200,), np.complex64)
+    assert np.array_equal(x, ((raw.astype(np.float32) - np.float32(127.4)) * np.float32(1 / 128.0)).view(np.complex64))
