@@ -221,6 +221,17 @@ struct FftState {
     int in_block = 0;         // frames already folded into the current averaging block
     float* d_window = nullptr;
     float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_tlo = nullptr, *d_thi = nullptr;
+    // two work slots: sub-batch b runs on slot b & 1 (own stream, scratch, vals, host staging) so the column
+    // pass of one sub-batch overlaps the row pass / fold of the previous one (fills wave tails and
+    // overlaps the memory-bound and compute-bound phases of these short kernels)
+    float2* d_scratch2[2] = {nullptr, nullptr};
+    float* d_vals2[2] = {nullptr, nullptr};
+    float2* d_in2[2] = {nullptr, nullptr};
+    size_t in_cap2[2] = {0, 0};
+    cudaStream_t ws[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fold[2] = {nullptr, nullptr};
+    cudaEvent_t ev_start = nullptr;
+    unsigned long long batch_no = 0;
     float2* d_scratch = nullptr;
     float* d_vals = nullptr;
     float* d_acc = nullptr;
@@ -236,6 +247,14 @@ inline void fft_free(FftState& s) {
     cudaFree(s.d_tw2);
     cudaFree(s.d_tlo);
     cudaFree(s.d_thi);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(s.d_scratch2[i]);
+        cudaFree(s.d_vals2[i]);
+        cudaFree(s.d_in2[i]);
+        if (s.ws[i]) cudaStreamDestroy(s.ws[i]);
+        if (s.ev_fold[i]) cudaEventDestroy(s.ev_fold[i]);
+    }
+    if (s.ev_start) cudaEventDestroy(s.ev_start);
     cudaFree(s.d_scratch);
     cudaFree(s.d_vals);
     cudaFree(s.d_acc);
@@ -303,8 +322,13 @@ inline int fft_config(FftState& s, int L, const float* window, int avg, cudaStre
     FCK(cudaMemcpyAsync(s.d_tw2, t2.data(), t2.size() * sizeof(float2), cudaMemcpyHostToDevice, st));
     FCK(cudaMemcpyAsync(s.d_tlo, lo.data(), lo.size() * sizeof(float2), cudaMemcpyHostToDevice, st));
     FCK(cudaMemcpyAsync(s.d_thi, hi.data(), hi.size() * sizeof(float2), cudaMemcpyHostToDevice, st));
-    FCK(cudaMalloc(&s.d_scratch, (size_t)s.sb * L * sizeof(float2)));
-    FCK(cudaMalloc(&s.d_vals, (size_t)s.sb * L * sizeof(float)));
+    for (int i = 0; i < 2; ++i) {
+        FCK(cudaMalloc(&s.d_scratch2[i], (size_t)s.sb * L * sizeof(float2)));
+        FCK(cudaMalloc(&s.d_vals2[i], (size_t)s.sb * L * sizeof(float)));
+        FCK(cudaStreamCreateWithFlags(&s.ws[i], cudaStreamNonBlocking));
+        FCK(cudaEventCreateWithFlags(&s.ev_fold[i], cudaEventDisableTiming));
+    }
+    FCK(cudaEventCreateWithFlags(&s.ev_start, cudaEventDisableTiming));
     FCK(cudaMalloc(&s.d_acc, (size_t)L * sizeof(float)));
     FCK(cudaMemsetAsync(s.d_acc, 0, (size_t)L * sizeof(float), st));
     FCK(cudaStreamSynchronize(st));
@@ -358,15 +382,16 @@ inline int fft_process(FftState& s, const float2* iq, size_t nsamples, int in_me
     const size_t will_emit = (s.in_block + nframes) / (size_t)s.avg;
     if (will_emit > cap_vec || (will_emit && !out)) return -6;  // RCB_ERANGE
     const float2* d_x = iq;
-    if (in_mem == 0) {  // host: stage one sub-batch at a time
+    if (in_mem == 0) {  // host: stage one sub-batch at a time (one staging buffer per work slot)
         const size_t need = (size_t)s.sb * L;
-        if (s.in_cap < need) {
-            cudaFree(s.d_in);
-            s.d_in = nullptr;
-            s.in_cap = 0;
-            FCK(cudaMalloc(&s.d_in, need * sizeof(float2)));
-            s.in_cap = need;
-        }
+        for (int i = 0; i < 2; ++i)
+            if (s.in_cap2[i] < need) {
+                cudaFree(s.d_in2[i]);
+                s.d_in2[i] = nullptr;
+                s.in_cap2[i] = 0;
+                FCK(cudaMalloc(&s.d_in2[i], need * sizeof(float2)));
+                s.in_cap2[i] = need;
+            }
     }
     if (out_mem == 0 && will_emit) {
         if (s.emit_cap < will_emit * L) {
@@ -379,21 +404,28 @@ inline int fft_process(FftState& s, const float2* iq, size_t nsamples, int in_me
     }
     float* d_out = (out_mem == 0) ? s.d_emit : out;
     size_t done = 0, emitted = 0;
+    // everything queued on the caller's stream so far (input production, previous outputs consumed) first
+    FCK(cudaEventRecord(s.ev_start, st));
+    FCK(cudaStreamWaitEvent(s.ws[0], s.ev_start, 0));
+    FCK(cudaStreamWaitEvent(s.ws[1], s.ev_start, 0));
+    int last_slot = -1;
     while (done < nframes) {
+        const int sl = (int)(s.batch_no++ & 1);
+        cudaStream_t wst = s.ws[sl];
         const int room = s.avg - s.in_block;
         const int nfr = (int)std::min<size_t>(std::min<size_t>(s.sb, nframes - done), (size_t)room);
         if (in_mem == 0) {
-            FCK(cudaMemcpyAsync(s.d_in, iq + done * L, (size_t)nfr * L * sizeof(float2), cudaMemcpyHostToDevice, st));
+            FCK(cudaMemcpyAsync(s.d_in2[sl], iq + done * L, (size_t)nfr * L * sizeof(float2), cudaMemcpyHostToDevice, wst));
             *h2d += (size_t)nfr * L * sizeof(float2);
-            d_x = s.d_in;
+            d_x = s.d_in2[sl];
         } else {
             d_x = iq + done * L;
         }
         FftParams p{};
         p.x = d_x;
         p.window = s.d_window;
-        p.scratch = s.d_scratch;
-        p.vals = s.d_vals;
+        p.scratch = s.d_scratch2[sl];
+        p.vals = s.d_vals2[sl];
         p.tw1 = s.d_tw1;
         p.tw2 = s.d_tw2;
         p.t_lo = s.d_tlo;
@@ -401,16 +433,20 @@ inline int fft_process(FftState& s, const float2* iq, size_t nsamples, int in_me
         p.L = s.L;
         p.L1 = s.L1;
         p.L2 = s.L2;
-        int rc = (s.R1 == 8) ? fft_launch_cols<8>(p, nfr, st) : (s.R1 == 16) ? fft_launch_cols<16>(p, nfr, st)
-                                                                            : fft_launch_cols<32>(p, nfr, st);
+        int rc = (s.R1 == 8) ? fft_launch_cols<8>(p, nfr, wst) : (s.R1 == 16) ? fft_launch_cols<16>(p, nfr, wst)
+                                                                            : fft_launch_cols<32>(p, nfr, wst);
         if (rc) return rc;
-        rc = (s.R2 == 8) ? fft_launch_rows<8>(p, nfr, st) : (s.R2 == 16) ? fft_launch_rows<16>(p, nfr, st)
-                                                                        : fft_launch_rows<32>(p, nfr, st);
+        rc = (s.R2 == 8) ? fft_launch_rows<8>(p, nfr, wst) : (s.R2 == 16) ? fft_launch_rows<16>(p, nfr, wst)
+                                                                        : fft_launch_rows<32>(p, nfr, wst);
         if (rc) return rc;
         const bool complete = (s.in_block + nfr == s.avg);
         float* emit = complete ? d_out + emitted * L : nullptr;
-        fft_fold_kernel<<<(unsigned)((L / 4 + 255) / 256), 256, 0, st>>>(s.d_vals, nfr, s.L, s.d_acc, emit);
+        // the block sum is accumulated in stream order of the sub-batches: wait for the previous fold
+        if (last_slot >= 0 && last_slot != sl) FCK(cudaStreamWaitEvent(wst, s.ev_fold[last_slot], 0));
+        fft_fold_kernel<<<(unsigned)((L / 4 + 255) / 256), 256, 0, wst>>>(s.d_vals2[sl], nfr, s.L, s.d_acc, emit);
         FCK(cudaGetLastError());
+        FCK(cudaEventRecord(s.ev_fold[sl], wst));
+        last_slot = sl;
         *launches += 3;
         s.in_block += nfr;
         if (complete) {
@@ -418,6 +454,11 @@ inline int fft_process(FftState& s, const float2* iq, size_t nsamples, int in_me
             ++emitted;
         }
         done += nfr;
+    }
+    // rejoin the caller's stream
+    if (last_slot >= 0) {
+        FCK(cudaStreamWaitEvent(st, s.ev_fold[0], 0));
+        FCK(cudaStreamWaitEvent(st, s.ev_fold[1], 0));
     }
     if (out_mem == 0 && emitted) {
         FCK(cudaMemcpyAsync(out, s.d_emit, emitted * L * sizeof(float), cudaMemcpyDeviceToHost, st));
