@@ -204,10 +204,10 @@ int pfb_launch_r(rcb_t* h, const PfbParams& p, bool q) {
         default: return pfb_launch_rm<R, PFB_OUT_IQ | PFB_OUT_FM>(h, p, q);
     }
 }
-template <int R, int W = 8>
+template <int R, int W = 8, bool PK = true>
 int pfb_launch_tma(rcb_t* h, const PfbParams& p, bool query_only) {
     using G = PfbTmaGeom<R, W>;
-    auto kern = pfb_fm_tma_kernel<R, W>;
+    auto kern = pfb_fm_tma_kernel<R, W, PK>;
     const size_t smem = G::smem_bytes;
     if (query_only) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -233,7 +233,10 @@ int pfb_launch_fast(rcb_t* h, const PfbParams& p, bool q) {
         switch (h->pfb.R) {
             case 8: return pfb_launch_tma<8>(h, p, q);
             case 16: return pfb_launch_tma<16>(h, p, q);
-            case 32: return (h->pfb.variant == 16) ? pfb_launch_tma<32, 16>(h, p, q) : pfb_launch_tma<32>(h, p, q);
+            case 32:
+                if (h->pfb.variant == 16) return pfb_launch_tma<32, 16, false>(h, p, q);
+                if (h->pfb.variant == 3) return pfb_launch_tma<32, 8, false>(h, p, q);  // scalar-arithmetic v5 kernel
+                return pfb_launch_tma<32>(h, p, q);
         }
     }
     switch (h->pfb.R) {

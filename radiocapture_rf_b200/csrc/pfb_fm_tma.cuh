@@ -16,6 +16,7 @@
 // Shared memory: 8 x 8 KB work + 9 x 4 KB phase ring + 8 KB twiddles + 4 KB taps = 112.1 KB -> 2 CTAs/SM.
 #pragma once
 #include "pfb_fm.cuh"
+#include "fft_packed.cuh"
 
 namespace rcb {
 
@@ -65,7 +66,8 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // twiddle table layout expected in p.twiddle for this kernel: dense [R][R] complex, 16-byte chunks swizzled:
 //   tw[ll*R + (((m1>>1) ^ swz(ll))<<1 | (m1&1))] = W_N^{+(R-1-ll) m1}
 // taps layout: float4 groups as in pfb_fm.cuh (P = 1).
-template <int R, int W = 8>
+// PK = true: packed f32x2 arithmetic (fft_packed.cuh) for both radix-R passes, atan2 and the demod.
+template <int R, int W = 8, bool PK = false>
 __global__ void __launch_bounds__(32 * W, 16 / W) pfb_fm_tma_kernel(const PfbParams p) {
     using G = PfbTmaGeom<R, W>;
     constexpr int THREADS = G::THREADS;
@@ -143,6 +145,65 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pfb_fm_tma_kernel(const PfbPar
         // ---- wait for the TMA copy of this warp's frames, FIR, first radix-R pass ----
         mbar_wait(row_bar, row_par);
         row_par ^= 1u;
+        float ph[R];
+        const bool range_last = (it + 1 == cur1);
+        // issue the TMA copy of the frames this warp transforms next (its buffer has been fully consumed)
+        auto issue_next = [&]() {
+            if (!range_last) {
+                frame0 += FPI;
+                issue_rows(frame0);
+            } else if (nxt0 < NI) {  // seamless hand-over: prefetch the warm-up frames of the next range
+                frame0 = (long long)(nxt0 - 1) * FPI + warp * F;
+                issue_rows(frame0);
+            }
+        };
+        if constexpr (PK) {
+            // ---- packed path: scalar DIF stage (taps folded in) + R/2-point transform on f32x2 pairs ----
+            float2 pr[R / 2], pi[R / 2];
+            {
+                float hreg[R];
+#pragma unroll
+                for (int jq = 0; jq < R / 4; ++jq) {
+                    const float4 h = tap4[jq * R + ll];
+                    hreg[4 * jq + 0] = h.x; hreg[4 * jq + 1] = h.y; hreg[4 * jq + 2] = h.z; hreg[4 * jq + 3] = h.w;
+                }
+                // DFT input j is sample row jj = R-1-j of this lane's column
+                auto get = [&](auto j) { return wf[(R - 1 - decltype(j)::value) * R + ll]; };
+                auto tap = [&](auto j) { return hreg[R - 1 - decltype(j)::value]; };
+                fft_packed<R, +1, true>(pr, pi, get, tap);
+            }
+            __syncwarp();  // every lane has read its samples: the buffer becomes the transpose scratch
+            {
+                const int sw = pfb_swz<R>(ll);
+                const float4* twp = reinterpret_cast<const float4*>(tws + ll * R);
+                float4* bp = reinterpret_cast<float4*>(wf + ll * R);
+#pragma unroll
+                for (int c = 0; c < R / 2; ++c) {  // pair c = (X[2c], X[2c+1]) -> one 16-byte chunk
+                    const float4 t = twp[c ^ sw];
+                    const float2 b0 = make_float2(fmaf(pr[c].x, t.x, -pi[c].x * t.y), fmaf(pr[c].x, t.y, pi[c].x * t.x));
+                    const float2 b1 = make_float2(fmaf(pr[c].y, t.z, -pi[c].y * t.w), fmaf(pr[c].y, t.w, pi[c].y * t.z));
+                    bp[c ^ sw] = make_float4(b0.x, b0.y, b1.x, b1.y);
+                }
+            }
+            __syncwarp();
+            {
+                const int ch = ll >> 1, wi = ll & 1;
+                float2 u[R];
+#pragma unroll
+                for (int l2 = 0; l2 < R; ++l2) u[R - 1 - l2] = wf[l2 * R + (((ch ^ pfb_swz<R>(l2)) << 1) | wi)];
+                __syncwarp();  // scratch fully consumed: start the copy of the next frames right away
+                issue_next();
+                auto get = [&](auto j) { return u[decltype(j)::value]; };
+                auto tap = [&](auto) { return 1.0f; };
+                fft_packed<R, +1, false>(pr, pi, get, tap);  // (pr[q], pi[q]) = Y[ll + R*(2q)], Y[ll + R*(2q+1)]
+            }
+#pragma unroll
+            for (int q = 0; q < R / 2; ++q) {
+                const float2 a = atan2_nan_p2(pi[q], pr[q]);
+                ph[2 * q] = a.x;
+                ph[2 * q + 1] = a.y;
+            }
+        } else {
         float2 v[R];
 #pragma unroll
         for (int jq = 0; jq < R / 4; ++jq) {
@@ -178,19 +239,11 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pfb_fm_tma_kernel(const PfbPar
             for (int l2 = 0; l2 < R; ++l2) v[R - 1 - l2] = wf[l2 * R + (((ch ^ pfb_swz<R>(l2)) << 1) | wi)];
         }
         __syncwarp();  // scratch fully consumed: start the copy of the next frames right away
-        const bool range_last = (it + 1 == cur1);
-        if (!range_last) {
-            frame0 += FPI;
-            issue_rows(frame0);
-        } else if (nxt0 < NI) {  // seamless hand-over: prefetch the warm-up frames of the next range
-            frame0 = (long long)(nxt0 - 1) * FPI + warp * F;
-            issue_rows(frame0);
-        }
+        issue_next();
         fft_inreg<R, +1>(v);  // v[m2] = Y[ll + R*m2]
-
-        float ph[R];
 #pragma unroll
         for (int m2 = 0; m2 < R; ++m2) ph[m2] = atan2_nan(v[m2].y, v[m2].x);
+        }
 
         int slot = base_slot + warp * F + fr + 1;
         slot = (slot >= NSLOT) ? slot - NSLOT : slot;
@@ -237,24 +290,43 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pfb_fm_tma_kernel(const PfbPar
                 }
                 s = (s + 1 == NSLOT) ? 0 : s + 1;
             }
+            float o[CPT][8];
+            if constexpr (PK && CPT >= 2) {  // packed over channel pairs; the NaN select unpacks for free
+#pragma unroll
+                for (int q = 0; q < CPT; q += 2) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float2 d = p2sub(make_float2(pw[j + 1][q], pw[j + 1][q + 1]), make_float2(pw[j][q], pw[j][q + 1]));
+                        const float2 k = p2add(p2fmas(d, 0.15915494309189535f, make_float2(12582912.0f, 12582912.0f)),
+                                               make_float2(-12582912.0f, -12582912.0f));
+                        d = p2fmas(k, -6.283185307179586f, d);
+                        d = p2muls(d, p.gain);
+                        o[q][j] = (d.x != d.x) ? 0.0f : d.x;
+                        o[q + 1][j] = (d.y != d.y) ? 0.0f : d.y;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < CPT; ++q) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float d = pw[j + 1][q] - pw[j][q];
+                        const float k = (d * 0.15915494309189535f + 12582912.0f) - 12582912.0f;
+                        d = fmaf(k, -6.283185307179586f, d);
+                        d *= p.gain;
+                        o[q][j] = (d != d) ? 0.0f : d;
+                    }
+                }
+            }
 #pragma unroll
             for (int q = 0; q < CPT; ++q) {
-                float o[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float d = pw[j + 1][q] - pw[j][q];
-                    const float k = (d * 0.15915494309189535f + 12582912.0f) - 12582912.0f;
-                    d = fmaf(k, -6.283185307179586f, d);
-                    d *= p.gain;
-                    o[j] = (d != d) ? 0.0f : d;
-                }
                 float* dst = dst0 + q * rowstride;
                 if (full) {
-                    st_global_v8(dst, o);
-                } else if (!(p.debug_flags & 1) || o[0] == 123456.789f) {
+                    st_global_v8(dst, o[q]);
+                } else if (!(p.debug_flags & 1) || o[q][0] == 123456.789f) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        if (t0 + j < p.T) dst[j] = o[j];
+                        if (t0 + j < p.T) dst[j] = o[q][j];
                 }
             }
         }
