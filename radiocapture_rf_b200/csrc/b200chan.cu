@@ -76,6 +76,8 @@ struct rcb_ctx {
         float* d_taps = nullptr;
         float2* d_tw = nullptr;
         float2* d_tw_tma = nullptr;  // dense swizzled table for pfb_fm_tma_kernel
+        float* d_taps_kc = nullptr;  // [PT][N] column-major taps for the time-blocked FIR (P > 1)
+        int PT = 1;                  // compiled taps-per-arm of the fast FM kernel (P rounded up to 2^k)
         bool use_tma = false;
 
         float2* d_hist[2] = {nullptr, nullptr};
@@ -204,10 +206,10 @@ int pfb_launch_r(rcb_t* h, const PfbParams& p, bool q) {
         default: return pfb_launch_rm<R, PFB_OUT_IQ | PFB_OUT_FM>(h, p, q);
     }
 }
-template <int R, int W = 8, bool PK = true>
+template <int R, int W = 8, bool PK = true, int PT = 1>
 int pfb_launch_tma(rcb_t* h, const PfbParams& p, bool query_only) {
     using G = PfbTmaGeom<R, W>;
-    auto kern = pfb_fm_tma_kernel<R, W, PK>;
+    auto kern = pfb_fm_tma_kernel<R, W, PK, PT>;
     const size_t smem = G::smem_bytes;
     if (query_only) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -221,6 +223,7 @@ int pfb_launch_tma(rcb_t* h, const PfbParams& p, bool query_only) {
     const int grid = std::max(1, std::min(NI, h->pfb.blocks_per_sm * h->sm_count));
     PfbParams q = p;
     q.twiddle = h->pfb.d_tw_tma;
+    q.taps_kc = h->pfb.d_taps_kc;
     q.work_counter = h->pfb.d_counter;
     CK(cudaMemsetAsync(h->pfb.d_counter, 0, sizeof(int), h->stream));
     kern<<<grid, G::THREADS, smem, h->stream>>>(q);
@@ -228,13 +231,31 @@ int pfb_launch_tma(rcb_t* h, const PfbParams& p, bool query_only) {
     return RCB_OK;
 }
 
+template <int R>
+int pfb_launch_tma_p(rcb_t* h, const PfbParams& p, bool q) {
+    switch (h->pfb.PT) {
+        case 2: return pfb_launch_tma<R, 8, true, 2>(h, p, q);
+        case 4: return pfb_launch_tma<R, 8, true, 4>(h, p, q);
+        case 8: return pfb_launch_tma<R, 8, true, 8>(h, p, q);
+        case 16: return pfb_launch_tma<R, 8, true, 16>(h, p, q);
+    }
+    return RCB_EUNSUPPORTED;
+}
+
 int pfb_launch_fast(rcb_t* h, const PfbParams& p, bool q) {
+    if (h->pfb.use_tma && h->pfb.PT > 1) {
+        switch (h->pfb.R) {
+            case 8: return pfb_launch_tma_p<8>(h, p, q);
+            case 16: return pfb_launch_tma_p<16>(h, p, q);
+            case 32: return pfb_launch_tma_p<32>(h, p, q);
+        }
+    }
     if (h->pfb.use_tma) {
         switch (h->pfb.R) {
             case 8: return pfb_launch_tma<8>(h, p, q);
             case 16: return pfb_launch_tma<16>(h, p, q);
             case 32:
-                if (h->pfb.variant == 16) return pfb_launch_tma<32, 16, false>(h, p, q);
+                if (h->pfb.variant == 16) return pfb_launch_tma<32, 16, true>(h, p, q);
                 if (h->pfb.variant == 3) return pfb_launch_tma<32, 8, false>(h, p, q);  // scalar-arithmetic v5 kernel
                 return pfb_launch_tma<32>(h, p, q);
         }
@@ -253,6 +274,8 @@ void pfb_free(rcb_t* h) {
     cudaFree(s.d_tw);
     cudaFree(s.d_tw_tma);
     s.d_tw_tma = nullptr;
+    cudaFree(s.d_taps_kc);
+    s.d_taps_kc = nullptr;
 
     cudaFree(s.d_hist[0]);
     cudaFree(s.d_hist[1]);
@@ -597,7 +620,18 @@ extern "C" int rcb_pfb_config(rcb_t* h, int nchans, const float* taps, int ntaps
             }
         s.taps_smem = ((size_t)P * N * sizeof(float) <= 16384);
         // FM-only, one tap per arm: the TMA-staged kernel (RCB_PFB_VARIANT=9 keeps the register-prefetch one)
-        s.use_tma = (P == 1 && out_mask == RCB_OUT_FM && s.variant != 9);
+        // 2..16 taps per arm: same kernel with the time-blocked arm FIR in front (P rounded up to 2, 4, 8, 16 with
+        // zero taps; RCB_PFB_VARIANT=9 keeps the register-prefetch kernel for both)
+        s.PT = 1;
+        while (s.PT < P) s.PT *= 2;
+        s.use_tma = (s.PT <= 16 && out_mask == RCB_OUT_FM && s.variant != 9);
+        if (s.use_tma && s.PT > 1) {
+            std::vector<float> kc((size_t)s.PT * N, 0.f);
+            for (int k = 0; k < P; ++k)
+                for (int c = 0; c < N; ++c) kc[(size_t)k * N + c] = hp[(size_t)(N - 1 - c) + (size_t)k * N];
+            CK(cudaMalloc(&s.d_taps_kc, kc.size() * sizeof(float)));
+            CK(cudaMemcpy(s.d_taps_kc, kc.data(), kc.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
         if (s.use_tma) {
             std::vector<float2> tt((size_t)N);
             for (int ll = 0; ll < R; ++ll) {

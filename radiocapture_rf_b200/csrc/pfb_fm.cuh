@@ -39,6 +39,7 @@ struct PfbParams {
     const float2* hist;     // P*N samples preceding x (rows -P .. -1)
     const float* taps;      // fast path, float4 groups: taps[((k*(R/4) + jj/4)*R + ll)*4 + jj%4] =
                             //   h[R*(R-1-jj) + (R-1-ll) + k*N];  generic path: taps[k*N + i] = h[i + k*N]
+    const float* taps_kc;   // [P][N]: taps_kc[k*N + c] = h[(N-1-c) + k*N] (tap of column c; pfb_fm_tma_kernel, P > 1)
     const float2* zeros;    // N complex zeros (rows outside the stream)
     int debug_flags;        // RCB_PFB_DEBUG (measurement experiments only): 1 = suppress FM stores, 2 = load rows once
     int* work_counter;      // zeroed before each launch: dynamic tail-chunk counter (pfb_fm_tma_kernel)

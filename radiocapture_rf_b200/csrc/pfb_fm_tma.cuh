@@ -67,7 +67,12 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 //   tw[ll*R + (((m1>>1) ^ swz(ll))<<1 | (m1&1))] = W_N^{+(R-1-ll) m1}
 // taps layout: float4 groups as in pfb_fm.cuh (P = 1).
 // PK = true: packed f32x2 arithmetic (fft_packed.cuh) for both radix-R passes, atan2 and the demod.
-template <int R, int W = 8, bool PK = false>
+// PT  > 1  : PT taps per arm.  The TMA row copy is replaced by a time-blocked arm FIR: a thread owns one
+//             column (arm) for 8 consecutive frames, loads the 8 + PT - 1 samples of that column once
+//             (coalesced 256 B per warp and row; the PT - 1 history rows are L1/L2 hits) and its PT taps,
+//             and produces the 8 filtered samples with PT packed FFMA2 each (re/im pair x broadcast tap),
+//             written to the frame buffers the FFT warps then transform exactly like TMA-landed rows.
+template <int R, int W = 8, bool PK = false, int PT = 1>
 __global__ void __launch_bounds__(32 * W, 16 / W) pfb_fm_tma_kernel(const PfbParams p) {
     using G = PfbTmaGeom<R, W>;
     constexpr int THREADS = G::THREADS;
@@ -88,7 +93,7 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pfb_fm_tma_kernel(const PfbPar
 
     for (int i = tid; i < N; i += THREADS) {
         tws[i] = p.twiddle[i];
-        taps_s[i] = p.taps[i];
+        if constexpr (PT == 1) taps_s[i] = p.taps[i];
     }
     if (tid < W) mbar_init(bars + tid, 1);
     if (tid == W) mbar_init(cta_bar, THREADS);
@@ -122,7 +127,7 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pfb_fm_tma_kernel(const PfbPar
 
     long long frame0 = (long long)(cur0 - 1) * FPI + warp * F;  // first of this warp's F frames
     auto issue_rows = [&](long long f0) {
-        if (lane == 0) {
+        if (PT == 1 && lane == 0) {
             fence_proxy_async();
             mbar_expect_tx(row_bar, (uint32_t)(F * N * 8));
 #pragma unroll
@@ -142,9 +147,45 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pfb_fm_tma_kernel(const PfbPar
             const int c = atomicAdd(p.work_counter, 1);
             s_next = tail0 + c * kTailChunk;
         }
-        // ---- wait for the TMA copy of this warp's frames, FIR, first radix-R pass ----
-        mbar_wait(row_bar, row_par);
-        row_par ^= 1u;
+        if constexpr (PT == 1) {
+            // ---- wait for the TMA copy of this warp's frames ----
+            mbar_wait(row_bar, row_par);
+            row_par ^= 1u;
+        } else {
+            // ---- time-blocked arm FIR of this iteration's FPI frames into the warps' frame buffers ----
+            // task = (column c, group of TBK consecutive frames); 16-frame groups where the iteration has them
+            constexpr int TBK = (FPI % 16 == 0 && N * (FPI / 16) >= THREADS) ? 16 : 8;
+            constexpr int NX = TBK + PT - 1;
+            constexpr int TASKS = N * (FPI / TBK) / THREADS;
+#pragma unroll 1
+            for (int q = 0; q < TASKS; ++q) {
+                const int task = q * THREADS + tid;
+                const int c = task % N, g = task / N;
+                const long long f0 = (long long)it * FPI + TBK * g;
+                const long long r0 = f0 - (PT - 1);
+                float2 xs[NX];
+                if (r0 >= 0 && f0 + TBK <= p.T) {
+                    const float2* b = p.x + r0 * N + c;
+#pragma unroll
+                    for (int j = 0; j < NX; ++j) xs[j] = __ldg(b + (long long)j * N);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NX; ++j) xs[j] = __ldg(pfb_row_ptr<R>(p, r0 + j) + c);
+                }
+                float hk[PT];
+#pragma unroll
+                for (int k = 0; k < PT; ++k) hk[k] = __ldg(p.taps_kc + k * N + c);
+#pragma unroll
+                for (int t = 0; t < TBK; ++t) {
+                    float2 acc = p2muls(xs[t + PT - 1], hk[0]);
+#pragma unroll
+                    for (int k = 1; k < PT; ++k) acc = p2fmas(xs[t + PT - 1 - k], hk[k], acc);
+                    const int fi = TBK * g + t;  // frame within the iteration -> owning warp's buffer
+                    work_all[(fi / F) * G::WORK + (fi % F) * FSW + c] = acc;
+                }
+            }
+            __syncthreads();
+        }
         float ph[R];
         const bool range_last = (it + 1 == cur1);
         // issue the TMA copy of the frames this warp transforms next (its buffer has been fully consumed)
@@ -163,14 +204,14 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pfb_fm_tma_kernel(const PfbPar
             {
                 float hreg[R];
 #pragma unroll
-                for (int jq = 0; jq < R / 4; ++jq) {
+                for (int jq = 0; PT == 1 && jq < R / 4; ++jq) {
                     const float4 h = tap4[jq * R + ll];
                     hreg[4 * jq + 0] = h.x; hreg[4 * jq + 1] = h.y; hreg[4 * jq + 2] = h.z; hreg[4 * jq + 3] = h.w;
                 }
                 // DFT input j is sample row jj = R-1-j of this lane's column
                 auto get = [&](auto j) { return wf[(R - 1 - decltype(j)::value) * R + ll]; };
                 auto tap = [&](auto j) { return hreg[R - 1 - decltype(j)::value]; };
-                fft_packed<R, +1, true>(pr, pi, get, tap);
+                fft_packed<R, +1, PT == 1>(pr, pi, get, tap);
             }
             __syncwarp();  // every lane has read its samples: the buffer becomes the transpose scratch
             {
@@ -266,8 +307,13 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pfb_fm_tma_kernel(const PfbPar
         // ---- demod: 8 consecutive frames of CPT channels per thread ----
         if (it >= cur0) {
             constexpr int CPT = N * (FPI / 8) / THREADS;  // 4, 2, 1 for R = 32, 16, 8
-            const int g = tid / (N / CPT);
-            const int m0 = (tid % (N / CPT)) * CPT;
+            // thread -> (8-frame group g, CPT adjacent channels).  With more than one group per iteration the
+            // groups of one channel set sit in the two halves of the same warp, so one store instruction
+            // covers 64 contiguous bytes of each channel row (half the L2 write requests of 32 B sectors)
+            constexpr int GRP = FPI / 8;
+            constexpr bool kPairLanes = (GRP == 2 && CPT >= 2);
+            const int g = kPairLanes ? (lane >> 4) : tid / (N / CPT);
+            const int m0 = kPairLanes ? (warp * 16 + (lane & 15)) * CPT : (tid % (N / CPT)) * CPT;
             const long long t0 = (long long)it * FPI + 8 * g;
             int s = base_slot + 8 * g;
             s = (s >= NSLOT) ? s - NSLOT : s;

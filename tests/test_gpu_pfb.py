@@ -62,6 +62,25 @@ def test_pfb_iq_fm_parity(engine, n, tpa, frames):
     _check(engine, n, taps, frames, seed=n + tpa)
 
 
+@pytest.mark.parametrize("n,tpa,frames", [(1024, 16, 96), (1024, 3, 131), (1024, 2, 200), (1024, 8, 77),
+                                          (256, 16, 300), (256, 12, 257), (256, 2, 130),
+                                          (64, 8, 700), (64, 2, 1024), (64, 16, 333)])
+def test_pfb_fm_only_multi_tap_fast_kernel(engine, n, tpa, frames):
+    """FM-only output with 2..16 taps per arm runs the time-blocked-FIR variant of the headline kernel
+    (P rounded up to a power of two with zero taps): same parity bar as every other path."""
+    taps = fd.pfb_prototype(n, tpa)
+    _check(engine, n, taps, frames, seed=1000 + n + tpa, mode=OUT_FM)
+
+
+@pytest.mark.parametrize("n,tpa", [(1024, 16), (256, 5), (64, 4)])
+def test_pfb_fm_only_multi_tap_split_invariance(engine, n, tpa):
+    taps = fd.pfb_prototype(n, tpa)
+    frames = 257
+    _, a_fm = _check(engine, n, taps, frames, seed=8, mode=OUT_FM)
+    _, b_fm = _check(engine, n, taps, frames, seed=8, mode=OUT_FM, blocks=[1, 2, 3, 100, 9, 1, 141])
+    assert np.array_equal(a_fm, b_fm)
+
+
 def test_pfb_cfg3_literal_256_taps_1024_channels(engine):
     """BASELINE config 3, literal reading: 256-tap prototype, 1024 channels -> 1 tap/arm, 768 zero arms."""
     taps = fd.pfb_prototype(4, 64)  # any 256-tap low-pass
