@@ -233,6 +233,7 @@ int pfb_launch_tma(rcb_t* h, const PfbParams& p, bool query_only) {
 
 template <int R>
 int pfb_launch_tma_p(rcb_t* h, const PfbParams& p, bool q) {
+    if (R == 32 && h->pfb.variant == 16 && h->pfb.PT == 16) return pfb_launch_tma<32, 16, true, 16>(h, p, q);
     switch (h->pfb.PT) {
         case 2: return pfb_launch_tma<R, 8, true, 2>(h, p, q);
         case 4: return pfb_launch_tma<R, 8, true, 4>(h, p, q);

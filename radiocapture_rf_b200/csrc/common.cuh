@@ -64,6 +64,13 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     return p;
 }
 
+__device__ __forceinline__ float2 ldg_f2_hint(const float2* p, uint64_t policy) {
+    float2 r;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(r.x), "=f"(r.y) : "l"(p), "l"(policy));
+    return r;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // streaming (read-once) 64-bit load: bypass L1 allocation
 __device__ __forceinline__ float2 ld_stream_f2(const float2* p) {
     float2 r;

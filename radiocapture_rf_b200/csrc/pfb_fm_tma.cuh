@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pfb_fm_tma_kernel(const PfbPar
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     const float4* tap4 = reinterpret_cast<const float4*>(taps_s);
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
 
     // ---- work distribution: a static contiguous run (7/8 of the even share) per CTA, then the tail of the
     // ---- launch is handed out dynamically in chunks of kTailChunk iterations (atomic counter).  SMs differ
@@ -157,6 +158,14 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pfb_fm_tma_kernel(const PfbPar
             constexpr int TBK = (FPI % 16 == 0 && N * (FPI / 16) >= THREADS) ? 16 : 8;
             constexpr int NX = TBK + PT - 1;
             constexpr int TASKS = N * (FPI / TBK) / THREADS;
+            if (p.debug_flags & 16) {  // experiment: pull the next iteration's new rows into L2 now
+                const long long nf = (long long)(it + 1) * FPI;
+                if (nf >= 0 && nf + FPI <= p.T) {
+                    const char* b = reinterpret_cast<const char*>(p.x + nf * N);
+#pragma unroll
+                    for (int u = 0; u < (FPI * N * 8) / (128 * THREADS); ++u) prefetch_l2(b + (size_t)(u * THREADS + tid) * 128);
+                }
+            }
 #pragma unroll 1
             for (int q = 0; q < TASKS; ++q) {
                 const int task = q * THREADS + tid;
@@ -166,8 +175,13 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pfb_fm_tma_kernel(const PfbPar
                 float2 xs[NX];
                 if (r0 >= 0 && f0 + TBK <= p.T) {
                     const float2* b = p.x + r0 * N + c;
+                    if (p.debug_flags & 4) {  // experiment: keep input rows in L2 until their last use as history
 #pragma unroll
-                    for (int j = 0; j < NX; ++j) xs[j] = __ldg(b + (long long)j * N);
+                        for (int j = 0; j < NX; ++j) xs[j] = ldg_f2_hint(b + (long long)j * N, pol_keep);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < NX; ++j) xs[j] = __ldg(b + (long long)j * N);
+                    }
                 } else {
 #pragma unroll
                     for (int j = 0; j < NX; ++j) xs[j] = __ldg(pfb_row_ptr<R>(p, r0 + j) + c);
@@ -368,7 +382,8 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pfb_fm_tma_kernel(const PfbPar
             for (int q = 0; q < CPT; ++q) {
                 float* dst = dst0 + q * rowstride;
                 if (full) {
-                    st_global_v8(dst, o[q]);
+                    if (PT > 1 && (p.debug_flags & 8)) st_global_v8_hint(dst, o[q], pol_stream);
+                    else st_global_v8(dst, o[q]);
                 } else if (!(p.debug_flags & 1) || o[q][0] == 123456.789f) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
