@@ -37,6 +37,10 @@ WORKLOADS = {
                  desc="cfg3: 1024-channel PFB, 256-tap prototype, fused FM demod, one 200 Msps stream"),
     "cfg3_p16": dict(nchans=1024, ntaps=16384, out="fm", log2n=28, streams=1,
                      desc="cfg3 variant: 1024-channel PFB, 16 taps/arm (16384-tap prototype), fused FM demod"),
+    "cfg3_iqfm_p16": dict(nchans=1024, ntaps=16384, out="iq+fm", log2n=27, streams=1,
+                          desc="1024-channel PFB, 16 taps/arm, IQ + fused FM out (what pfb-mode channel requests consume)"),
+    "cfg2_p16_iqfm": dict(nchans=64, ntaps=1024, out="iq+fm", log2n=27, streams=1,
+                          desc="64-channel PFB, 16 taps/arm, IQ + fused FM out"),
     "cfg2": dict(nchans=64, ntaps=128, out="iq", log2n=27, streams=1,
                  desc="cfg2: 64-channel PFB, 128-tap prototype, IQ out, one 25 Msps stream"),
     "cfg1": dict(kind="ddc", fs=2.4e6, rate=12500, nchan=1, log2n=24, streams=1, nchans=1, ntaps=349, out="iq+fm",
@@ -284,9 +288,11 @@ class StreamCtx(object):
         self.ntaps = ntaps or cfg["ntaps"]
         self.n = 1 << (log2n or cfg["log2n"])
         self.frames = self.n // self.nch
-        self.fm = cfg["out"] == "fm"
+        self.fm = "fm" in cfg["out"]
+        self.iq = "iq" in cfg["out"]
         self.e = Engine(device)
-        self.ch = PfbChannelizer(self.e, self.nch, make_taps(self.nch, self.ntaps), OUT_FM if self.fm else OUT_IQ, 5.0)
+        self.ch = PfbChannelizer(self.e, self.nch, make_taps(self.nch, self.ntaps),
+                                 (OUT_FM if self.fm else 0) | (OUT_IQ if self.iq else 0), 5.0)
         base_n = min(self.n, 1 << 24)
         base = synth_block(base_n, self.nch, seed)
         self.d_in = self.e.dev_alloc(self.n * 8)
@@ -304,14 +310,12 @@ class StreamCtx(object):
             self.ch.set_out_block(out_block)
         nb = -(-self.frames // out_block) if out_block else 0
         out_elems = nb * self.nch * out_block if out_block else self.n
-        self.d_out = self.e.dev_alloc(out_elems * (4 if self.fm else 8))
-        self.bytes_per_sample = 8 + (4 if self.fm else 8)
+        self.d_fm = self.e.dev_alloc(out_elems * 4) if self.fm else None
+        self.d_iq = self.e.dev_alloc(out_elems * 8) if self.iq else None
+        self.bytes_per_sample = 8 + (4 if self.fm else 0) + (8 if self.iq else 0)
 
     def step(self):
-        if self.fm:
-            self.ch.process_device(self.d_in, self.n, None, self.d_out, self.frames)
-        else:
-            self.ch.process_device(self.d_in, self.n, self.d_out, None, self.frames)
+        self.ch.process_device(self.d_in, self.n, self.d_iq, self.d_fm, self.frames)
 
     def close(self):
         self.e.close()
@@ -405,27 +409,30 @@ def run_e2e(device, wl, steps, warmup, dist, local, log2n=26):
     from radiocapture_rf_b200.engine import Engine, PfbChannelizer, OUT_FM, OUT_IQ
     cfg = WORKLOADS[wl]
     nch = cfg["nchans"]
-    fm = cfg["out"] == "fm"
+    fm, iq = "fm" in cfg["out"], "iq" in cfg["out"]
     n = 1 << log2n
     frames = n // nch
     e = Engine(device)
-    ch = PfbChannelizer(e, nch, make_taps(nch, cfg["ntaps"]), OUT_FM if fm else OUT_IQ, 5.0)
+    ch = PfbChannelizer(e, nch, make_taps(nch, cfg["ntaps"]), (OUT_FM if fm else 0) | (OUT_IQ if iq else 0), 5.0)
     hin = e.pinned((n,), np.complex64)
     base = synth_block(min(n, 1 << 22), nch, 5)
     for i in range(0, n, len(base)):
         hin[i:i + len(base)] = base[:min(len(base), n - i)]
-    hout = e.pinned((nch, frames), np.float32 if fm else np.complex64)
+    hfm = e.pinned((nch, frames), np.float32) if fm else None
+    hiq = e.pinned((nch, frames), np.complex64) if iq else None
     for _ in range(warmup):
-        ch.process(hin, out_iq=None if fm else hout, out_fm=hout if fm else None)
+        ch.process(hin, out_iq=hiq, out_fm=hfm)
     barrier(dist, local)
     t0 = time.perf_counter()
     for _ in range(steps):
-        ch.process(hin, out_iq=None if fm else hout, out_fm=hout if fm else None)   # returns after the D2H completed
+        ch.process(hin, out_iq=hiq, out_fm=hfm)   # returns after the D2H completed
     dt = time.perf_counter() - t0
     barrier(dist, local)
+    hout = hfm if fm else hiq
     chk = float(np.abs(hout[:, -8:]).sum())   # the result is really on the host
+    d2h = (hfm.nbytes if fm else 0) + (hiq.nbytes if iq else 0)
     e.close()
-    return n * steps / dt / 1e6, n * 8, hout.nbytes, chk
+    return n * steps / dt / 1e6, n * 8, d2h, chk
 
 
 def run_e2e_ddc(device, wl, steps, dist, local, log2n=24):

@@ -206,10 +206,10 @@ int pfb_launch_r(rcb_t* h, const PfbParams& p, bool q) {
         default: return pfb_launch_rm<R, PFB_OUT_IQ | PFB_OUT_FM>(h, p, q);
     }
 }
-template <int R, int W = 8, bool PK = true, int PT = 1>
+template <int R, int W = 8, bool PK = true, int PT = 1, int MODE = PFB_OUT_FM>
 int pfb_launch_tma(rcb_t* h, const PfbParams& p, bool query_only) {
-    using G = PfbTmaGeom<R, W>;
-    auto kern = pfb_fm_tma_kernel<R, W, PK, PT>;
+    using G = PfbTmaGeom<R, W, MODE>;
+    auto kern = pfb_fm_tma_kernel<R, W, PK, PT, MODE>;
     const size_t smem = G::smem_bytes;
     if (query_only) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -231,34 +231,42 @@ int pfb_launch_tma(rcb_t* h, const PfbParams& p, bool query_only) {
     return RCB_OK;
 }
 
-template <int R>
-int pfb_launch_tma_p(rcb_t* h, const PfbParams& p, bool q) {
-    if (R == 32 && h->pfb.variant == 16 && h->pfb.PT == 16) return pfb_launch_tma<32, 16, true, 16>(h, p, q);
+// fast kernel dispatch: taps per arm (1, 2, 4, 8, 16) x output mode
+template <int R, int MODE>
+int pfb_launch_tma_pm(rcb_t* h, const PfbParams& p, bool q) {
     switch (h->pfb.PT) {
-        case 2: return pfb_launch_tma<R, 8, true, 2>(h, p, q);
-        case 4: return pfb_launch_tma<R, 8, true, 4>(h, p, q);
-        case 8: return pfb_launch_tma<R, 8, true, 8>(h, p, q);
-        case 16: return pfb_launch_tma<R, 8, true, 16>(h, p, q);
+        case 1: return pfb_launch_tma<R, 8, true, 1, MODE>(h, p, q);
+        case 2: return pfb_launch_tma<R, 8, true, 2, MODE>(h, p, q);
+        case 4: return pfb_launch_tma<R, 8, true, 4, MODE>(h, p, q);
+        case 8: return pfb_launch_tma<R, 8, true, 8, MODE>(h, p, q);
+        case 16: return pfb_launch_tma<R, 8, true, 16, MODE>(h, p, q);
     }
     return RCB_EUNSUPPORTED;
 }
+template <int R>
+int pfb_launch_tma_r(rcb_t* h, const PfbParams& p, bool q) {
+    const int v = h->pfb.variant;
+    if (h->pfb.mode == RCB_OUT_FM) {
+        if (R == 32) {
+            // 1024 channels, FM only: measured variants.  8+ taps per arm run one 16-warp CTA
+            // per SM with 16-frame FIR tasks (fewer history re-reads); RCB_PFB_VARIANT=8 forces 2 x 8 warps.
+            if (h->pfb.PT == 1 && v == 16) return pfb_launch_tma<32, 16, true, 1>(h, p, q);
+            if (h->pfb.PT == 1 && v == 3) return pfb_launch_tma<32, 8, false, 1>(h, p, q);  // scalar-arithmetic v5 kernel
+            if (h->pfb.PT == 16 && v != 8) return pfb_launch_tma<32, 16, true, 16>(h, p, q);
+            if (h->pfb.PT == 8 && v != 8) return pfb_launch_tma<32, 16, true, 8>(h, p, q);
+        }
+        return pfb_launch_tma_pm<R, PFB_OUT_FM>(h, p, q);
+    }
+    if (h->pfb.mode == RCB_OUT_IQ) return pfb_launch_tma_pm<R, PFB_OUT_IQ>(h, p, q);
+    return pfb_launch_tma_pm<R, PFB_OUT_IQ | PFB_OUT_FM>(h, p, q);
+}
 
 int pfb_launch_fast(rcb_t* h, const PfbParams& p, bool q) {
-    if (h->pfb.use_tma && h->pfb.PT > 1) {
-        switch (h->pfb.R) {
-            case 8: return pfb_launch_tma_p<8>(h, p, q);
-            case 16: return pfb_launch_tma_p<16>(h, p, q);
-            case 32: return pfb_launch_tma_p<32>(h, p, q);
-        }
-    }
     if (h->pfb.use_tma) {
         switch (h->pfb.R) {
-            case 8: return pfb_launch_tma<8>(h, p, q);
-            case 16: return pfb_launch_tma<16>(h, p, q);
-            case 32:
-                if (h->pfb.variant == 16) return pfb_launch_tma<32, 16, true>(h, p, q);
-                if (h->pfb.variant == 3) return pfb_launch_tma<32, 8, false>(h, p, q);  // scalar-arithmetic v5 kernel
-                return pfb_launch_tma<32>(h, p, q);
+            case 8: return pfb_launch_tma_r<8>(h, p, q);
+            case 16: return pfb_launch_tma_r<16>(h, p, q);
+            case 32: return pfb_launch_tma_r<32>(h, p, q);
         }
     }
     switch (h->pfb.R) {
@@ -625,7 +633,7 @@ extern "C" int rcb_pfb_config(rcb_t* h, int nchans, const float* taps, int ntaps
         // zero taps; RCB_PFB_VARIANT=9 keeps the register-prefetch kernel for both)
         s.PT = 1;
         while (s.PT < P) s.PT *= 2;
-        s.use_tma = (s.PT <= 16 && out_mask == RCB_OUT_FM && s.variant != 9);
+        s.use_tma = (s.PT <= 16 && s.variant != 9);
         if (s.use_tma && s.PT > 1) {
             std::vector<float> kc((size_t)s.PT * N, 0.f);
             for (int k = 0; k < P; ++k)

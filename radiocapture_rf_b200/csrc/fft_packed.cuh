@@ -198,4 +198,28 @@ __device__ __forceinline__ float2 atan2_nan_p2(float2 im, float2 re) {
     return make_float2(copysignf(r0, im.x), copysignf(r1, im.y));
 }
 
+// same, with the reference's fast_atan2f(0, 0) = 0 (used on conj-products, where no NaN sentinel is needed)
+__device__ __forceinline__ float2 atan2_zero_p2(float2 im, float2 re) {
+    const float ax0 = fabsf(re.x), ay0 = fabsf(im.x), ax1 = fabsf(re.y), ay1 = fabsf(im.y);
+    const float mx0 = fmaxf(ax0, ay0), mx1 = fmaxf(ax1, ay1);
+    const float2 mn = make_float2(fminf(ax0, ay0), fminf(ax1, ay1));
+    const float2 rc = make_float2(mx0 == 0.0f ? 0.0f : rcp_approx(mx0), mx1 == 0.0f ? 0.0f : rcp_approx(mx1));
+    const float2 z = p2mul(mn, rc);
+    const float2 s = p2mul(z, z);
+    float2 r = p2fmas(s, -0.004370174370706081f, make_float2(0.023092154413461685f, 0.023092154413461685f));
+    r = p2fma(r, s, make_float2(-0.05784549191594124f, -0.05784549191594124f));
+    r = p2fma(r, s, make_float2(0.0979914739727974f, 0.0979914739727974f));
+    r = p2fma(r, s, make_float2(-0.13978290557861328f, -0.13978290557861328f));
+    r = p2fma(r, s, make_float2(0.1996297985315323f, 0.1996297985315323f));
+    r = p2fma(r, s, make_float2(-0.33331674337387085f, -0.33331674337387085f));
+    r = p2mul(r, s);
+    r = p2fma(r, z, z);
+    float r0 = r.x, r1 = r.y;
+    r0 = (ay0 > ax0) ? (1.57079632679489661923f - r0) : r0;
+    r1 = (ay1 > ax1) ? (1.57079632679489661923f - r1) : r1;
+    r0 = (re.x < 0.0f) ? (3.14159265358979323846f - r0) : r0;
+    r1 = (re.y < 0.0f) ? (3.14159265358979323846f - r1) : r1;
+    return make_float2(copysignf(r0, im.x), copysignf(r1, im.y));
+}
+
 }  // namespace rcb

@@ -20,7 +20,7 @@
 
 namespace rcb {
 
-template <int R, int W = 8>
+template <int R, int W = 8, int MODE = PFB_OUT_FM>
 struct PfbTmaGeom {
     static constexpr int N = R * R;
     static constexpr int F = 32 / R;
@@ -31,10 +31,12 @@ struct PfbTmaGeom {
     static constexpr int FSW = N + (R == 8 ? 8 : 0);       // frame stride inside a warp's work buffer (complex)
     static constexpr int WORK = F * FSW;                    // complex per warp
     static constexpr size_t work_bytes = (size_t)WARPS * WORK * 8;
-    static constexpr size_t ring_bytes = (size_t)NSLOT * N * 4;
+    // ring element: angle(Y) (4 B) when only FM is produced, Y itself (8 B) when IQ is an output
+    static constexpr size_t ring_bytes = (size_t)NSLOT * N * (MODE == PFB_OUT_FM ? 4 : 8);
     static constexpr size_t tw_bytes = (size_t)N * 8;
     static constexpr size_t taps_bytes = (size_t)N * 4;
     static constexpr size_t smem_bytes = work_bytes + ring_bytes + tw_bytes + taps_bytes + 256;
+    static constexpr int MIN_CTAS = (2 * smem_bytes <= 227 * 1024 && W <= 8) ? 2 : 1;
 };
 
 template <int R>
@@ -72,9 +74,13 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 //             (coalesced 256 B per warp and row; the PT - 1 history rows are L1/L2 hits) and its PT taps,
 //             and produces the 8 filtered samples with PT packed FFMA2 each (re/im pair x broadcast tap),
 //             written to the frame buffers the FFT warps then transform exactly like TMA-landed rows.
-template <int R, int W = 8, bool PK = false, int PT = 1>
-__global__ void __launch_bounds__(32 * W, 16 / W) pfb_fm_tma_kernel(const PfbParams p) {
-    using G = PfbTmaGeom<R, W>;
+// MODE    : PFB_OUT_FM (angle ring, headline), PFB_OUT_IQ or PFB_OUT_IQ | PFB_OUT_FM (the ring holds Y; the demod
+//             phase emits 8 consecutive frames of a channel as two 32 B sector stores of complex64 and, for
+//             IQ + FM, conj-multiplies neighbouring frames and runs the packed atan2 itself).  PK only.
+template <int R, int W = 8, bool PK = false, int PT = 1, int MODE = PFB_OUT_FM>
+__global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pfb_fm_tma_kernel(const PfbParams p) {
+    using G = PfbTmaGeom<R, W, MODE>;
+    static_assert(PK || MODE == PFB_OUT_FM, "IQ outputs are implemented on the packed path only");
     constexpr int THREADS = G::THREADS;
     constexpr int N = G::N, F = G::F, FPI = G::FPI, NSLOT = G::NSLOT, FSW = G::FSW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -201,6 +207,7 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pfb_fm_tma_kernel(const PfbPar
             __syncthreads();
         }
         float ph[R];
+        float yre[MODE == PFB_OUT_FM ? 1 : R], yim[MODE == PFB_OUT_FM ? 1 : R];
         const bool range_last = (it + 1 == cur1);
         // issue the TMA copy of the frames this warp transforms next (its buffer has been fully consumed)
         auto issue_next = [&]() {
@@ -252,11 +259,19 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pfb_fm_tma_kernel(const PfbPar
                 auto tap = [&](auto) { return 1.0f; };
                 fft_packed<R, +1, false>(pr, pi, get, tap);  // (pr[q], pi[q]) = Y[ll + R*(2q)], Y[ll + R*(2q+1)]
             }
+            if constexpr (MODE == PFB_OUT_FM) {
 #pragma unroll
-            for (int q = 0; q < R / 2; ++q) {
-                const float2 a = atan2_nan_p2(pi[q], pr[q]);
-                ph[2 * q] = a.x;
-                ph[2 * q + 1] = a.y;
+                for (int q = 0; q < R / 2; ++q) {
+                    const float2 a = atan2_nan_p2(pi[q], pr[q]);
+                    ph[2 * q] = a.x;
+                    ph[2 * q + 1] = a.y;
+                }
+            } else {  // keep Y: written to the ring below (needs pr/pi in scope -> stash in yre/yim)
+#pragma unroll
+                for (int q = 0; q < R / 2; ++q) {
+                    yre[2 * q] = pr[q].x; yre[2 * q + 1] = pr[q].y;
+                    yim[2 * q] = pi[q].x; yim[2 * q + 1] = pi[q].y;
+                }
             }
         } else {
         float2 v[R];
@@ -307,10 +322,14 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pfb_fm_tma_kernel(const PfbPar
             cta_par ^= 1u;
         }
         first_ever = false;
-        {
+        if constexpr (MODE == PFB_OUT_FM) {
             float* fb = ring + slot * N;
 #pragma unroll
             for (int m2 = 0; m2 < R; ++m2) fb[m2 * R + ll] = ph[m2];
+        } else {
+            float2* fb = reinterpret_cast<float2*>(ring) + slot * N;
+#pragma unroll
+            for (int m2 = 0; m2 < R; ++m2) fb[m2 * R + ll] = make_float2(yre[m2], yim[m2]);
         }
         __syncthreads();
         if (range_first) {
@@ -333,8 +352,9 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pfb_fm_tma_kernel(const PfbPar
             s = (s >= NSLOT) ? s - NSLOT : s;
             const bool full = (t0 + 8 <= p.T) && !(p.debug_flags & 1);  // RCB_PFB_DEBUG=1: measurement only
             // (m0, t0) -> element index; consecutive channels are `rowstride` apart in both layouts
-            float* dst0 = p.out_fm + pfb_out_index(p, m0, t0);
+            float* dst0 = (MODE & PFB_OUT_FM) ? p.out_fm + pfb_out_index(p, m0, t0) : nullptr;
             const long long rowstride = (p.oblock_log2 > 0) ? (1LL << p.oblock_log2) : p.ostride;
+            if constexpr (MODE == PFB_OUT_FM) {
             float pw[9][CPT];  // all ring loads first (9 vector LDS), then CPT*8 independent wrap chains
 #pragma unroll
             for (int j = 0; j < 9; ++j) {
@@ -382,12 +402,82 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pfb_fm_tma_kernel(const PfbPar
             for (int q = 0; q < CPT; ++q) {
                 float* dst = dst0 + q * rowstride;
                 if (full) {
-                    if (PT > 1 && (p.debug_flags & 8)) st_global_v8_hint(dst, o[q], pol_stream);
+                    if (PT > 1 && !(p.debug_flags & 8)) st_global_v8_hint(dst, o[q], pol_stream);  // keeps the input rows in L2 (+6 %)
                     else st_global_v8(dst, o[q]);
                 } else if (!(p.debug_flags & 1) || o[q][0] == 123456.789f) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         if (t0 + j < p.T) dst[j] = o[q][j];
+                }
+            }
+                    } else {
+                const float2* ring2 = reinterpret_cast<const float2*>(ring);
+                float2* dq0 = (MODE & PFB_OUT_IQ) ? p.out_iq + pfb_out_index(p, m0, t0) : nullptr;
+                constexpr int CW = (CPT >= 2) ? 2 : 1;  // channels handled together
+#pragma unroll
+                for (int q0 = 0; q0 < CPT; q0 += CW) {
+                    float2 y[9][CW];
+                    int sj = s;
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) {
+                        const float2* src = ring2 + sj * N + m0 + q0;
+                        if constexpr (CW == 2) {
+                            const float4 t = *reinterpret_cast<const float4*>(src);
+                            y[j][0] = make_float2(t.x, t.y);
+                            y[j][1] = make_float2(t.z, t.w);
+                        } else {
+                            y[j][0] = *src;
+                        }
+                        sj = (sj + 1 == NSLOT) ? 0 : sj + 1;
+                    }
+                    if constexpr ((MODE & PFB_OUT_IQ) != 0) {
+#pragma unroll
+                        for (int c = 0; c < CW; ++c) {
+                            float2* dst = dq0 + (q0 + c) * rowstride;
+                            if (full) {
+#pragma unroll
+                                for (int hh = 0; hh < 2; ++hh) {
+                                    float o[8];
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        o[2 * j] = y[1 + 4 * hh + j][c].x;
+                                        o[2 * j + 1] = y[1 + 4 * hh + j][c].y;
+                                    }
+                                    st_global_v8(reinterpret_cast<float*>(dst + 4 * hh), o);
+                                }
+                            } else if (!(p.debug_flags & 1)) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    if (t0 + j < p.T) dst[j] = y[j + 1][c];
+                            }
+                        }
+                    }
+                    if constexpr ((MODE & PFB_OUT_FM) != 0) {
+                        float o[CW][8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if constexpr (CW == 2) {  // p = y[j+1] conj(y[j]) for both channels, packed atan2
+                                const float2 a0 = cmul_conj(y[j + 1][0], y[j][0]), a1 = cmul_conj(y[j + 1][1], y[j][1]);
+                                const float2 ang = atan2_zero_p2(make_float2(a0.y, a1.y), make_float2(a0.x, a1.x));
+                                o[0][j] = p.gain * ang.x;
+                                o[1][j] = p.gain * ang.y;
+                            } else {
+                                const float2 a0 = cmul_conj(y[j + 1][0], y[j][0]);
+                                o[0][j] = p.gain * atan2_fast(a0.y, a0.x);
+                            }
+                        }
+#pragma unroll
+                        for (int c = 0; c < CW; ++c) {
+                            float* dst = dst0 + (q0 + c) * rowstride;
+                            if (full) {
+                                st_global_v8(dst, o[c]);
+                            } else if (!(p.debug_flags & 1)) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    if (t0 + j < p.T) dst[j] = o[c][j];
+                            }
+                        }
+                    }
                 }
             }
         }
