@@ -532,6 +532,15 @@ def run_b200(args):
                                     "value": cp.n * stp * world / (msp * 1e-3) / 1e6,
                                     "roofline_frac": cp.n * stp * 12 / (msp * 1e-3) / 1e9 / peak}
             cp.close()
+        if args.out_block != 8:  # frame-major blocks of 8: each CTA iteration writes one contiguous 32 KB piece
+            c8 = StreamCtx(device, wl, seed=3, log2n=args.log2n, out_block=8)
+            ms8, _, _, _ = timed_loop([c8], max(3, args.steps // 2), 3, dist, local)
+            ms8 = allreduce_max(dist, local, ms8)
+            st8 = max(3, args.steps // 2)
+            also["out_block_8"] = {"workload": cfg["desc"] + ", output channel-major inside blocks of 8 frames",
+                                   "unit": "Msps", "value": c8.n * st8 * world / (ms8 * 1e-3) / 1e6,
+                                   "roofline_frac": c8.n * st8 * 12 / (ms8 * 1e-3) / 1e9 / peak}
+            c8.close()
         c16 = StreamCtx(device, "cfg3_p16", seed=3, log2n=args.log2n, out_block=args.out_block)
         ms16, _, _, _ = timed_loop([c16], max(3, args.steps // 2), 2, dist, local)
         ms16 = allreduce_max(dist, local, ms16)

@@ -36,6 +36,7 @@ struct DdcChan {
     double center_freq = 0, samp_rate = 1;
     std::vector<float> taps;
     float2* d_ctaps_rev = nullptr;
+    float4* d_ctaps4_rev = nullptr;
     float2* d_out_iq = nullptr;
     float* d_out_fm = nullptr;
     float2* d_prev = nullptr;
@@ -206,10 +207,10 @@ int pfb_launch_r(rcb_t* h, const PfbParams& p, bool q) {
         default: return pfb_launch_rm<R, PFB_OUT_IQ | PFB_OUT_FM>(h, p, q);
     }
 }
-template <int R, int W = 8, bool PK = true, int PT = 1, int MODE = PFB_OUT_FM>
+template <int R, int W = 8, bool PK = true, int PT = 1, int MODE = PFB_OUT_FM, bool OB8 = false>
 int pfb_launch_tma(rcb_t* h, const PfbParams& p, bool query_only) {
     using G = PfbTmaGeom<R, W, MODE>;
-    auto kern = pfb_fm_tma_kernel<R, W, PK, PT, MODE>;
+    auto kern = pfb_fm_tma_kernel<R, W, PK, PT, MODE, OB8>;
     const size_t smem = G::smem_bytes;
     if (query_only) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -218,6 +219,13 @@ int pfb_launch_tma(rcb_t* h, const PfbParams& p, bool query_only) {
         h->pfb.blocks_per_sm = std::max(nb, 1);
         h->pfb.smem = smem;
         return RCB_OK;
+    }
+    if (OB8) {  // layout variants are picked per launch: opt in to the shared-memory size once
+        static bool attr_set = false;
+        if (!attr_set) {
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
     }
     const int NI = (p.T + G::FPI - 1) / G::FPI;
     const int grid = std::max(1, std::min(NI, h->pfb.blocks_per_sm * h->sm_count));
@@ -251,6 +259,7 @@ int pfb_launch_tma_r(rcb_t* h, const PfbParams& p, bool q) {
             // 1024 channels, FM only: measured variants.  8+ taps per arm run one 16-warp CTA
             // per SM with 16-frame FIR tasks (fewer history re-reads); RCB_PFB_VARIANT=8 forces 2 x 8 warps.
             if (h->pfb.PT == 1 && v == 16) return pfb_launch_tma<32, 16, true, 1>(h, p, q);
+            if (h->pfb.PT == 1 && !q && p.oblock_log2 == 3 && p.out_fm) return pfb_launch_tma<32, 8, true, 1, PFB_OUT_FM, true>(h, p, q);
             if (h->pfb.PT == 1 && v == 3) return pfb_launch_tma<32, 8, false, 1>(h, p, q);  // scalar-arithmetic v5 kernel
             if (h->pfb.PT == 16 && v != 8) return pfb_launch_tma<32, 16, true, 16>(h, p, q);
             if (h->pfb.PT == 8 && v != 8) return pfb_launch_tma<32, 16, true, 8>(h, p, q);
@@ -451,6 +460,7 @@ extern "C" int rcb_close(rcb_t* h) {
     pfb_free(h);
     for (auto& kv : h->ddc.chans) {
         cudaFree(kv.second.d_ctaps_rev);
+        cudaFree(kv.second.d_ctaps4_rev);
         cudaFree(kv.second.d_out_iq);
         cudaFree(kv.second.d_out_fm);
         cudaFree(kv.second.d_prev);
@@ -813,6 +823,12 @@ int ddc_upload_taps(rcb_t* h, DdcChan& c) {
     c.d_ctaps_rev = nullptr;
     CK(cudaMalloc(&c.d_ctaps_rev, sizeof(float2) * c.ntaps));
     CK(cudaMemcpyAsync(c.d_ctaps_rev, rev.data(), sizeof(float2) * c.ntaps, cudaMemcpyHostToDevice, h->stream));
+    std::vector<float4> rev4(c.ntaps);
+    for (int r = 0; r < c.ntaps; ++r) rev4[r] = make_float4(rev[r].x, rev[r].y, -rev[r].y, rev[r].x);
+    if (c.d_ctaps4_rev) cudaFree(c.d_ctaps4_rev);
+    c.d_ctaps4_rev = nullptr;
+    CK(cudaMalloc(&c.d_ctaps4_rev, sizeof(float4) * c.ntaps));
+    CK(cudaMemcpyAsync(c.d_ctaps4_rev, rev4.data(), sizeof(float4) * c.ntaps, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     double cyc = c.center_freq * (double)c.decim / c.samp_rate;
     cyc -= floor(cyc);
@@ -897,6 +913,7 @@ extern "C" int rcb_ddc_close(rcb_t* h, int chan_id) {
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     cudaFree(it->second.d_ctaps_rev);
+    cudaFree(it->second.d_ctaps4_rev);
     cudaFree(it->second.d_out_iq);
     cudaFree(it->second.d_out_fm);
     cudaFree(it->second.d_prev);
@@ -968,6 +985,7 @@ extern "C" int rcb_ddc_process(rcb_t* h, const void* iq, size_t nsamples, int in
             }
             DdcChanDev& dv = d.h_chans[ci++];
             dv.ctaps_rev = c.d_ctaps_rev;
+            dv.ctaps4_rev = c.d_ctaps4_rev;
             dv.out_iq = c.d_out_iq;
             dv.out_fm = (c.out_mask & RCB_OUT_FM) ? c.d_out_fm : nullptr;
             dv.prev = c.d_prev;
@@ -1036,16 +1054,23 @@ extern "C" int rcb_ddc_process(rcb_t* h, const void* iq, size_t nsamples, int in
                     // output quads per CTA: as many as the group's channel count leaves warps for and smem allows
                     const size_t per_group = std::min<size_t>(16, b.second.size());
                     int oq = per_group <= 4 ? 8 : (per_group <= 8 ? 4 : 2);
-                    while (oq > 2 && (size_t)((4 * oq - 1) * decim + ntaps) * sizeof(float2) > 160 * 1024) oq >>= 1;
-                    const size_t smem = (size_t)((4 * oq - 1) * decim + ntaps) * sizeof(float2);
+                    // a lone channel: 16 outputs x 1 channel per warp (no idle accumulators) when the tile fits
+                    const bool lone = (per_group == 1 && (size_t)(127 * decim + ntaps) * sizeof(float2) <= 160 * 1024);
+                    const int opw = lone ? 16 : 4;
+                    while (oq > 2 && (size_t)((opw * oq - 1) * decim + ntaps) * sizeof(float2) > 160 * 1024) oq >>= 1;
+                    const size_t smem = (size_t)((opw * oq - 1) * decim + ntaps) * sizeof(float2);
                     if (smem > d.tile_smem_attr) {
                         CK(cudaFuncSetAttribute(ddc_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                         CK(cudaFuncSetAttribute(ddc_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                         CK(cudaFuncSetAttribute(ddc_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        CK(cudaFuncSetAttribute(ddc_tile_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                         d.tile_smem_attr = smem;
                     }
-                    dim3 grid((unsigned)((nout + 4 * oq - 1) / (4 * oq)), (unsigned)ng);
-                    if (oq == 8)
+                    dim3 grid((unsigned)((nout + opw * oq - 1) / (opw * oq)), (unsigned)ng);
+                    if (lone)
+                        ddc_tile_kernel<8, 1><<<grid, 256, smem, h->stream>>>(d.d_chans, d.d_groups + gi, d_x, (long long)nsamples,
+                                                                              d.d_hist[d.hist_cur], kDdcHistCap);
+                    else if (oq == 8)
                         ddc_tile_kernel<8><<<grid, 256, smem, h->stream>>>(d.d_chans, d.d_groups + gi, d_x, (long long)nsamples,
                                                                            d.d_hist[d.hist_cur], kDdcHistCap);
                     else if (oq == 4)

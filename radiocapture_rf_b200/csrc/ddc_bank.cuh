@@ -16,11 +16,14 @@
 // The optional FM demod of the narrowband result runs in ddc_fm_kernel (output rates are fs/D).
 #pragma once
 #include "common.cuh"
+#include "fft_packed.cuh"
 
 namespace rcb {
 
 struct DdcChanDev {
     const float2* ctaps_rev;  // [ntaps]  ct_rev[r] = h[K-1-r] e^{+j w (K-1-r)}
+    const float4* ctaps4_rev; // [ntaps]  (t.re, t.im, -t.im, t.re) of ct_rev[r]: the two f32x2 multiplicands of a
+                              //          packed complex MAC  acc += x.re * (t.re, t.im) + x.im * (-t.im, t.re)
     float2* out_iq;           // [nout] this block's outputs
     float* out_fm;            // [nout] or null
     float2* prev;             // device scalar: last output of the previous block (FM carry)
@@ -110,20 +113,23 @@ struct DdcGroupDev {
     long long s_first;
 };
 
-// OQ = output quads per CTA (8 / 4 / 2 for groups of <= 4 / <= 8 / <= 16 channels), 8/OQ channel quads.
-// grid (ceil(nout / (4*OQ)), ngroups), block 256, dynamic smem ((4*OQ-1)*decim + ntaps) * 8 bytes
-template <int OQ>
+// OQ = output groups per CTA (8 / 4 / 2 for groups of <= 4 / <= 8 / <= 16 channels), 8/OQ channel groups.
+// CPW = channels per warp (4, or 1 for a lone channel), OPW = 16 / CPW consecutive outputs per warp: every lane
+// keeps OPW x CPW = 16 complex accumulators either way (a lone channel would waste 3/4 of a 4 x 4 block).
+// grid (ceil(nout / (OPW*OQ)), ngroups), block 256, dynamic smem ((OPW*OQ-1)*decim + ntaps) * 8 bytes
+template <int OQ, int CPW = 4>
 __global__ void __launch_bounds__(256) ddc_tile_kernel(const DdcChanDev* __restrict__ chans,
                                                        const DdcGroupDev* __restrict__ groups,
                                                        const float2* __restrict__ x, long long nsamp,
                                                        const float2* __restrict__ hist, int hist_cap) {
+    constexpr int OPW = 16 / CPW;
     extern __shared__ __align__(16) float2 ddc_tile[];
     const DdcGroupDev& g = groups[blockIdx.y];
-    const int o_base = blockIdx.x * (4 * OQ);
+    const int o_base = blockIdx.x * (OPW * OQ);
     if (o_base >= g.nout) return;
     const int D = g.decim, K = g.ntaps;
     const long long w0 = g.s_first + (long long)o_base * D - (K - 1);
-    const int tile_len = (4 * OQ - 1) * D + K;
+    const int tile_len = (OPW * OQ - 1) * D + K;
     for (int t = threadIdx.x; t < tile_len; t += 256) {
         const long long idx = w0 + t;
         ddc_tile[t] = (idx < nsamp) ? ddc_x_at(x, hist, hist_cap, idx) : make_float2(0.f, 0.f);
@@ -131,53 +137,56 @@ __global__ void __launch_bounds__(256) ddc_tile_kernel(const DdcChanDev* __restr
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int oq = warp % OQ, cq = warp / OQ;
-    if (cq * 4 >= g.nch || o_base + oq * 4 >= g.nout) return;
-    int cidx[4];
-    const float2* tp[4];
+    if (cq * CPW >= g.nch || o_base + oq * OPW >= g.nout) return;
+    int cidx[CPW];
+    const float4* tp[CPW];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        cidx[i] = g.ch[cq * 4 + i];
-        tp[i] = chans[cidx[i] >= 0 ? cidx[i] : g.ch[cq * 4]].ctaps_rev;
+    for (int i = 0; i < CPW; ++i) {
+        cidx[i] = g.ch[cq * CPW + i];
+        tp[i] = chans[cidx[i] >= 0 ? cidx[i] : g.ch[cq * CPW]].ctaps4_rev;
     }
-    float2 acc[4][4];
+    float2 acc[OPW][CPW];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+    for (int q = 0; q < OPW; ++q)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[q][i] = make_float2(0.f, 0.f);
-    const float2* xt = ddc_tile + (oq * 4) * D;
+        for (int i = 0; i < CPW; ++i) acc[q][i] = make_float2(0.f, 0.f);
+    const float2* xt = ddc_tile + (oq * OPW) * D;
     for (int r = lane; r < K; r += 32) {
-        float2 xv[4], tv[4];
+        float2 xv[OPW];
+        float4 tv[CPW];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) xv[q] = xt[q * D + r];
+        for (int q = 0; q < OPW; ++q) xv[q] = xt[q * D + r];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) tv[i] = __ldg(tp[i] + r);
+        for (int i = 0; i < CPW; ++i) tv[i] = __ldg(tp[i] + r);
+        // complex MAC = two packed FFMA2 (sample part broadcast, tap pair / rotated tap pair): 32 issue slots
+        // per 16 MACs instead of 64 scalar FFMA
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < OPW; ++q)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                acc[q][i].x = fmaf(tv[i].x, xv[q].x, fmaf(-tv[i].y, xv[q].y, acc[q][i].x));
-                acc[q][i].y = fmaf(tv[i].x, xv[q].y, fmaf(tv[i].y, xv[q].x, acc[q][i].y));
+            for (int i = 0; i < CPW; ++i) {
+                acc[q][i] = p2fmas(make_float2(tv[i].x, tv[i].y), xv[q].x, acc[q][i]);
+                acc[q][i] = p2fmas(make_float2(tv[i].z, tv[i].w), xv[q].y, acc[q][i]);
             }
     }
     float2 mine = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+    for (int q = 0; q < OPW; ++q)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < CPW; ++i) {
             float2 a = acc[q][i];
 #pragma unroll
             for (int sft = 16; sft > 0; sft >>= 1) {
                 a.x += __shfl_xor_sync(0xffffffffu, a.x, sft);
                 a.y += __shfl_xor_sync(0xffffffffu, a.y, sft);
             }
-            if (lane == q * 4 + i) mine = a;
+            if (lane == q * CPW + i) mine = a;
         }
     if (lane < 16) {
-        const int q = lane >> 2, i = lane & 3;
-        const int o = o_base + oq * 4 + q;
+        const int q = lane / CPW, i = lane % CPW;
+        const int o = o_base + oq * OPW + q;
         int ci = cidx[0];
 #pragma unroll
-        for (int u = 1; u < 4; ++u)
+        for (int u = 1; u < CPW; ++u)
             if (i == u) ci = cidx[u];
         if (ci >= 0 && o < g.nout) {
             const DdcChanDev& ch = chans[ci];

@@ -24,6 +24,7 @@
 
 #include "common.cuh"
 #include "fft_inreg.cuh"
+#include "fft_packed.cuh"
 
 namespace rcb {
 
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(256, 2) fft_cols_kernel(const FftParams p) {
     for (int jj = 0; jj < R; ++jj) v[jj] = region[col * CS + jj * R + ll];
     __syncthreads();  // everyone holds its column in registers: the region can be reused
     float2* buf = region + col * FS;
-    warp_fft_2pass<R, -1, false>(v, buf, tws, ll);  // v[m2] = A[k1 = ll + R*m2] for column c0+col
+    warp_fft_2pass_packed<R, -1, false>(v, buf, tws, ll);  // v[m2] = A[k1 = ll + R*m2] for column c0+col
     __syncthreads();  // all per-frame scratch dead: region becomes the [k1][CB] output tile
     {
         const int n2 = c0 + col;
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(256, 2) fft_rows_kernel(const FftParams p) {
 #pragma unroll
     for (int jj = 0; jj < R; ++jj) v[jj] = __ldcg(src + jj * R + ll);
     float2* buf = bufs + row * FS;
-    warp_fft_2pass<R, -1, false>(v, buf, tws, ll);  // v[m2] = X[k1 + L1*k2], k2 = ll + R*m2
+    warp_fft_2pass_packed<R, -1, false>(v, buf, tws, ll);  // v[m2] = X[k1 + L1*k2], k2 = ll + R*m2
     float* fb = reinterpret_cast<float*>(buf);
 #pragma unroll
     for (int m2 = 0; m2 < R; ++m2) {

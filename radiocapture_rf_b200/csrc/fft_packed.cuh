@@ -222,4 +222,44 @@ __device__ __forceinline__ float2 atan2_zero_p2(float2 im, float2 re) {
     return make_float2(copysignf(r0, im.x), copysignf(r1, im.y));
 }
 
+// Drop-in packed replacement of warp_fft_2pass (fft_inreg.cuh): N = R*R point DFT of one frame spread over
+// R lanes, both radix-R passes on f32x2 pairs, same scratch / twiddle table layout (row stride R+2).
+template <int R, int SIGN, bool REV>
+__device__ __forceinline__ void warp_fft_2pass_packed(float2 (&v)[R], float2* __restrict__ buf,
+                                                      const float2* __restrict__ tws, const int ll) {
+    constexpr int S = R + 2;
+    float2 pr[R / 2], pi[R / 2];
+    {
+        auto get = [&](auto j) { return v[decltype(j)::value]; };
+        auto tap = [&](auto) { return 1.0f; };
+        fft_packed<R, SIGN, false>(pr, pi, get, tap);  // (pr[c], pi[c]) = first-pass outputs m1 = 2c, 2c+1
+    }
+    {
+        const float4* twp = reinterpret_cast<const float4*>(tws + ll * S);
+        float4* bp = reinterpret_cast<float4*>(buf + ll * S);
+#pragma unroll
+        for (int c = 0; c < R / 2; ++c) {
+            const float4 t = twp[c];
+            const float2 b0 = make_float2(fmaf(pr[c].x, t.x, -pi[c].x * t.y), fmaf(pr[c].x, t.y, pi[c].x * t.x));
+            const float2 b1 = make_float2(fmaf(pr[c].y, t.z, -pi[c].y * t.w), fmaf(pr[c].y, t.w, pi[c].y * t.z));
+            bp[c] = make_float4(b0.x, b0.y, b1.x, b1.y);
+        }
+    }
+    __syncwarp();
+    {
+        float2 u[R];
+#pragma unroll
+        for (int l2 = 0; l2 < R; ++l2) u[REV ? (R - 1 - l2) : l2] = buf[l2 * S + ll];
+        auto get = [&](auto j) { return u[decltype(j)::value]; };
+        auto tap = [&](auto) { return 1.0f; };
+        fft_packed<R, SIGN, false>(pr, pi, get, tap);
+    }
+#pragma unroll
+    for (int q = 0; q < R / 2; ++q) {  // v[m2] = X[ll + R*m2]
+        v[2 * q] = make_float2(pr[q].x, pi[q].x);
+        v[2 * q + 1] = make_float2(pr[q].y, pi[q].y);
+    }
+    __syncwarp();
+}
+
 }  // namespace rcb

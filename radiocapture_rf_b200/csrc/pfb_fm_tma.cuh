@@ -77,8 +77,13 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // MODE    : PFB_OUT_FM (angle ring, headline), PFB_OUT_IQ or PFB_OUT_IQ | PFB_OUT_FM (the ring holds Y; the demod
 //             phase emits 8 consecutive frames of a channel as two 32 B sector stores of complex64 and, for
 //             IQ + FM, conj-multiplies neighbouring frames and runs the packed atan2 itself).  PK only.
-template <int R, int W = 8, bool PK = false, int PT = 1, int MODE = PFB_OUT_FM>
+// OB8     : the device output layout is channel-major inside time blocks of exactly 8 frames (oblock_log2 == 3),
+//             i.e. one CTA iteration writes one contiguous 32 KB piece.  The demod threads then take channels
+//             lane + 32 q, so a store instruction covers 1 KB of contiguous memory (8 full lines instead of 32
+//             scattered sectors: a quarter of the LSU wavefronts of the store path).
+template <int R, int W = 8, bool PK = false, int PT = 1, int MODE = PFB_OUT_FM, bool OB8 = false>
 __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pfb_fm_tma_kernel(const PfbParams p) {
+    static_assert(!OB8 || (R == 32 && W == 8 && MODE == PFB_OUT_FM), "OB8 is an FM-only 1024-channel layout variant");
     using G = PfbTmaGeom<R, W, MODE>;
     static_assert(PK || MODE == PFB_OUT_FM, "IQ outputs are implemented on the packed path only");
     constexpr int THREADS = G::THREADS;
@@ -345,8 +350,10 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
             // covers 64 contiguous bytes of each channel row (half the L2 write requests of 32 B sectors)
             constexpr int GRP = FPI / 8;
             constexpr bool kPairLanes = (GRP == 2 && CPT >= 2);
+            constexpr int MSTR = OB8 ? 32 : 1;  // channel stride between the CPT channels of a thread
             const int g = kPairLanes ? (lane >> 4) : tid / (N / CPT);
-            const int m0 = kPairLanes ? (warp * 16 + (lane & 15)) * CPT : (tid % (N / CPT)) * CPT;
+            const int m0 = OB8 ? (warp * (32 * CPT) + lane)
+                               : (kPairLanes ? (warp * 16 + (lane & 15)) * CPT : (tid % (N / CPT)) * CPT);
             const long long t0 = (long long)it * FPI + 8 * g;
             int s = base_slot + 8 * g;
             s = (s >= NSLOT) ? s - NSLOT : s;
@@ -359,7 +366,10 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
 #pragma unroll
             for (int j = 0; j < 9; ++j) {
                 const float* src = ring + s * N + m0;
-                if constexpr (CPT == 4) {
+                if constexpr (OB8) {
+#pragma unroll
+                    for (int q = 0; q < CPT; ++q) pw[j][q] = src[32 * q];
+                } else if constexpr (CPT == 4) {
                     const float4 t = *reinterpret_cast<const float4*>(src);
                     pw[j][0] = t.x; pw[j][1] = t.y; pw[j][2] = t.z; pw[j][3] = t.w;
                 } else if constexpr (CPT == 2) {
@@ -400,7 +410,7 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
             }
 #pragma unroll
             for (int q = 0; q < CPT; ++q) {
-                float* dst = dst0 + q * rowstride;
+                float* dst = dst0 + q * MSTR * rowstride;
                 if (full) {
                     if (PT > 1 && !(p.debug_flags & 8)) st_global_v8_hint(dst, o[q], pol_stream);  // keeps the input rows in L2 (+6 %)
                     else st_global_v8(dst, o[q]);

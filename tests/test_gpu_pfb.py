@@ -157,12 +157,13 @@ def test_pfb_tone_lands_in_its_bin(engine):
     np.testing.assert_allclose(fm[m, 64:], 5.0 * 2 * np.pi * df, rtol=0, atol=2e-4)
 
 
-@pytest.mark.parametrize("n,tpa,mode", [(1024, 0.25, OUT_FM), (256, 4, OUT_IQ | OUT_FM), (20, None, OUT_FM)])
-def test_pfb_blocked_device_output_layout(engine, n, tpa, mode):
+@pytest.mark.parametrize("n,tpa,mode,block", [(1024, 0.25, OUT_FM, 64), (256, 4, OUT_IQ | OUT_FM, 64), (20, None, OUT_FM, 64),
+                                              (1024, 0.25, OUT_FM, 8), (1024, 2, OUT_IQ | OUT_FM, 8), (64, 2, OUT_FM, 8)])
+def test_pfb_blocked_device_output_layout(engine, n, tpa, mode, block):
     """rcb_pfb_set_out_block: channel-major inside time blocks (device-resident outputs) carries exactly
     the same samples as the plain [N][T] layout, including a ragged last block."""
     taps = fd.pfb_prototype(n, tpa) if tpa else fd.pfb_prototype(n)
-    frames, block = 300, 64
+    frames = 300
     x, _ = synth.pfb_stream(n * frames, 1.0e6 * n / 4.0, n, 21)
     ch = PfbChannelizer(engine, n, taps, mode, 5.0)
     iq_ref, fm_ref = ch.process(x)
