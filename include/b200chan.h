@@ -86,7 +86,9 @@ int rcb_pfb_reset(rcb_t* h);
  * [N][out_stride]): element (m, n) at ((n / frames) * nchans + m) * frames + n % frames.  Each channel is then
  * delivered as contiguous `frames`-sample messages - the unit a zeromq.pub_sink sends (channel.py:36) - and the
  * rows one kernel iteration writes stay within a few MB (TLB / DRAM page locality).  The output buffer must hold
- * ceil(nout / frames) * nchans * frames elements; out_stride is ignored.  Device-resident outputs only. */
+ * ceil(nout / frames) * nchans * frames elements; out_stride is ignored.  Device-resident outputs only.
+ * frames = 8 is the kernel's native granularity (one CTA iteration = one contiguous nchans*8-element piece,
+ * full-line stores: +7 % on the 1024-channel FM path) for consumers that run on the GPU themselves. */
 int rcb_pfb_set_out_block(rcb_t* h, int frames);
 int rcb_pfb_process(rcb_t* h, const void* iq, size_t nsamples, int in_mem,
                     void* out_iq, void* out_fm, size_t out_stride, int out_mem, size_t* nout);
