@@ -22,9 +22,12 @@
 
 #include <vector>
 
+#include <cuda.h>  // CUtensorMap (the encoder is fetched with cudaGetDriverEntryPoint: no libcuda link dependency)
+
 #include "common.cuh"
 #include "fft_inreg.cuh"
 #include "fft_packed.cuh"
+#include "pfb_fm_tma.cuh"  // mbarrier / TMA helpers
 
 namespace rcb {
 
@@ -146,6 +149,120 @@ __global__ void __launch_bounds__(256, 2) fft_cols_kernel(const FftParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// A (TMA version): column FFTs.  grid (L2/CB, SB), block 256, 2 CTAs/SM.
+//   * the [L1 rows][CB columns] tile of one frame (CB = 256/R columns = 64..256 B per row) is fetched by ONE
+//     thread as a 2-D TMA tensor copy (UTMALDG) straight into shared memory - no registers are tied up by loads in
+//     flight and no transposing store pass; the window column (32 B sectors, L2 resident) and the tables are loaded
+//     while the copy flies;
+//   * L1 = R*R point DFT of a column, n1 = R a + b: lane (b, c) of warp b/BL runs the first packed radix-R pass
+//     over a (rows R a + b: a warp reads BL full rows = 256 contiguous bytes per step, conflict free) with the
+//     window multiply folded into the scalar DIF stage, applies W_L1^{-b ka}, and writes V[ka][b][c] back into the
+//     tile (row pitch R+1 rows per ka for R = 32 so the second pass reads conflict free);
+//   * second packed radix-R pass over b by lane (ka, c), W_L^{-n2 k1} = W_L^{-n2 ka} (one sincospi per lane)
+//     x W_L^{-n2 R kb} (256-entry table per CTA), 64..256 B row segments of B[k1][n2] to the L2-resident scratch.
+// ---------------------------------------------------------------------------------------------
+template <int R>
+struct FftColsGeom {
+    static constexpr int L1 = R * R;
+    static constexpr int CB = 256 / R;  // columns per CTA
+    static constexpr int BL = R / 8;    // b (pass 1) / ka (pass 2) values per warp
+    static constexpr int RP = R + (R == 32 ? 1 : 0);
+    static constexpr int S = R + 2;     // row stride of the inner twiddle table (tw1)
+    static constexpr int BOX_ROWS = L1 < 256 ? L1 : 256;
+    static constexpr size_t tile_bytes = (size_t)R * RP * CB * 8;
+    static constexpr size_t smem = tile_bytes + (size_t)R * S * 8 + (size_t)R * CB * 8 + 64;
+};
+
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* tm, int x, int y, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(tm), "r"(x), "r"(y), "r"(smem_u32(bar))
+        : "memory");
+}
+
+template <int R>
+__global__ void __launch_bounds__(256, 2) fft_cols_tma_kernel(const __grid_constant__ CUtensorMap tm, const FftParams p) {
+    using G = FftColsGeom<R>;
+    constexpr int L1 = G::L1, CB = G::CB, BL = G::BL, RP = G::RP, S = G::S;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* tile = reinterpret_cast<float2*>(smem_raw);
+    float2* tws = reinterpret_cast<float2*>(smem_raw + G::tile_bytes);
+    float2* rho = tws + R * S;  // [kb][c] = W_L^{-(c0 + c) R kb}
+    uint64_t* bar = reinterpret_cast<uint64_t*>(rho + R * CB);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sub = lane / CB, c = lane % CB;
+    const int b = warp * BL + sub;  // pass 1: residue b of n1;  pass 2: ka
+    const int c0 = blockIdx.x * CB, f = blockIdx.y;
+    const int n2 = c0 + c;
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, (uint32_t)(L1 * CB * 8));
+#pragma unroll
+        for (int r0 = 0; r0 < L1; r0 += G::BOX_ROWS) tma_load_2d(tile + r0 * CB, &tm, c0 * 2, f * L1 + r0, bar);
+    }
+    float wv[R];  // window column of this lane: w[(R a + b) L2 + n2]
+#pragma unroll
+    for (int a = 0; a < R; ++a) wv[a] = __ldg(p.window + (size_t)(R * a + b) * p.L2 + n2);
+    for (int i = tid; i < R * S; i += 256) tws[i] = p.tw1[i];
+    {
+        const int kb = tid / CB, cc = tid % CB;  // R * CB = 256 entries, one per thread
+        const unsigned e = ((unsigned)(c0 + cc) * (unsigned)(R * kb)) & (unsigned)(p.L - 1);
+        float sn, cs;
+        sincospif(-2.0f * (float)e / (float)p.L, &sn, &cs);
+        rho[kb * CB + cc] = make_float2(cs, sn);
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+
+    float2 pr[R / 2], pi[R / 2];
+    {
+        auto get = [&](auto j) { return tile[(R * decltype(j)::value + b) * CB + c]; };
+        auto tap = [&](auto j) { return wv[decltype(j)::value]; };
+        fft_packed<R, -1, true>(pr, pi, get, tap);  // (pr[q], pi[q]) = V[ka = 2q], V[2q + 1]
+    }
+    __syncthreads();  // every lane holds its column: the tile becomes the exchange buffer
+    {
+        const float4* twp = reinterpret_cast<const float4*>(tws + b * S);
+#pragma unroll
+        for (int q = 0; q < R / 2; ++q) {
+            const float4 t = twp[q];
+            tile[((2 * q) * RP + b) * CB + c] =
+                make_float2(fmaf(pr[q].x, t.x, -pi[q].x * t.y), fmaf(pr[q].x, t.y, pi[q].x * t.x));
+            tile[((2 * q + 1) * RP + b) * CB + c] =
+                make_float2(fmaf(pr[q].y, t.z, -pi[q].y * t.w), fmaf(pr[q].y, t.w, pi[q].y * t.z));
+        }
+    }
+    __syncthreads();
+    const int ka = b;
+    {
+        auto get = [&](auto j) { return tile[(ka * RP + decltype(j)::value) * CB + c]; };
+        auto tap = [&](auto) { return 1.0f; };
+        fft_packed<R, -1, false>(pr, pi, get, tap);  // (pr[q], pi[q]) = A[ka + R kb], kb = 2q, 2q + 1
+    }
+    float2 b0;
+    {
+        const unsigned e = ((unsigned)n2 * (unsigned)ka) & (unsigned)(p.L - 1);
+        float sn, cs;
+        sincospif(-2.0f * (float)e / (float)p.L, &sn, &cs);
+        b0 = make_float2(cs, sn);
+    }
+    float2* out = p.scratch + ((size_t)f * L1 + ka) * p.L2 + n2;
+#pragma unroll
+    for (int q = 0; q < R / 2; ++q) {
+        const float2 w0 = cmul(b0, rho[(2 * q) * CB + c]), w1 = cmul(b0, rho[(2 * q + 1) * CB + c]);
+        out[(size_t)(R * (2 * q)) * p.L2] = cmul(make_float2(pr[q].x, pi[q].x), w0);
+        out[(size_t)(R * (2 * q + 1)) * p.L2] = cmul(make_float2(pr[q].y, pi[q].y), w1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // B: row FFTs + log power.  grid (L1/CB, SB), block 256.
 // ---------------------------------------------------------------------------------------------
 template <int R>
@@ -219,6 +336,7 @@ struct FftState {
     bool configured = false;
     int L = 0, L1 = 0, L2 = 0, R1 = 0, R2 = 0, avg = 0;
     int sb = 0;               // frames per sub-batch (scratch kept L2 resident)
+    bool cols_tma = true;     // column pass: TMA tile kernel (RCB_FFT_VARIANT=1 selects the register-staged one)
     int in_block = 0;         // frames already folded into the current averaging block
     float* d_window = nullptr;
     float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_tlo = nullptr, *d_thi = nullptr;
@@ -298,6 +416,7 @@ inline int fft_config(FftState& s, int L, const float* window, int avg, cudaStre
     s.L1 = r1 * r1;
     s.L2 = r2 * r2;
     s.avg = avg;
+    if (const char* e = getenv("RCB_FFT_VARIANT")) s.cols_tma = (atoi(e) != 1);
     // sub-batch: keep scratch (8 B) + vals (4 B) per sample under ~48 MB so they stay in L2
     size_t budget_mb = 48;
     if (const char* e = getenv("RCB_FFT_SCRATCH_MB")) budget_mb = (size_t)std::max(1, atoi(e));
@@ -359,6 +478,49 @@ inline int fft_launch_cols(const FftParams& p, int nfr, cudaStream_t st) {
     FCK(cudaGetLastError());
     return 0;
 }
+typedef CUresult (*rcb_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline rcb_tmap_encode_fn fft_tmap_encoder() {
+    static rcb_tmap_encode_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<rcb_tmap_encode_fn>(ptr);
+    }
+    return fn;
+}
+
+// TMA column pass over the nfr frames at p.x; returns 1 when it cannot run (no encoder / misaligned input)
+template <int R>
+inline int fft_launch_cols_tma(const FftParams& p, int nfr, cudaStream_t st) {
+    using G = FftColsGeom<R>;
+    rcb_tmap_encode_fn enc = fft_tmap_encoder();
+    if (!enc || (reinterpret_cast<uintptr_t>(p.x) & 15)) return 1;
+    CUtensorMap tm;
+    const cuuint64_t gdim[2] = {(cuuint64_t)p.L2 * 2, (cuuint64_t)nfr * (cuuint64_t)p.L1};
+    const cuuint64_t gstr[1] = {(cuuint64_t)p.L2 * 8};
+    const cuuint32_t box[2] = {(cuuint32_t)(G::CB * 2), (cuuint32_t)G::BOX_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float2*>(p.x), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return 1;
+    static bool attr = false;
+    if (!attr) {
+        FCK(cudaFuncSetAttribute(fft_cols_tma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem));
+        attr = true;
+    }
+    dim3 grid(p.L2 / G::CB, nfr);
+    fft_cols_tma_kernel<R><<<grid, 256, G::smem, st>>>(tm, p);
+    FCK(cudaGetLastError());
+    return 0;
+}
+
 template <int R>
 inline int fft_launch_rows(const FftParams& p, int nfr, cudaStream_t st) {
     using G = FftGeom<R>;
@@ -434,7 +596,12 @@ inline int fft_process(FftState& s, const float2* iq, size_t nsamples, int in_me
         p.L = s.L;
         p.L1 = s.L1;
         p.L2 = s.L2;
-        int rc = (s.R1 == 8) ? fft_launch_cols<8>(p, nfr, wst) : (s.R1 == 16) ? fft_launch_cols<16>(p, nfr, wst)
+        int rc = 1;
+        if (s.cols_tma)
+            rc = (s.R1 == 8) ? fft_launch_cols_tma<8>(p, nfr, wst) : (s.R1 == 16) ? fft_launch_cols_tma<16>(p, nfr, wst)
+                                                                                : fft_launch_cols_tma<32>(p, nfr, wst);
+        if (rc == 1)  // register-staged predecessor (RCB_FFT_VARIANT=1, or no tensor-map encoder / misaligned input)
+            rc = (s.R1 == 8) ? fft_launch_cols<8>(p, nfr, wst) : (s.R1 == 16) ? fft_launch_cols<16>(p, nfr, wst)
                                                                             : fft_launch_cols<32>(p, nfr, wst);
         if (rc) return rc;
         rc = (s.R2 == 8) ? fft_launch_rows<8>(p, nfr, wst) : (s.R2 == 16) ? fft_launch_rows<16>(p, nfr, wst)
