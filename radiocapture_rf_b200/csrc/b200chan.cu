@@ -1274,7 +1274,7 @@ extern "C" int rcb_fft_process(rcb_t* h, const void* iq, size_t nsamples, int in
     CK(cudaSetDevice(h->device));
     uint64_t launches = 0, h2d = 0, d2h = 0;
     int rc = fft_process(h->fft, (const float2*)iq, nsamples, in_mem, (float*)out_sums, cap_vectors, out_mem, nvec,
-                         h->stream, &launches, &h2d, &d2h);
+                         h->stream, &launches, &h2d, &d2h, h->sm_count);
     h->stats.kernel_launches += launches;
     h->stats.h2d_bytes += h2d;
     h->stats.d2h_bytes += d2h;

@@ -337,6 +337,13 @@ struct FftState {
     int L = 0, L1 = 0, L2 = 0, R1 = 0, R2 = 0, avg = 0;
     int sb = 0;               // frames per sub-batch (scratch kept L2 resident)
     bool cols_tma = true;     // column pass: TMA tile kernel (RCB_FFT_VARIANT=1 selects the register-staged one)
+    bool rows_k1 = false;     // RCB_FFT_VARIANT=3: row pass on the persistent K1 pipeline (pfb_fm_tma_kernel, MODE = PFB_LOGPOW).
+                              // Same 21 us per 4-frame sub-batch as fft_rows_kernel but it fills every SM, which stops the
+                              // other work slot's kernels from overlapping (cfg4 101 vs 116 Gsps): not the default.
+    float2* d_tw_rows = nullptr;  // dense swizzled W_L2^{-ll m1} table for it
+    float2* d_zeros = nullptr;    // one all-zero row
+    int* d_counter[2] = {nullptr, nullptr};
+    int rows_blocks_per_sm = 0;
     int in_block = 0;         // frames already folded into the current averaging block
     float* d_window = nullptr;
     float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_tlo = nullptr, *d_thi = nullptr;
@@ -366,6 +373,10 @@ inline void fft_free(FftState& s) {
     cudaFree(s.d_tw2);
     cudaFree(s.d_tlo);
     cudaFree(s.d_thi);
+    cudaFree(s.d_tw_rows);
+    cudaFree(s.d_zeros);
+    cudaFree(s.d_counter[0]);
+    cudaFree(s.d_counter[1]);
     for (int i = 0; i < 2; ++i) {
         cudaFree(s.d_scratch2[i]);
         cudaFree(s.d_vals2[i]);
@@ -416,7 +427,10 @@ inline int fft_config(FftState& s, int L, const float* window, int avg, cudaStre
     s.L1 = r1 * r1;
     s.L2 = r2 * r2;
     s.avg = avg;
-    if (const char* e = getenv("RCB_FFT_VARIANT")) s.cols_tma = (atoi(e) != 1);
+    if (const char* e = getenv("RCB_FFT_VARIANT")) {
+        s.cols_tma = (atoi(e) != 1);
+        s.rows_k1 = (atoi(e) == 3);
+    }
     // sub-batch: keep scratch (8 B) + vals (4 B) per sample under ~48 MB so they stay in L2
     size_t budget_mb = 48;
     if (const char* e = getenv("RCB_FFT_SCRATCH_MB")) budget_mb = (size_t)std::max(1, atoi(e));
@@ -447,6 +461,24 @@ inline int fft_config(FftState& s, int L, const float* window, int avg, cudaStre
         FCK(cudaMalloc(&s.d_vals2[i], (size_t)s.sb * L * sizeof(float)));
         FCK(cudaStreamCreateWithFlags(&s.ws[i], cudaStreamNonBlocking));
         FCK(cudaEventCreateWithFlags(&s.ev_fold[i], cudaEventDisableTiming));
+    }
+    {   // row pass on the K1 pipeline: dense twiddle table, 16-byte chunks XOR-swizzled like pfb_fm_tma_kernel expects
+        const int R = r2, N = s.L2;
+        std::vector<float2> tt((size_t)N);
+        for (int ll = 0; ll < R; ++ll) {
+            const int sw = (R == 8) ? ((ll >> 1) & 3) : (ll & (R / 2 - 1));
+            for (int m1 = 0; m1 < R; ++m1) {
+                const double a = -2.0 * M_PI * (double)((ll * m1) % N) / (double)N;
+                tt[(size_t)ll * R + ((((m1 >> 1) ^ sw) << 1) | (m1 & 1))] = make_float2((float)cos(a), (float)sin(a));
+            }
+        }
+        FCK(cudaMalloc(&s.d_tw_rows, tt.size() * sizeof(float2)));
+        FCK(cudaMemcpyAsync(s.d_tw_rows, tt.data(), tt.size() * sizeof(float2), cudaMemcpyHostToDevice, st));
+        FCK(cudaMalloc(&s.d_zeros, (size_t)N * sizeof(float2)));
+        FCK(cudaMemsetAsync(s.d_zeros, 0, (size_t)N * sizeof(float2), st));
+        FCK(cudaMalloc(&s.d_counter[0], sizeof(int)));
+        FCK(cudaMalloc(&s.d_counter[1], sizeof(int)));
+        FCK(cudaStreamSynchronize(st));
     }
     FCK(cudaEventCreateWithFlags(&s.ev_start, cudaEventDisableTiming));
     FCK(cudaMalloc(&s.d_acc, (size_t)L * sizeof(float)));
@@ -521,6 +553,38 @@ inline int fft_launch_cols_tma(const FftParams& p, int nfr, cudaStream_t st) {
     return 0;
 }
 
+// row pass on the K1 pipeline: rows of the scratch are the "frames", bins k2 the "channels"
+template <int R>
+inline int fft_launch_rows_k1(FftState& s, const FftParams& fp, int nfr, int slot, cudaStream_t st, int sm_count) {
+    using G = PfbTmaGeom<R, 8, PFB_LOGPOW>;
+    auto kern = pfb_fm_tma_kernel<R, 8, true, 1, PFB_LOGPOW>;
+    if (!s.rows_blocks_per_sm) {
+        FCK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes));
+        int nb = 0;
+        FCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, G::THREADS, G::smem_bytes));
+        s.rows_blocks_per_sm = nb > 0 ? nb : 1;
+    }
+    PfbParams p{};
+    p.x = fp.scratch;
+    p.hist = s.d_zeros;
+    p.zeros = s.d_zeros;
+    p.taps = nullptr;
+    p.twiddle = s.d_tw_rows;
+    p.work_counter = s.d_counter[slot];
+    p.out_fm = fp.vals;
+    p.ostride = fp.L1;
+    p.T = nfr * fp.L1;
+    p.P = 0;
+    p.N = fp.L2;
+    p.gain = 1.0f;
+    const int NI = (p.T + G::FPI - 1) / G::FPI;
+    const int grid = std::max(1, std::min(NI, s.rows_blocks_per_sm * sm_count));
+    FCK(cudaMemsetAsync(s.d_counter[slot], 0, sizeof(int), st));
+    kern<<<grid, G::THREADS, G::smem_bytes, st>>>(p);
+    FCK(cudaGetLastError());
+    return 0;
+}
+
 template <int R>
 inline int fft_launch_rows(const FftParams& p, int nfr, cudaStream_t st) {
     using G = FftGeom<R>;
@@ -537,7 +601,8 @@ inline int fft_launch_rows(const FftParams& p, int nfr, cudaStream_t st) {
 }
 
 inline int fft_process(FftState& s, const float2* iq, size_t nsamples, int in_mem, float* out, size_t cap_vec,
-                       int out_mem, size_t* nvec, cudaStream_t st, uint64_t* launches, uint64_t* h2d, uint64_t* d2h) {
+                       int out_mem, size_t* nvec, cudaStream_t st, uint64_t* launches, uint64_t* h2d, uint64_t* d2h,
+                       int sm_count = kNumSMsB200) {
     *nvec = 0;
     const size_t L = (size_t)s.L;
     size_t nframes = nsamples / L;
@@ -604,8 +669,13 @@ inline int fft_process(FftState& s, const float2* iq, size_t nsamples, int in_me
             rc = (s.R1 == 8) ? fft_launch_cols<8>(p, nfr, wst) : (s.R1 == 16) ? fft_launch_cols<16>(p, nfr, wst)
                                                                             : fft_launch_cols<32>(p, nfr, wst);
         if (rc) return rc;
-        rc = (s.R2 == 8) ? fft_launch_rows<8>(p, nfr, wst) : (s.R2 == 16) ? fft_launch_rows<16>(p, nfr, wst)
-                                                                        : fft_launch_rows<32>(p, nfr, wst);
+        if (s.rows_k1)
+            rc = (s.R2 == 8) ? fft_launch_rows_k1<8>(s, p, nfr, sl, wst, sm_count)
+                             : (s.R2 == 16) ? fft_launch_rows_k1<16>(s, p, nfr, sl, wst, sm_count)
+                                            : fft_launch_rows_k1<32>(s, p, nfr, sl, wst, sm_count);
+        else
+            rc = (s.R2 == 8) ? fft_launch_rows<8>(p, nfr, wst) : (s.R2 == 16) ? fft_launch_rows<16>(p, nfr, wst)
+                                                                            : fft_launch_rows<32>(p, nfr, wst);
         if (rc) return rc;
         const bool complete = (s.in_block + nfr == s.avg);
         float* emit = complete ? d_out + emitted * L : nullptr;

@@ -32,7 +32,7 @@
 
 namespace rcb {
 
-enum { PFB_OUT_IQ = 1, PFB_OUT_FM = 2 };
+enum { PFB_OUT_IQ = 1, PFB_OUT_FM = 2, PFB_LOGPOW = 4 /* K3 row pass on the K1 pipeline (pfb_fm_tma.cuh) */ };
 
 struct PfbParams {
     const float2* x;        // T*N new samples (row n = frame n)

@@ -20,6 +20,9 @@
 
 namespace rcb {
 
+// the ring holds one float per (frame, bin) - angle(Y) or log power - unless IQ is an output
+__host__ __device__ constexpr bool pfb_ring_f32(int mode) { return mode == PFB_OUT_FM || mode == PFB_LOGPOW; }
+
 template <int R, int W = 8, int MODE = PFB_OUT_FM>
 struct PfbTmaGeom {
     static constexpr int N = R * R;
@@ -32,7 +35,7 @@ struct PfbTmaGeom {
     static constexpr int WORK = F * FSW;                    // complex per warp
     static constexpr size_t work_bytes = (size_t)WARPS * WORK * 8;
     // ring element: angle(Y) (4 B) when only FM is produced, Y itself (8 B) when IQ is an output
-    static constexpr size_t ring_bytes = (size_t)NSLOT * N * (MODE == PFB_OUT_FM ? 4 : 8);
+    static constexpr size_t ring_bytes = (size_t)NSLOT * N * (pfb_ring_f32(MODE) ? 4 : 8);
     static constexpr size_t tw_bytes = (size_t)N * 8;
     static constexpr size_t taps_bytes = (size_t)N * 4;
     static constexpr size_t smem_bytes = work_bytes + ring_bytes + tw_bytes + taps_bytes + 256;
@@ -86,6 +89,12 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
     static_assert(!OB8 || (R == 32 && W == 8 && MODE == PFB_OUT_FM), "OB8 is an FM-only 1024-channel layout variant");
     using G = PfbTmaGeom<R, W, MODE>;
     static_assert(PK || MODE == PFB_OUT_FM, "IQ outputs are implemented on the packed path only");
+    // MODE = PFB_LOGPOW: the K3 row pass (fft_vector.py: fft_vcc + mag^2 + nlog10_ff) on the same pipeline - forward
+    // transform of contiguous rows in natural order, no taps, log10(|X|^2) + 1 into the ring, the "demod" phase
+    // copies 8 consecutive rows of a bin as one sector into vals[f][fftshift(k2) * L1 + k1] (ostride = L1).
+    static_assert(MODE != PFB_LOGPOW || (PK && PT == 1 && !OB8), "log-power mode: packed, no taps");
+    constexpr int SG = (MODE == PFB_LOGPOW) ? -1 : +1;
+    constexpr bool REVI = (MODE != PFB_LOGPOW);  // PFB arms are commutated in reverse order
     constexpr int THREADS = G::THREADS;
     constexpr int N = G::N, F = G::F, FPI = G::FPI, NSLOT = G::NSLOT, FSW = G::FSW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -104,7 +113,7 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
 
     for (int i = tid; i < N; i += THREADS) {
         tws[i] = p.twiddle[i];
-        if constexpr (PT == 1) taps_s[i] = p.taps[i];
+        if constexpr (PT == 1 && MODE != PFB_LOGPOW) taps_s[i] = p.taps[i];
     }
     if (tid < W) mbar_init(bars + tid, 1);
     if (tid == W) mbar_init(cta_bar, THREADS);
@@ -118,7 +127,9 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
     // ---- by up to +-10 % in sustained speed with TMA staging (profiles/r01_pfb_fm_v3_*): a purely static split
     // ---- leaves the fast SMs idle for 11 % of the launch.  Every range starts with one warm-up iteration
     // ---- that recomputes the frame before it (no Y / phase state is carried between ranges or launches).
-    constexpr int kTailChunk = 4;
+    // log-power rows are independent: no warm-up iteration, single-iteration dynamic chunks
+    constexpr int WARM = (MODE == PFB_LOGPOW) ? 0 : 1;
+    constexpr int kTailChunk = (MODE == PFB_LOGPOW) ? 2 : 4;
     const int NI = (p.T + FPI - 1) / FPI;
     const int stat = (int)(((long long)(NI / (int)gridDim.x) * 7) / 8);
     const int tail0 = stat * (int)gridDim.x;
@@ -137,7 +148,7 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
     }
     int nxt0 = NI, nxt1 = NI;  // following range (nxt0 >= NI: none)
 
-    long long frame0 = (long long)(cur0 - 1) * FPI + warp * F;  // first of this warp's F frames
+    long long frame0 = (long long)(cur0 - WARM) * FPI + warp * F;  // first of this warp's F frames
     auto issue_rows = [&](long long f0) {
         if (PT == 1 && lane == 0) {
             fence_proxy_async();
@@ -153,8 +164,8 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
     uint32_t row_par = 0, cta_par = 0;
     bool first_ever = true;
 #pragma unroll 1
-    for (int it = cur0 - 1;; ++it) {
-        const bool range_first = (it == cur0 - 1);
+    for (int it = cur0 - WARM;; ++it) {
+        const bool range_first = (it == cur0 - WARM);
         if (range_first && tid == 0) {  // reserve the range that follows the current one
             const int c = atomicAdd(p.work_counter, 1);
             s_next = tail0 + c * kTailChunk;
@@ -212,7 +223,7 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
             __syncthreads();
         }
         float ph[R];
-        float yre[MODE == PFB_OUT_FM ? 1 : R], yim[MODE == PFB_OUT_FM ? 1 : R];
+        float yre[pfb_ring_f32(MODE) ? 1 : R], yim[pfb_ring_f32(MODE) ? 1 : R];
         const bool range_last = (it + 1 == cur1);
         // issue the TMA copy of the frames this warp transforms next (its buffer has been fully consumed)
         auto issue_next = [&]() {
@@ -220,7 +231,7 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
                 frame0 += FPI;
                 issue_rows(frame0);
             } else if (nxt0 < NI) {  // seamless hand-over: prefetch the warm-up frames of the next range
-                frame0 = (long long)(nxt0 - 1) * FPI + warp * F;
+                frame0 = (long long)(nxt0 - WARM) * FPI + warp * F;
                 issue_rows(frame0);
             }
         };
@@ -230,14 +241,14 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
             {
                 float hreg[R];
 #pragma unroll
-                for (int jq = 0; PT == 1 && jq < R / 4; ++jq) {
+                for (int jq = 0; PT == 1 && MODE != PFB_LOGPOW && jq < R / 4; ++jq) {
                     const float4 h = tap4[jq * R + ll];
                     hreg[4 * jq + 0] = h.x; hreg[4 * jq + 1] = h.y; hreg[4 * jq + 2] = h.z; hreg[4 * jq + 3] = h.w;
                 }
                 // DFT input j is sample row jj = R-1-j of this lane's column
-                auto get = [&](auto j) { return wf[(R - 1 - decltype(j)::value) * R + ll]; };
+                auto get = [&](auto j) { return wf[(REVI ? R - 1 - decltype(j)::value : decltype(j)::value) * R + ll]; };
                 auto tap = [&](auto j) { return hreg[R - 1 - decltype(j)::value]; };
-                fft_packed<R, +1, PT == 1>(pr, pi, get, tap);
+                fft_packed<R, SG, PT == 1 && MODE != PFB_LOGPOW>(pr, pi, get, tap);
             }
             __syncwarp();  // every lane has read its samples: the buffer becomes the transpose scratch
             {
@@ -257,12 +268,12 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
                 const int ch = ll >> 1, wi = ll & 1;
                 float2 u[R];
 #pragma unroll
-                for (int l2 = 0; l2 < R; ++l2) u[R - 1 - l2] = wf[l2 * R + (((ch ^ pfb_swz<R>(l2)) << 1) | wi)];
+                for (int l2 = 0; l2 < R; ++l2) u[REVI ? R - 1 - l2 : l2] = wf[l2 * R + (((ch ^ pfb_swz<R>(l2)) << 1) | wi)];
                 __syncwarp();  // scratch fully consumed: start the copy of the next frames right away
                 issue_next();
                 auto get = [&](auto j) { return u[decltype(j)::value]; };
                 auto tap = [&](auto) { return 1.0f; };
-                fft_packed<R, +1, false>(pr, pi, get, tap);  // (pr[q], pi[q]) = Y[ll + R*(2q)], Y[ll + R*(2q+1)]
+                fft_packed<R, SG, false>(pr, pi, get, tap);  // (pr[q], pi[q]) = Y[ll + R*(2q)], Y[ll + R*(2q+1)]
             }
             if constexpr (MODE == PFB_OUT_FM) {
 #pragma unroll
@@ -270,6 +281,13 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
                     const float2 a = atan2_nan_p2(pi[q], pr[q]);
                     ph[2 * q] = a.x;
                     ph[2 * q + 1] = a.y;
+                }
+            } else if constexpr (MODE == PFB_LOGPOW) {
+#pragma unroll
+                for (int q = 0; q < R / 2; ++q) {  // nlog10_ff(1, L, 1): log10(max(|X|^2, 1e-18)) + 1
+                    const float2 pw2 = p2fma(pr[q], pr[q], p2mul(pi[q], pi[q]));
+                    ph[2 * q] = fmaf(log2f(fmaxf(pw2.x, 1e-18f)), 0.30102999566398120f, 1.0f);
+                    ph[2 * q + 1] = fmaf(log2f(fmaxf(pw2.y, 1e-18f)), 0.30102999566398120f, 1.0f);
                 }
             } else {  // keep Y: written to the ring below (needs pr/pi in scope -> stash in yre/yim)
 #pragma unroll
@@ -327,7 +345,7 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
             cta_par ^= 1u;
         }
         first_ever = false;
-        if constexpr (MODE == PFB_OUT_FM) {
+        if constexpr (pfb_ring_f32(MODE)) {
             float* fb = ring + slot * N;
 #pragma unroll
             for (int m2 = 0; m2 < R; ++m2) fb[m2 * R + ll] = ph[m2];
@@ -340,6 +358,10 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
         if (range_first) {
             nxt0 = s_next;
             nxt1 = min(nxt0 + kTailChunk, NI);
+            if (range_last && nxt0 < NI) {  // single-iteration range: the follow-up range was not known in time
+                frame0 = (long long)(nxt0 - WARM) * FPI + warp * F;
+                issue_rows(frame0);
+            }
         }
 
         // ---- demod: 8 consecutive frames of CPT channels per thread ----
@@ -360,8 +382,12 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
             const bool full = (t0 + 8 <= p.T) && !(p.debug_flags & 1);  // RCB_PFB_DEBUG=1: measurement only
             // (m0, t0) -> element index; consecutive channels are `rowstride` apart in both layouts
             float* dst0 = (MODE & PFB_OUT_FM) ? p.out_fm + pfb_out_index(p, m0, t0) : nullptr;
+            if constexpr (MODE == PFB_LOGPOW) {  // t = f * L1 + k1 (ostride = L1), bin m = k2 -> vals[f][fftshift(k2)][k1]
+                const long long fidx = t0 / p.ostride;
+                dst0 = p.out_fm + fidx * (long long)N * p.ostride + (long long)((m0 + N / 2) % N) * p.ostride + (t0 - fidx * p.ostride);
+            }
             const long long rowstride = (p.oblock_log2 > 0) ? (1LL << p.oblock_log2) : p.ostride;
-            if constexpr (MODE == PFB_OUT_FM) {
+            if constexpr (pfb_ring_f32(MODE)) {
             float pw[9][CPT];  // all ring loads first (9 vector LDS), then CPT*8 independent wrap chains
 #pragma unroll
             for (int j = 0; j < 9; ++j) {
@@ -381,7 +407,12 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
                 s = (s + 1 == NSLOT) ? 0 : s + 1;
             }
             float o[CPT][8];
-            if constexpr (PK && CPT >= 2) {  // packed over channel pairs; the NaN select unpacks for free
+            if constexpr (MODE == PFB_LOGPOW) {
+#pragma unroll
+                for (int q = 0; q < CPT; ++q)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[q][j] = pw[j + 1][q];
+            } else if constexpr (PK && CPT >= 2) {  // packed over channel pairs; the NaN select unpacks for free
 #pragma unroll
                 for (int q = 0; q < CPT; q += 2) {
 #pragma unroll
@@ -497,7 +528,7 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
             if (nxt0 >= NI) break;
             cur0 = nxt0;
             cur1 = nxt1;
-            it = cur0 - 2;  // ++it -> warm-up iteration of the new range
+            it = cur0 - 1 - WARM;  // ++it -> warm-up iteration of the new range
         }
     }
 }

@@ -9,8 +9,8 @@ for ln in sys.stdin:
     print('value %.1f Gsps  frac %.4f  ms/step %.4f e2e %.0f' % (d['value']/1e3, d['roofline']['frac'], d['ms_per_step'], d['e2e']['value']))
 "; }
 echo "== cfg4 TMA cols"; run --workload cfg4
-echo "== cfg4 old cols"; RCB_FFT_VARIANT=1 run --workload cfg4
+echo "== cfg4 TMA cols, old rows"; RCB_FFT_VARIANT=2 run --workload cfg4; echo "== cfg4 old cols"; RCB_FFT_VARIANT=1 run --workload cfg4
 echo "== cfg4_16k TMA cols"; run --workload cfg4_16k
 echo "== cfg4_16k old cols"; RCB_FFT_VARIANT=1 run --workload cfg4_16k
-ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 12 --csv --log-file gpurun_out/launches_cfg4_v2.csv python bench.py --workload cfg4 --steps 2 --warmup 3 --no-cpu --no-also --e2e-steps 1 > gpurun_out/ncu_l4.log 2>&1
-grep -E "fft_|fold" gpurun_out/launches_cfg4_v2.csv | awk -F, '{print $5, $NF}' | head -12
+ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 12 --csv --log-file gpurun_out/launches_cfg4_v3.csv python bench.py --workload cfg4 --steps 2 --warmup 3 --no-cpu --no-also --e2e-steps 1 > gpurun_out/ncu_l4.log 2>&1
+grep -E "fft_|fold" gpurun_out/launches_cfg4_v3.csv | awk -F, '{print $5, $NF}' | head -12
