@@ -514,7 +514,7 @@ def run_b200(args):
     tr = load_traffic(wl)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (tr * n_launch_samples) if tr else None, "peak_source": peak_src,
-                "kernel": "fft_cols_kernel+fft_rows_kernel" if is_fft else ("ddc_bank_kernel" if is_ddc else "pfb_fm_tma_kernel"),
+                "kernel": "fft_cols_tma_kernel+fft_rows_kernel" if is_fft else ("ddc_tile_kernel" if is_ddc else "pfb_fm_tma_kernel"),
                 "algorithmic_bytes_per_launch": n_launch_samples * bps,
                 "kernel_ms_per_launch": kern_ms}
     for c in ctxs:

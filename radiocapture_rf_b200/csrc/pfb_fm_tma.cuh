@@ -39,7 +39,14 @@ struct PfbTmaGeom {
     static constexpr size_t tw_bytes = (size_t)N * 8;
     static constexpr size_t taps_bytes = (size_t)N * 4;
     static constexpr size_t smem_bytes = work_bytes + ring_bytes + tw_bytes + taps_bytes + 256;
-    static constexpr int MIN_CTAS = (2 * smem_bytes <= 227 * 1024 && W <= 8) ? 2 : 1;
+    // resident CTAs per SM the register allocation is tuned for (small transforms leave room for more warps)
+    static constexpr int MIN_CTAS_BASE = (2 * smem_bytes <= 227 * 1024 && W <= 8) ? 2 : 1;
+#ifdef RCB_OCC_EXPERIMENT
+    static constexpr int MIN_CTAS = (W == 8 && R == 8 && 4 * smem_bytes <= 227 * 1024) ? 4
+                                    : (W == 8 && R == 16 && 3 * smem_bytes <= 227 * 1024) ? 3 : MIN_CTAS_BASE;
+#else
+    static constexpr int MIN_CTAS = MIN_CTAS_BASE;
+#endif
 };
 
 template <int R>
