@@ -37,6 +37,8 @@ WORKLOADS = {
                  desc="cfg3: 1024-channel PFB, 256-tap prototype, fused FM demod, one 200 Msps stream"),
     "cfg3_p16": dict(nchans=1024, ntaps=16384, out="fm", log2n=28, streams=1,
                      desc="cfg3 variant: 1024-channel PFB, 16 taps/arm (16384-tap prototype), fused FM demod"),
+    "cfg3_p8": dict(nchans=1024, ntaps=8192, out="fm", log2n=28, streams=1,
+                    desc="cfg3 variant: 1024-channel PFB, 8 taps/arm (8192-tap prototype), fused FM demod"),
     "cfg3_iqfm_p16": dict(nchans=1024, ntaps=16384, out="iq+fm", log2n=27, streams=1,
                           desc="1024-channel PFB, 16 taps/arm, IQ + fused FM out (what pfb-mode channel requests consume)"),
     "cfg2_p16_iqfm": dict(nchans=64, ntaps=1024, out="iq+fm", log2n=27, streams=1,

@@ -19,6 +19,7 @@
 #include "fft_logpow.cuh"
 #include "pfb_fm.cuh"
 #include "pfb_fm_tma.cuh"
+#include "pfb_fm_ws.cuh"
 
 using namespace rcb;
 
@@ -239,6 +240,28 @@ int pfb_launch_tma(rcb_t* h, const PfbParams& p, bool query_only) {
     return RCB_OK;
 }
 
+// warp-specialised producer / consumer kernel (FM only, 2..16 taps per arm)
+template <int R, int PT>
+int pfb_launch_ws(rcb_t* h, const PfbParams& p, bool query_only) {
+    using G = PfbWsGeom<R>;
+    auto kern = pfb_fm_ws_kernel<R, PT>;
+    const size_t smem = G::smem_bytes(PT);
+    if (query_only) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->pfb.blocks_per_sm = 1;
+        h->pfb.smem = smem;
+        return RCB_OK;
+    }
+    const int NI = (p.T + G::FPI - 1) / G::FPI;
+    const int grid = std::max(1, std::min(NI, h->sm_count));
+    PfbParams q = p;
+    q.twiddle = h->pfb.d_tw_tma;
+    q.taps_kc = h->pfb.d_taps_kc;
+    kern<<<grid, G::THREADS, smem, h->stream>>>(q);
+    CKL(h);
+    return RCB_OK;
+}
+
 // fast kernel dispatch: taps per arm (1, 2, 4, 8, 16) x output mode
 template <int R, int MODE>
 int pfb_launch_tma_pm(rcb_t* h, const PfbParams& p, bool q) {
@@ -261,8 +284,14 @@ int pfb_launch_tma_r(rcb_t* h, const PfbParams& p, bool q) {
             if (h->pfb.PT == 1 && v == 16) return pfb_launch_tma<32, 16, true, 1>(h, p, q);
             if (h->pfb.PT == 1 && !q && p.oblock_log2 == 3 && p.out_fm) return pfb_launch_tma<32, 8, true, 1, PFB_OUT_FM, true>(h, p, q);
             if (h->pfb.PT == 1 && v == 3) return pfb_launch_tma<32, 8, false, 1>(h, p, q);  // scalar-arithmetic v5 kernel
-            if (h->pfb.PT == 16 && v != 8) return pfb_launch_tma<32, 16, true, 16>(h, p, q);
-            if (h->pfb.PT == 8 && v != 8) return pfb_launch_tma<32, 16, true, 8>(h, p, q);
+            if (h->pfb.PT == 16 && v == 16) return pfb_launch_tma<32, 16, true, 16>(h, p, q);
+            if (h->pfb.PT == 8 && v == 16) return pfb_launch_tma<32, 16, true, 8>(h, p, q);
+        }
+        // 8+ taps per arm: warp-specialised producer / consumer kernel (RCB_PFB_VARIANT=8 / 16: the phase-serial
+        // 2 x 8-warp / 16-warp variants)
+        if (R == 32 && v != 8 && v != 16) {
+            if (h->pfb.PT == 16) return pfb_launch_ws<R, 16>(h, p, q);
+            if (h->pfb.PT == 8) return pfb_launch_ws<R, 8>(h, p, q);
         }
         return pfb_launch_tma_pm<R, PFB_OUT_FM>(h, p, q);
     }
