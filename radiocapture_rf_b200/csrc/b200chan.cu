@@ -241,10 +241,10 @@ int pfb_launch_tma(rcb_t* h, const PfbParams& p, bool query_only) {
 }
 
 // warp-specialised producer / consumer kernel (FM only, 2..16 taps per arm)
-template <int R, int PT>
+template <int R, int PT, int PW = 8>
 int pfb_launch_ws(rcb_t* h, const PfbParams& p, bool query_only) {
-    using G = PfbWsGeom<R>;
-    auto kern = pfb_fm_ws_kernel<R, PT>;
+    using G = PfbWsGeom<R, PW>;
+    auto kern = pfb_fm_ws_kernel<R, PT, PW>;
     const size_t smem = G::smem_bytes(PT);
     if (query_only) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -290,8 +290,8 @@ int pfb_launch_tma_r(rcb_t* h, const PfbParams& p, bool q) {
         // 8+ taps per arm: warp-specialised producer / consumer kernel (RCB_PFB_VARIANT=8 / 16: the phase-serial
         // 2 x 8-warp / 16-warp variants)
         if (R == 32 && v != 8 && v != 16) {
-            if (h->pfb.PT == 16) return pfb_launch_ws<R, 16>(h, p, q);
-            if (h->pfb.PT == 8) return pfb_launch_ws<R, 8>(h, p, q);
+            if (h->pfb.PT == 16) return (v == 12) ? pfb_launch_ws<R, 16, 12>(h, p, q) : pfb_launch_ws<R, 16>(h, p, q);
+            if (h->pfb.PT == 8) return (v == 12) ? pfb_launch_ws<R, 8, 12>(h, p, q) : pfb_launch_ws<R, 8>(h, p, q);
         }
         return pfb_launch_tma_pm<R, PFB_OUT_FM>(h, p, q);
     }

@@ -5,13 +5,15 @@
 // with every warp in the same phase: the FIR phase waits on its global loads with nothing else to issue
 // (profiles/r01_pfb_fm_p16_v2_w16_summary.txt: issue slots 35 % busy, long_sb + lg = 28 % of the stall samples).
 // Here one 16-warp CTA per SM is split into
-//   * 8 PRODUCER warps: the time-blocked arm FIR of iteration k+1 (one column x 8 frames per task, PT packed
-//     FFMA2 per output, written to one of two sets of frame buffers) and the demod + sector stores of iteration k;
+//   * 8 PRODUCER warps: nothing but the time-blocked arm FIR, one buffer set ahead (one column x 8 frames per task,
+//     PT packed FFMA2 per output, written to one of two sets of frame buffers);
 //   * 8 CONSUMER warps: one frame each per iteration - both packed radix-R passes (in-place swizzled transpose in
-//     the frame buffer), packed atan2, angle ring;
-// handing frame buffers and the angle ring back and forth through four mbarriers (full / empty per buffer set,
-// ring full / ring free), one elected lane per warp arriving after __syncwarp().  The producers' load latency now
-// overlaps the consumers' arithmetic instead of stalling the whole SM.
+//     the frame buffer), packed atan2, angle ring - then, after a named barrier of the consumer warps only, the
+//     demod + sector stores of that iteration (with the demod on the producer side the producers were the critical
+//     path and the consumers spun 35 % of the time);
+// handing the frame buffers back and forth through full / empty mbarriers per buffer set (one elected lane per warp
+// arriving after __syncwarp()).  The producers' load latency now overlaps the consumers' arithmetic instead of
+// stalling the whole SM.
 // Arithmetic, ring layout, output layout and the warm-up-iteration scheme (no state carried between CTAs or
 // launches) are those of pfb_fm_tma_kernel; shared memory: 2 x 8 x 8 KB frame buffers + 36 KB ring + 8 KB twiddles.
 #pragma once
@@ -19,12 +21,12 @@
 
 namespace rcb {
 
-template <int R>
+template <int R, int PW = 8>
 struct PfbWsGeom {
     static constexpr int N = R * R;
     static constexpr int F = 32 / R;
-    static constexpr int CW = 8;  // consumer warps (= producer warps)
-    static constexpr int THREADS = 2 * CW * 32;
+    static constexpr int CW = 8;  // consumer warps; PW producer warps (8, or 12 with setmaxnreg register rebalancing)
+    static constexpr int THREADS = (CW + PW) * 32;
     static constexpr int FPI = CW * F;
     static constexpr int NSLOT = FPI + 1;
     static constexpr int FSW = N + (R == 8 ? 8 : 0);
@@ -35,9 +37,9 @@ struct PfbWsGeom {
     static constexpr size_t smem_bytes(int /*PT*/) { return 2 * set_bytes + ring_bytes + tw_bytes + 128; }
 };
 
-template <int R, int PT>
-__global__ void __launch_bounds__(512, 1) pfb_fm_ws_kernel(const PfbParams p) {
-    using G = PfbWsGeom<R>;
+template <int R, int PT, int PW = 8>
+__global__ void __launch_bounds__((8 + PW) * 32, 1) pfb_fm_ws_kernel(const PfbParams p) {
+    using G = PfbWsGeom<R, PW>;
     constexpr int N = G::N, F = G::F, FPI = G::FPI, NSLOT = G::NSLOT, FSW = G::FSW, CW = G::CW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float2* work_all = reinterpret_cast<float2*>(smem_raw);  // [2 sets][CW][WORK]
@@ -46,8 +48,7 @@ __global__ void __launch_bounds__(512, 1) pfb_fm_ws_kernel(const PfbParams p) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * G::set_bytes + G::ring_bytes + G::tw_bytes);
     uint64_t* u_full = bars;       // [2] producers -> consumers: frame buffers of set s hold filtered frames
     uint64_t* u_empty = bars + 2;  // [2] consumers -> producers: set s has been transformed
-    uint64_t* ring_full = bars + 4;  // consumers -> producers: this iteration's angles are in the ring
-    uint64_t* ring_free = bars + 5;  // producers -> consumers: the demod has read the ring
+    uint64_t* ring_free = bars + 4;  // consumer threads: arrive after the demod reads / wait before the next ring write
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // contiguous run of iterations per CTA (+ one warm-up iteration that recomputes the frame before the run)
@@ -59,35 +60,34 @@ __global__ void __launch_bounds__(512, 1) pfb_fm_ws_kernel(const PfbParams p) {
 
     for (int i = tid; i < N; i += G::THREADS) tws[i] = p.twiddle[i];
     if (tid == 0) {
-        mbar_init(u_full + 0, CW);
-        mbar_init(u_full + 1, CW);
+        mbar_init(u_full + 0, PW);
+        mbar_init(u_full + 1, PW);
         mbar_init(u_empty + 0, CW);
         mbar_init(u_empty + 1, CW);
-        mbar_init(ring_full, CW);
-        mbar_init(ring_free, CW);
+        mbar_init(ring_free, CW * 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     if (warp >= CW) {
-        // =========================== producers: arm FIR (k+1) and demod (k) ===========================
-        const int ptid = tid - CW * 32, pwarp = warp - CW;
-        constexpr int PTHREADS = CW * 32;
+        // =========================== producers: arm FIR, one buffer set ahead ===========================
+        // 12 producer warps: 640 threads start with 96 registers each; the producers give registers back so that the
+        // consumer warpgroups can grow to 120 (640 x 96 = 384 x 80 + 256 x 120: the pool is what the CTA was launched with)
+        if constexpr (PW > 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        const int ptid = tid - CW * 32;
+        constexpr int PTHREADS = PW * 32;
         constexpr int TBK = 8, NX = TBK + PT - 1;
-        constexpr int TASKS = N * (FPI / TBK) / PTHREADS;
-        const uint64_t pol_stream = l2_policy_evict_first();
+        constexpr int NTASK = N * (FPI / TBK);
         // (Staging the task windows one task ahead with cp.async was measured slower: 184 vs 200 Gsps on cfg3_p16 -
         // 8-byte LDGSTS cost an LSU wavefront each and 7x the shared-memory bank conflicts.)
-        int base_slot = 0;
         int k = 0;
-        for (int it = it0 - 1;; ++it, ++k) {
-            if (it < it1) {
+        for (int it = it0 - 1; it < it1; ++it, ++k) {
+            {
                 const int s = k & 1;
                 if (k >= 2) mbar_wait(u_empty + s, (uint32_t)(((k >> 1) - 1) & 1));
                 float2* wset = work_all + (size_t)s * CW * G::WORK;
 #pragma unroll 1
-                for (int q = 0; q < TASKS; ++q) {
-                    const int task = q * PTHREADS + ptid;
+                for (int task = ptid; task < NTASK; task += PTHREADS) {
                     const int c = task % N, g = task / N;
                     const long long f0 = (long long)it * FPI + TBK * g;
                     const long long r0 = f0 - (PT - 1);
@@ -115,88 +115,27 @@ __global__ void __launch_bounds__(512, 1) pfb_fm_ws_kernel(const PfbParams p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(u_full + s);
             }
-            if (k >= 1) {
-                // ---- demod of iteration it-1: CPT channels x 8 consecutive frames per thread ----
-                const int dit = it - 1;
-                mbar_wait(ring_full, (uint32_t)((k - 1) & 1));
-                if (dit >= it0) {
-                    constexpr int CPT = N * (FPI / 8) / PTHREADS;  // 4, 2, 1 for R = 32, 16, 8
-                    constexpr int GRP = FPI / 8;
-                    constexpr bool kPairLanes = (GRP == 2 && CPT >= 2);
-                    const int g = kPairLanes ? (lane >> 4) : ptid / (N / CPT);
-                    const int m0 = kPairLanes ? (pwarp * 16 + (lane & 15)) * CPT : (ptid % (N / CPT)) * CPT;
-                    const long long t0 = (long long)dit * FPI + 8 * g;
-                    int sl = base_slot + 8 * g;
-                    sl = (sl >= NSLOT) ? sl - NSLOT : sl;
-                    const bool full = (t0 + 8 <= p.T);
-                    float* dst0 = p.out_fm + pfb_out_index(p, m0, t0);
-                    const long long rowstride = (p.oblock_log2 > 0) ? (1LL << p.oblock_log2) : p.ostride;
-                    float pw[9][CPT];
-#pragma unroll
-                    for (int j = 0; j < 9; ++j) {
-                        const float* src = ring + sl * N + m0;
-                        if constexpr (CPT == 4) {
-                            const float4 t = *reinterpret_cast<const float4*>(src);
-                            pw[j][0] = t.x; pw[j][1] = t.y; pw[j][2] = t.z; pw[j][3] = t.w;
-                        } else if constexpr (CPT == 2) {
-                            const float2 t = *reinterpret_cast<const float2*>(src);
-                            pw[j][0] = t.x; pw[j][1] = t.y;
-                        } else {
-                            pw[j][0] = *src;
-                        }
-                        sl = (sl + 1 == NSLOT) ? 0 : sl + 1;
-                    }
-                    float o[CPT][8];
-                    if constexpr (CPT >= 2) {
-#pragma unroll
-                        for (int q = 0; q < CPT; q += 2) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                float2 d = p2sub(make_float2(pw[j + 1][q], pw[j + 1][q + 1]), make_float2(pw[j][q], pw[j][q + 1]));
-                                const float2 kk = p2add(p2fmas(d, 0.15915494309189535f, make_float2(12582912.0f, 12582912.0f)),
-                                                        make_float2(-12582912.0f, -12582912.0f));
-                                d = p2fmas(kk, -6.283185307179586f, d);
-                                d = p2muls(d, p.gain);
-                                o[q][j] = (d.x != d.x) ? 0.0f : d.x;
-                                o[q + 1][j] = (d.y != d.y) ? 0.0f : d.y;
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float d = pw[j + 1][0] - pw[j][0];
-                            const float kk = (d * 0.15915494309189535f + 12582912.0f) - 12582912.0f;
-                            d = fmaf(kk, -6.283185307179586f, d);
-                            d *= p.gain;
-                            o[0][j] = (d != d) ? 0.0f : d;
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < CPT; ++q) {
-                        float* dst = dst0 + q * rowstride;
-                        if (full) {
-                            st_global_v8_hint(dst, o[q], pol_stream);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                if (t0 + j < p.T) dst[j] = o[q][j];
-                        }
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(ring_free);
-                base_slot = (base_slot == 0) ? NSLOT - 1 : base_slot - 1;
-            }
-            if (it >= it1) break;  // the demod of the last iteration has run
         }
     } else {
         // =========================== consumers: one frame set per warp and iteration ===========================
+        if constexpr (PW > 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
         const int fr = lane / R, ll = lane % R;
+        const uint64_t pol_stream = l2_policy_evict_first();
         int base_slot = 0;
         int k = 0;
         for (int it = it0 - 1; it < it1; ++it, ++k) {
             const int s = k & 1;
             float2* wf = work_all + (size_t)s * CW * G::WORK + warp * G::WORK + fr * FSW;
+            if (PT == 16 && !(p.debug_flags & 32)) {  // (measured: +7 % at 16 taps per arm, -4 % at 8)
+                // the consumers have slack: pull the new rows the producers will need two iterations from now into L2,
+                // so the FIR loads (the critical path) pay an L2 instead of an HBM latency
+                const long long nf = (long long)(it + 2) * FPI;
+                if (nf >= 0 && nf + FPI <= p.T && it + 2 < it1) {
+                    const char* b = reinterpret_cast<const char*>(p.x + nf * N);
+#pragma unroll
+                    for (int u = 0; u < (FPI * N * 8) / (128 * CW * 32); ++u) prefetch_l2(b + (size_t)(u * CW * 32 + tid) * 128);
+                }
+            }
             mbar_wait(u_full + s, (uint32_t)((k >> 1) & 1));
             float2 pr[R / 2], pi[R / 2];
             {
@@ -238,14 +177,80 @@ __global__ void __launch_bounds__(512, 1) pfb_fm_ws_kernel(const PfbParams p) {
             }
             int slot = base_slot + warp * F + fr + 1;
             slot = (slot >= NSLOT) ? slot - NSLOT : slot;
-            if (k >= 1) mbar_wait(ring_free, (uint32_t)((k - 1) & 1));  // demod of the previous iteration has read the ring
+            if (k >= 1) mbar_wait(ring_free, (uint32_t)((k - 1) & 1));  // every consumer thread has read the ring
             {
                 float* fb = ring + slot * N;
 #pragma unroll
                 for (int m2 = 0; m2 < R; ++m2) fb[m2 * R + ll] = ph[m2];
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(ring_full);
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // consumer warps only: this iteration's angles are in the ring
+            // ---- demod: CPT channels x 8 consecutive frames per consumer thread ----
+            if (it >= it0) {
+                constexpr int CTHREADS = CW * 32;
+                constexpr int CPT = N * (FPI / 8) / CTHREADS;  // 4, 2, 1 for R = 32, 16, 8
+                constexpr int GRP = FPI / 8;
+                constexpr bool kPairLanes = (GRP == 2 && CPT >= 2);
+                const int g = kPairLanes ? (lane >> 4) : tid / (N / CPT);
+                const int m0 = kPairLanes ? (warp * 16 + (lane & 15)) * CPT : (tid % (N / CPT)) * CPT;
+                const long long t0 = (long long)it * FPI + 8 * g;
+                int sl = base_slot + 8 * g;
+                sl = (sl >= NSLOT) ? sl - NSLOT : sl;
+                const bool full = (t0 + 8 <= p.T);
+                float* dst0 = p.out_fm + pfb_out_index(p, m0, t0);
+                const long long rowstride = (p.oblock_log2 > 0) ? (1LL << p.oblock_log2) : p.ostride;
+                float pw[9][CPT];
+#pragma unroll
+                for (int j = 0; j < 9; ++j) {
+                    const float* src = ring + sl * N + m0;
+                    if constexpr (CPT == 4) {
+                        const float4 t = *reinterpret_cast<const float4*>(src);
+                        pw[j][0] = t.x; pw[j][1] = t.y; pw[j][2] = t.z; pw[j][3] = t.w;
+                    } else if constexpr (CPT == 2) {
+                        const float2 t = *reinterpret_cast<const float2*>(src);
+                        pw[j][0] = t.x; pw[j][1] = t.y;
+                    } else {
+                        pw[j][0] = *src;
+                    }
+                    sl = (sl + 1 == NSLOT) ? 0 : sl + 1;
+                }
+                float o[CPT][8];
+                if constexpr (CPT >= 2) {
+#pragma unroll
+                    for (int q = 0; q < CPT; q += 2) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float2 d = p2sub(make_float2(pw[j + 1][q], pw[j + 1][q + 1]), make_float2(pw[j][q], pw[j][q + 1]));
+                            const float2 kk = p2add(p2fmas(d, 0.15915494309189535f, make_float2(12582912.0f, 12582912.0f)),
+                                                    make_float2(-12582912.0f, -12582912.0f));
+                            d = p2fmas(kk, -6.283185307179586f, d);
+                            d = p2muls(d, p.gain);
+                            o[q][j] = (d.x != d.x) ? 0.0f : d.x;
+                            o[q + 1][j] = (d.y != d.y) ? 0.0f : d.y;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float d = pw[j + 1][0] - pw[j][0];
+                        const float kk = (d * 0.15915494309189535f + 12582912.0f) - 12582912.0f;
+                        d = fmaf(kk, -6.283185307179586f, d);
+                        d *= p.gain;
+                        o[0][j] = (d != d) ? 0.0f : d;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < CPT; ++q) {
+                    float* dst = dst0 + q * rowstride;
+                    if (full) {
+                        st_global_v8_hint(dst, o[q], pol_stream);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (t0 + j < p.T) dst[j] = o[q][j];
+                    }
+                }
+            }
+            mbar_arrive(ring_free);
             base_slot = (base_slot == 0) ? NSLOT - 1 : base_slot - 1;
         }
     }
