@@ -235,7 +235,8 @@ def cpu_run(wl, steps, warmup, log2n_cpu=None, budget_s=None):
     taps = make_taps(nch, ntaps)
     log2n = log2n_cpu or 22
     n = 1 << log2n
-    x = synth_block(n, nch, 3)
+    base = synth_block(min(n, 1 << 22), nch, 3)
+    x = np.tile(base, n // len(base)) if n > len(base) else base
     want_fm = cfg["out"] == "fm"
     threads = os.cpu_count() or gr_cpu.num_threads()   # torchrun exports OMP_NUM_THREADS=1: ask explicitly
     hist = None
@@ -259,7 +260,11 @@ def run_reference(args):
     if rank != 0:
         return 0
     cfg = WORKLOADS[args.workload]
-    msps, threads, done, n, dt = cpu_run(args.workload, args.steps, args.warmup)
+    # steps large enough that thread start-up does not understate the reference (2^26 samples = 0.5 GiB of IQ per step
+    # for the channelizer workloads: ~60 ms per step on 16 cores)
+    kind = cfg.get("kind")
+    msps, threads, done, n, dt = cpu_run(args.workload, args.steps, max(args.warmup, 1),
+                                         log2n_cpu=(25 if kind == "fft" else 24 if kind == "ddc" else 26), budget_s=150.0)
     sample = "%d steps x 2^%d samples of the %s stream (oracle/gr_cpu.c, OpenMP over frames)" % (
         done, int(np.log2(n)), args.workload)
     line = {
