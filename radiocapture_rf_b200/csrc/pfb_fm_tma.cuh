@@ -136,9 +136,11 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
     // ---- that recomputes the frame before it (no Y / phase state is carried between ranges or launches).
     // log-power rows are independent: no warm-up iteration, single-iteration dynamic chunks
     constexpr int WARM = (MODE == PFB_LOGPOW) ? 0 : 1;
-    constexpr int kTailChunk = (MODE == PFB_LOGPOW) ? 2 : 4;
+    // (RCB_PFB_DEBUG bits 8-11 / 12-15 override the chunk length / the static share in 16ths: tuning experiments)
+    const int kTailChunk = ((p.debug_flags >> 8) & 15) ? ((p.debug_flags >> 8) & 15) : ((MODE == PFB_LOGPOW) ? 2 : 4);
     const int NI = (p.T + FPI - 1) / FPI;
-    const int stat = (int)(((long long)(NI / (int)gridDim.x) * 7) / 8);
+    const int stat16 = ((p.debug_flags >> 12) & 15) ? ((p.debug_flags >> 12) & 15) : 14;
+    const int stat = (int)(((long long)(NI / (int)gridDim.x) * stat16) / 16);
     const int tail0 = stat * (int)gridDim.x;
     __shared__ int s_next;
     int cur0, cur1;
