@@ -241,10 +241,10 @@ int pfb_launch_tma(rcb_t* h, const PfbParams& p, bool query_only) {
 }
 
 // warp-specialised producer / consumer kernel (FM only, 2..16 taps per arm)
-template <int R, int PT, int PW = 8>
+template <int R, int PT, int PW = 8, int MODE = PFB_OUT_FM>
 int pfb_launch_ws(rcb_t* h, const PfbParams& p, bool query_only) {
-    using G = PfbWsGeom<R, PW>;
-    auto kern = pfb_fm_ws_kernel<R, PT, PW>;
+    using G = PfbWsGeom<R, PW, MODE>;
+    auto kern = pfb_fm_ws_kernel<R, PT, PW, MODE>;
     const size_t smem = G::smem_bytes(PT);
     if (query_only) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -294,6 +294,14 @@ int pfb_launch_tma_r(rcb_t* h, const PfbParams& p, bool q) {
             if (h->pfb.PT == 8) return (v == 12) ? pfb_launch_ws<R, 8, 12>(h, p, q) : pfb_launch_ws<R, 8>(h, p, q);
         }
         return pfb_launch_tma_pm<R, PFB_OUT_FM>(h, p, q);
+    }
+    // IQ outputs, 1024 channels, 8+ taps per arm: the warp-specialised kernel as well (208 KB: two frame-buffer sets +
+    // a ring of Y); RCB_PFB_VARIANT=8: the phase-serial one-CTA variant
+    if (R == 32 && v != 8 && (h->pfb.PT == 16 || h->pfb.PT == 8)) {
+        if (h->pfb.mode == RCB_OUT_IQ)
+            return h->pfb.PT == 16 ? pfb_launch_ws<R, 16, 8, PFB_OUT_IQ>(h, p, q) : pfb_launch_ws<R, 8, 8, PFB_OUT_IQ>(h, p, q);
+        return h->pfb.PT == 16 ? pfb_launch_ws<R, 16, 8, PFB_OUT_IQ | PFB_OUT_FM>(h, p, q)
+                               : pfb_launch_ws<R, 8, 8, PFB_OUT_IQ | PFB_OUT_FM>(h, p, q);
     }
     if (h->pfb.mode == RCB_OUT_IQ) return pfb_launch_tma_pm<R, PFB_OUT_IQ>(h, p, q);
     return pfb_launch_tma_pm<R, PFB_OUT_IQ | PFB_OUT_FM>(h, p, q);

@@ -75,6 +75,83 @@ __device__ __forceinline__ void tma_bulk_g2s_hint(void* dst_smem, const void* sr
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// demod phase when the ring holds Y (IQ / IQ+FM outputs): thread = CPT adjacent channels x 8 consecutive frames
+// starting at ring slot s (the slot of the frame before them); shared by the phase-serial and the warp-specialised
+// kernels.
+template <int N, int NSLOT, int CPT, int MODE>
+__device__ __forceinline__ void pfb_demod_from_y(const PfbParams& p, const float* ring, int s, int m0, long long t0,
+                                                 bool full, long long rowstride) {
+                const float2* ring2 = reinterpret_cast<const float2*>(ring);
+                float2* dq0 = (MODE & PFB_OUT_IQ) ? p.out_iq + pfb_out_index(p, m0, t0) : nullptr;
+                float* dst0 = (MODE & PFB_OUT_FM) ? p.out_fm + pfb_out_index(p, m0, t0) : nullptr;
+                constexpr int CW = (CPT >= 2) ? 2 : 1;  // channels handled together
+#pragma unroll
+                for (int q0 = 0; q0 < CPT; q0 += CW) {
+                    float2 y[9][CW];
+                    int sj = s;
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) {
+                        const float2* src = ring2 + sj * N + m0 + q0;
+                        if constexpr (CW == 2) {
+                            const float4 t = *reinterpret_cast<const float4*>(src);
+                            y[j][0] = make_float2(t.x, t.y);
+                            y[j][1] = make_float2(t.z, t.w);
+                        } else {
+                            y[j][0] = *src;
+                        }
+                        sj = (sj + 1 == NSLOT) ? 0 : sj + 1;
+                    }
+                    if constexpr ((MODE & PFB_OUT_IQ) != 0) {
+#pragma unroll
+                        for (int c = 0; c < CW; ++c) {
+                            float2* dst = dq0 + (q0 + c) * rowstride;
+                            if (full) {
+#pragma unroll
+                                for (int hh = 0; hh < 2; ++hh) {
+                                    float o[8];
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        o[2 * j] = y[1 + 4 * hh + j][c].x;
+                                        o[2 * j + 1] = y[1 + 4 * hh + j][c].y;
+                                    }
+                                    st_global_v8(reinterpret_cast<float*>(dst + 4 * hh), o);
+                                }
+                            } else if (!(p.debug_flags & 1)) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    if (t0 + j < p.T) dst[j] = y[j + 1][c];
+                            }
+                        }
+                    }
+                    if constexpr ((MODE & PFB_OUT_FM) != 0) {
+                        float o[CW][8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if constexpr (CW == 2) {  // p = y[j+1] conj(y[j]) for both channels, packed atan2
+                                const float2 a0 = cmul_conj(y[j + 1][0], y[j][0]), a1 = cmul_conj(y[j + 1][1], y[j][1]);
+                                const float2 ang = atan2_zero_p2(make_float2(a0.y, a1.y), make_float2(a0.x, a1.x));
+                                o[0][j] = p.gain * ang.x;
+                                o[1][j] = p.gain * ang.y;
+                            } else {
+                                const float2 a0 = cmul_conj(y[j + 1][0], y[j][0]);
+                                o[0][j] = p.gain * atan2_fast(a0.y, a0.x);
+                            }
+                        }
+#pragma unroll
+                        for (int c = 0; c < CW; ++c) {
+                            float* dst = dst0 + (q0 + c) * rowstride;
+                            if (full) {
+                                st_global_v8(dst, o[c]);
+                            } else if (!(p.debug_flags & 1)) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    if (t0 + j < p.T) dst[j] = o[c][j];
+                            }
+                        }
+                    }
+                }
+}
+
 // twiddle table layout expected in p.twiddle for this kernel: dense [R][R] complex, 16-byte chunks swizzled:
 //   tw[ll*R + (((m1>>1) ^ swz(ll))<<1 | (m1&1))] = W_N^{+(R-1-ll) m1}
 // taps layout: float4 groups as in pfb_fm.cuh (P = 1).
@@ -461,74 +538,7 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
                 }
             }
                     } else {
-                const float2* ring2 = reinterpret_cast<const float2*>(ring);
-                float2* dq0 = (MODE & PFB_OUT_IQ) ? p.out_iq + pfb_out_index(p, m0, t0) : nullptr;
-                constexpr int CW = (CPT >= 2) ? 2 : 1;  // channels handled together
-#pragma unroll
-                for (int q0 = 0; q0 < CPT; q0 += CW) {
-                    float2 y[9][CW];
-                    int sj = s;
-#pragma unroll
-                    for (int j = 0; j < 9; ++j) {
-                        const float2* src = ring2 + sj * N + m0 + q0;
-                        if constexpr (CW == 2) {
-                            const float4 t = *reinterpret_cast<const float4*>(src);
-                            y[j][0] = make_float2(t.x, t.y);
-                            y[j][1] = make_float2(t.z, t.w);
-                        } else {
-                            y[j][0] = *src;
-                        }
-                        sj = (sj + 1 == NSLOT) ? 0 : sj + 1;
-                    }
-                    if constexpr ((MODE & PFB_OUT_IQ) != 0) {
-#pragma unroll
-                        for (int c = 0; c < CW; ++c) {
-                            float2* dst = dq0 + (q0 + c) * rowstride;
-                            if (full) {
-#pragma unroll
-                                for (int hh = 0; hh < 2; ++hh) {
-                                    float o[8];
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) {
-                                        o[2 * j] = y[1 + 4 * hh + j][c].x;
-                                        o[2 * j + 1] = y[1 + 4 * hh + j][c].y;
-                                    }
-                                    st_global_v8(reinterpret_cast<float*>(dst + 4 * hh), o);
-                                }
-                            } else if (!(p.debug_flags & 1)) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j)
-                                    if (t0 + j < p.T) dst[j] = y[j + 1][c];
-                            }
-                        }
-                    }
-                    if constexpr ((MODE & PFB_OUT_FM) != 0) {
-                        float o[CW][8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            if constexpr (CW == 2) {  // p = y[j+1] conj(y[j]) for both channels, packed atan2
-                                const float2 a0 = cmul_conj(y[j + 1][0], y[j][0]), a1 = cmul_conj(y[j + 1][1], y[j][1]);
-                                const float2 ang = atan2_zero_p2(make_float2(a0.y, a1.y), make_float2(a0.x, a1.x));
-                                o[0][j] = p.gain * ang.x;
-                                o[1][j] = p.gain * ang.y;
-                            } else {
-                                const float2 a0 = cmul_conj(y[j + 1][0], y[j][0]);
-                                o[0][j] = p.gain * atan2_fast(a0.y, a0.x);
-                            }
-                        }
-#pragma unroll
-                        for (int c = 0; c < CW; ++c) {
-                            float* dst = dst0 + (q0 + c) * rowstride;
-                            if (full) {
-                                st_global_v8(dst, o[c]);
-                            } else if (!(p.debug_flags & 1)) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j)
-                                    if (t0 + j < p.T) dst[j] = o[c][j];
-                            }
-                        }
-                    }
-                }
+                pfb_demod_from_y<N, NSLOT, CPT, MODE>(p, ring, s, m0, t0, full, rowstride);
             }
         }
         mbar_arrive(cta_bar);

@@ -21,7 +21,7 @@
 
 namespace rcb {
 
-template <int R, int PW = 8>
+template <int R, int PW = 8, int MODE = PFB_OUT_FM>
 struct PfbWsGeom {
     static constexpr int N = R * R;
     static constexpr int F = 32 / R;
@@ -32,14 +32,14 @@ struct PfbWsGeom {
     static constexpr int FSW = N + (R == 8 ? 8 : 0);
     static constexpr int WORK = F * FSW;  // complex per consumer warp and buffer set
     static constexpr size_t set_bytes = (size_t)CW * WORK * 8;
-    static constexpr size_t ring_bytes = (size_t)NSLOT * N * 4;
+    static constexpr size_t ring_bytes = (size_t)NSLOT * N * (MODE == PFB_OUT_FM ? 4 : 8);  // angle(Y), or Y when IQ is an output
     static constexpr size_t tw_bytes = (size_t)N * 8;
     static constexpr size_t smem_bytes(int /*PT*/) { return 2 * set_bytes + ring_bytes + tw_bytes + 128; }
 };
 
-template <int R, int PT, int PW = 8>
+template <int R, int PT, int PW = 8, int MODE = PFB_OUT_FM>
 __global__ void __launch_bounds__((8 + PW) * 32, 1) pfb_fm_ws_kernel(const PfbParams p) {
-    using G = PfbWsGeom<R, PW>;
+    using G = PfbWsGeom<R, PW, MODE>;
     constexpr int N = G::N, F = G::F, FPI = G::FPI, NSLOT = G::NSLOT, FSW = G::FSW, CW = G::CW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float2* work_all = reinterpret_cast<float2*>(smem_raw);  // [2 sets][CW][WORK]
@@ -168,20 +168,29 @@ __global__ void __launch_bounds__((8 + PW) * 32, 1) pfb_fm_ws_kernel(const PfbPa
                 auto tap = [&](auto) { return 1.0f; };
                 fft_packed<R, +1, false>(pr, pi, get, tap);  // (pr[q], pi[q]) = Y[ll + R*(2q)], Y[ll + R*(2q+1)]
             }
-            float ph[R];
+            float ph[MODE == PFB_OUT_FM ? R : 1];
+            if constexpr (MODE == PFB_OUT_FM) {
 #pragma unroll
-            for (int q = 0; q < R / 2; ++q) {
-                const float2 a = atan2_nan_p2(pi[q], pr[q]);
-                ph[2 * q] = a.x;
-                ph[2 * q + 1] = a.y;
+                for (int q = 0; q < R / 2; ++q) {
+                    const float2 a = atan2_nan_p2(pi[q], pr[q]);
+                    ph[2 * q] = a.x;
+                    ph[2 * q + 1] = a.y;
+                }
             }
             int slot = base_slot + warp * F + fr + 1;
             slot = (slot >= NSLOT) ? slot - NSLOT : slot;
             if (k >= 1) mbar_wait(ring_free, (uint32_t)((k - 1) & 1));  // every consumer thread has read the ring
-            {
+            if constexpr (MODE == PFB_OUT_FM) {
                 float* fb = ring + slot * N;
 #pragma unroll
                 for (int m2 = 0; m2 < R; ++m2) fb[m2 * R + ll] = ph[m2];
+            } else {  // IQ is an output: the ring holds Y
+                float2* fb = reinterpret_cast<float2*>(ring) + slot * N;
+#pragma unroll
+                for (int q = 0; q < R / 2; ++q) {
+                    fb[(2 * q) * R + ll] = make_float2(pr[q].x, pi[q].x);
+                    fb[(2 * q + 1) * R + ll] = make_float2(pr[q].y, pi[q].y);
+                }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");  // consumer warps only: this iteration's angles are in the ring
             // ---- demod: CPT channels x 8 consecutive frames per consumer thread ----
@@ -196,8 +205,11 @@ __global__ void __launch_bounds__((8 + PW) * 32, 1) pfb_fm_ws_kernel(const PfbPa
                 int sl = base_slot + 8 * g;
                 sl = (sl >= NSLOT) ? sl - NSLOT : sl;
                 const bool full = (t0 + 8 <= p.T);
-                float* dst0 = p.out_fm + pfb_out_index(p, m0, t0);
                 const long long rowstride = (p.oblock_log2 > 0) ? (1LL << p.oblock_log2) : p.ostride;
+                if constexpr (MODE != PFB_OUT_FM) {
+                    pfb_demod_from_y<N, NSLOT, CPT, MODE>(p, ring, sl, m0, t0, full, rowstride);
+                } else {
+                float* dst0 = p.out_fm + pfb_out_index(p, m0, t0);
                 float pw[9][CPT];
 #pragma unroll
                 for (int j = 0; j < 9; ++j) {
@@ -248,6 +260,7 @@ __global__ void __launch_bounds__((8 + PW) * 32, 1) pfb_fm_ws_kernel(const PfbPa
                         for (int j = 0; j < 8; ++j)
                             if (t0 + j < p.T) dst[j] = o[q][j];
                     }
+                }
                 }
             }
             mbar_arrive(ring_free);
