@@ -40,7 +40,9 @@ def num_threads():
     return int(load().grc_num_threads())
 
 
-def pfb_fm(x, nchans, taps, gain, want_iq=True, want_fm=True, hist=None, nthreads=0):
+def pfb_fm(x, nchans, taps, gain, want_iq=True, want_fm=True, hist=None, nthreads=0, out_iq=None, out_fm=None):
+    """out_iq / out_fm: optional preallocated [nchans][t] outputs (a timed loop should not pay first-touch page
+    faults of fresh buffers on every step)."""
     lib = load()
     x = np.ascontiguousarray(x, np.complex64)
     taps = np.ascontiguousarray(taps, np.float32)
@@ -48,8 +50,10 @@ def pfb_fm(x, nchans, taps, gain, want_iq=True, want_fm=True, hist=None, nthread
     p = -(-len(taps) // nchans)
     if hist is None:
         hist = np.zeros(p * nchans, np.complex64)
-    iq = np.empty((nchans, t), np.complex64) if want_iq else None
-    fm = np.empty((nchans, t), np.float32) if want_fm else None
+    iq = (out_iq if out_iq is not None else np.empty((nchans, t), np.complex64)) if want_iq else None
+    fm = (out_fm if out_fm is not None else np.empty((nchans, t), np.float32)) if want_fm else None
+    assert iq is None or (iq.shape == (nchans, t) and iq.dtype == np.complex64 and iq.flags.c_contiguous)
+    assert fm is None or (fm.shape == (nchans, t) and fm.dtype == np.float32 and fm.flags.c_contiguous)
     rc = lib.grc_pfb_fm(x.ctypes.data, t, nchans, taps.ctypes.data, len(taps), gain,
                         iq.ctypes.data if want_iq else None, fm.ctypes.data if want_fm else None, max(t, 1),
                         hist.ctypes.data, nthreads)

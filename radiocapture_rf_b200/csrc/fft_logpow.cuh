@@ -185,9 +185,9 @@ template <int R>
 __global__ void __launch_bounds__(256, 2) fft_cols_tma_kernel(const __grid_constant__ CUtensorMap tm, const FftParams p) {
     using G = FftColsGeom<R>;
     constexpr int L1 = G::L1, CB = G::CB, BL = G::BL, RP = G::RP, S = G::S;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float2* tile = reinterpret_cast<float2*>(smem_raw);
-    float2* tws = reinterpret_cast<float2*>(smem_raw + G::tile_bytes);
+    extern __shared__ __align__(128) unsigned char smem_raw128[];
+    float2* tile = reinterpret_cast<float2*>(smem_raw128);
+    float2* tws = reinterpret_cast<float2*>(smem_raw128 + G::tile_bytes);
     float2* rho = tws + R * S;  // [kb][c] = W_L^{-(c0 + c) R kb}
     uint64_t* bar = reinterpret_cast<uint64_t*>(rho + R * CB);
 

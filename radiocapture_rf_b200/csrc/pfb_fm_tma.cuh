@@ -181,12 +181,12 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
     constexpr bool REVI = (MODE != PFB_LOGPOW);  // PFB arms are commutated in reverse order
     constexpr int THREADS = G::THREADS;
     constexpr int N = G::N, F = G::F, FPI = G::FPI, NSLOT = G::NSLOT, FSW = G::FSW;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float2* work_all = reinterpret_cast<float2*>(smem_raw);
-    float* ring = reinterpret_cast<float*>(smem_raw + G::work_bytes);
-    float2* tws = reinterpret_cast<float2*>(smem_raw + G::work_bytes + G::ring_bytes);
-    float* taps_s = reinterpret_cast<float*>(smem_raw + G::work_bytes + G::ring_bytes + G::tw_bytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + G::work_bytes + G::ring_bytes + G::tw_bytes + G::taps_bytes);
+    extern __shared__ __align__(128) unsigned char smem_raw128[];
+    float2* work_all = reinterpret_cast<float2*>(smem_raw128);
+    float* ring = reinterpret_cast<float*>(smem_raw128 + G::work_bytes);
+    float2* tws = reinterpret_cast<float2*>(smem_raw128 + G::work_bytes + G::ring_bytes);
+    float* taps_s = reinterpret_cast<float*>(smem_raw128 + G::work_bytes + G::ring_bytes + G::tw_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw128 + G::work_bytes + G::ring_bytes + G::tw_bytes + G::taps_bytes);
     uint64_t* cta_bar = bars + W;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

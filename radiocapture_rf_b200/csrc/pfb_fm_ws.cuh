@@ -41,11 +41,11 @@ template <int R, int PT, int PW = 8, int MODE = PFB_OUT_FM>
 __global__ void __launch_bounds__((8 + PW) * 32, 1) pfb_fm_ws_kernel(const PfbParams p) {
     using G = PfbWsGeom<R, PW, MODE>;
     constexpr int N = G::N, F = G::F, FPI = G::FPI, NSLOT = G::NSLOT, FSW = G::FSW, CW = G::CW;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float2* work_all = reinterpret_cast<float2*>(smem_raw);  // [2 sets][CW][WORK]
-    float* ring = reinterpret_cast<float*>(smem_raw + 2 * G::set_bytes);
-    float2* tws = reinterpret_cast<float2*>(smem_raw + 2 * G::set_bytes + G::ring_bytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * G::set_bytes + G::ring_bytes + G::tw_bytes);
+    extern __shared__ __align__(128) unsigned char smem_raw128[];
+    float2* work_all = reinterpret_cast<float2*>(smem_raw128);  // [2 sets][CW][WORK]
+    float* ring = reinterpret_cast<float*>(smem_raw128 + 2 * G::set_bytes);
+    float2* tws = reinterpret_cast<float2*>(smem_raw128 + 2 * G::set_bytes + G::ring_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw128 + 2 * G::set_bytes + G::ring_bytes + G::tw_bytes);
     uint64_t* u_full = bars;       // [2] producers -> consumers: frame buffers of set s hold filtered frames
     uint64_t* u_empty = bars + 2;  // [2] consumers -> producers: set s has been transformed
     uint64_t* ring_free = bars + 4;  // consumer threads: arrive after the demod reads / wait before the next ring write
