@@ -29,8 +29,10 @@ import uuid
 import numpy as np
 
 from . import channel as channel_mod
+from . import firdes
 from .channel import channel
-from .engine import DdcBank, Engine, OUT_IQ
+from ._lib import COPY_H2D, check
+from .engine import DdcBank, Engine, PfbChannelizer, OUT_IQ
 
 
 class SourceStream(object):
@@ -154,6 +156,116 @@ class SourceStream(object):
             self.engine.close()
 
 
+class BinStream(object):
+    """One output bin of a source's polyphase channelizer, acting as the (400 kHz) source of the second-stage
+    `channel` blocks the reference connects to it: `channel.channel(port, channel_rate, pfb_samp_rate, pfb_offset)`
+    + `self.connect((pfb, pfb_id), block)` (rc_frontend/receiver.py:403-417).  Own GPU handle = own DDC bank."""
+
+    def __init__(self, parent, bin_index, device):
+        self.parent = parent
+        self.bin_index = bin_index
+        self.lock = parent.lock
+        self.samp_rate = parent.pfb_samp_rate
+        self.engine = Engine(device)
+        self.bank = DdcBank(self.engine)
+        self.channels = {}
+
+    def open_channel(self, ch):
+        with self.lock:
+            cid = self.bank.open(ch.decim, ch.taps, float(ch.offset), float(ch.samp_rate), OUT_IQ, 1.0)
+            self.channels[cid] = ch
+            return cid
+
+    def retune_channel(self, cid, offset):
+        with self.lock:
+            self.bank.retune(cid, float(offset))
+
+    def set_channel_taps(self, cid, taps):
+        with self.lock:
+            self.bank.set_taps(cid, taps)
+
+    def close_channel(self, cid):
+        with self.lock:
+            self.channels.pop(cid, None)
+            self.bank.close(cid)
+
+    def push_device(self, d_ptr, nsamples):
+        """`nsamples` complex64 samples of this bin, resident on the device (a row of the PFB output)."""
+        self.bank.process_device(d_ptr, nsamples)
+        for cid, ch in list(self.channels.items()):
+            ch.deliver(self.bank.pull(cid, OUT_IQ))
+
+    def close(self):
+        self.engine.close()
+
+
+class PfbSourceStream(SourceStream):
+    """frontend_mode 'pfb' (rc_frontend/receiver.py:242-261): the wideband stream goes once through
+    `pfb.channelizer_ccf(num_channels, optfir.low_pass(1, N, 0.5, 0.7, 0.1, 80), 1.0, 100)` with
+    num_channels = samp_rate / 400 kHz (K1, device resident), and each requested channel is a second-stage
+    `channel` (freq_xlating_fir_filter_ccc at the 400 kHz bin rate: 59 taps, decimation 16 for 12.5 kHz channels)
+    on its bin (K2 on the bin's row of the PFB output - the samples never leave the GPU in between)."""
+
+    target_size = 400000  # rc_frontend/receiver.py:244
+
+    def __init__(self, source_id, cfg, device=0, block_samples=None, engine_factory=None):
+        if engine_factory is not None:
+            raise NotImplementedError("pfb mode needs the GPU engine")
+        SourceStream.__init__(self, source_id, cfg, device=device, block_samples=block_samples)
+        self.device = device
+        self.num_channels = int(self.samp_rate // self.target_size)
+        if self.num_channels < 1:
+            raise ValueError("samp_rate %s is below one %s Hz pfb bin" % (self.samp_rate, self.target_size))
+        self.pfb_samp_rate = self.samp_rate / float(self.num_channels)
+        self.pfb_taps = firdes.pfb_prototype(self.num_channels)
+        self.pfb = PfbChannelizer(self.engine, self.num_channels, self.pfb_taps, OUT_IQ, 1.0)
+        self.bins = {}
+        self._rem = np.zeros(0, np.complex64)
+        self._d_in = None
+        self._d_iq = None
+        self._cap = 0
+
+    def bin_stream(self, chan):
+        with self.lock:
+            if chan not in self.bins:
+                self.bins[chan] = BinStream(self, chan, self.device)
+            return self.bins[chan]
+
+    def push(self, iq):
+        with self.lock:
+            if self.channels:  # channels opened directly on the wideband stream (xlat style) keep working
+                SourceStream.push(self, iq)
+            else:
+                self.samples_in += len(iq)
+            n = self.num_channels
+            x = np.concatenate([self._rem, np.asarray(iq, np.complex64)]) if len(self._rem) else np.asarray(iq, np.complex64)
+            nfr = len(x) // n        # stream_to_streams granularity: whole frames only, the rest waits
+            self._rem = x[nfr * n:].copy()
+            if nfr == 0:
+                return
+            x = np.ascontiguousarray(x[:nfr * n])
+            if self._cap < nfr:
+                for b in (self._d_in, self._d_iq):
+                    if b is not None:
+                        b.free()
+                self._cap = nfr + nfr // 4
+                self._d_in = self.engine.dev_alloc(self._cap * n * 8)
+                self._d_iq = self.engine.dev_alloc(self._cap * n * 8)
+            check(self.engine.lib.rcb_memcpy(self.engine.h, self._d_in.ptr, x.ctypes.data, x.nbytes, COPY_H2D),
+                  "rcb_memcpy h2d", self.engine.h)
+            self.pfb.process_device(self._d_in, nfr * n, self._d_iq, None, nfr)   # bin m = row m, nfr samples
+            self.engine.sync()
+            for m, bs in list(self.bins.items()):
+                if bs.channels:
+                    bs.push_device(self._d_iq.ptr + m * nfr * 8, nfr)
+
+    def stop(self):
+        for bs in list(self.bins.values()):
+            bs.close()
+        self.bins = {}
+        SourceStream.stop(self)
+
+
 def _default_generator(src, n0, n):
     rng = np.random.default_rng(n0 & 0xffffffff)
     return (rng.standard_normal(2 * n, dtype=np.float32) * np.float32(0.05)).view(np.complex64)
@@ -199,7 +311,10 @@ class receiver(object):
         for source in sorted(self.realsources):
             cfg = dict(self.realsources[source])
             dev = (devices[numsources % ndev] if devices else 0)
-            stream = SourceStream(source, cfg, device=dev, engine_factory=engine_factory)
+            if self.frontend_mode == "pfb" and engine_factory is None:
+                stream = PfbSourceStream(source, cfg, device=dev)
+            else:
+                stream = SourceStream(source, cfg, device=dev, engine_factory=engine_factory)
             cfg["block"] = stream
             cfg["source_id"] = source
             self.sources[numsources] = cfg
@@ -244,10 +359,10 @@ class receiver(object):
 
     # ---- channel requests ------------------------------------------------------------------------
     def connect_channel(self, channel_rate, freq):
-        if self.frontend_mode in ("xlat", "pfb"):
-            # 'pfb' (rc_frontend/receiver.py:343-423) is bit-rotted upstream (Appendix C.4); its intent -
-            # many channels sharing one wideband pass - is what the DDC bank already does.
+        if self.frontend_mode == "xlat":
             return self.connect_channel_xlat(channel_rate, freq)
+        if self.frontend_mode == "pfb":
+            return self.connect_channel_pfb(channel_rate, freq)
         raise Exception("No frontend_mode selected")
 
     def connect_channel_xlat(self, channel_rate, freq):
@@ -301,18 +416,69 @@ class receiver(object):
             return block.block_id, port
 
     def connect_channel_pfb(self, channel_rate, freq):
-        return self.connect_channel_xlat(channel_rate, freq)
+        """rc_frontend/receiver.py:343-423 as intended (the shipped code is bit-rotted): pick the
+        source, the 400 kHz bin and the residual offset (:365-377), reuse an idle second-stage channel of that bin
+        (:386-394) or build `channel(port, channel_rate, pfb_samp_rate, pfb_offset)` and connect it to the bin
+        (:396-417)."""
+        source_id = None
+        if not self.scan_mode:
+            for i in list(self.sources):
+                if abs(freq - self.sources[i]["center_freq"]) < self.sources[i]["samp_rate"] / 2:
+                    source_id = i
+                    break
+            if source_id is None:
+                raise Exception("Unable to find source for frequency %s" % freq)
+        else:
+            source_id = 0
+        stream = self.sources[source_id]["block"]
+        if not isinstance(stream, PfbSourceStream):  # fake engines (host tests): the DDC bank does the whole job
+            return self.connect_channel_xlat(channel_rate, freq)
+        if freq < 10000000:  # scan mode, relative freq (:295-305)
+            freq = freq + self.sources[source_id]["center_freq"]
+        chan, pfb_offset, _ = self.pfb_bin_for(source_id, freq, stream.pfb_samp_rate)
+        half = stream.pfb_samp_rate / 2.0
+        if pfb_offset < -half + channel_rate / 2.0 or pfb_offset > half - channel_rate / 2.0:
+            self.log.warning("warning: %s edge boundary" % freq)
+        with self.access_lock:
+            block = None
+            for c in list(self.channels):
+                ch = self.channels[c]
+                if ch.source_id == source_id and ch.pfb_id == chan and ch.channel_rate == channel_rate and not ch.in_use:
+                    block = ch
+                    port = block.port
+                    block.set_offset(pfb_offset)
+                    block.channel_close_time = 0
+                    break
+            if block is None:
+                for x in range(0, 3):
+                    port = random.randint(10000, 60000)
+                    try:
+                        block = channel(port, channel_rate, stream.pfb_samp_rate, pfb_offset, sink=self.sink_kind)
+                        break
+                    except RuntimeError:
+                        self.log.error("Failed to build channel on port: %s attempt: %s" % (port, x))
+                        block = None
+                if block is None:
+                    return False, False
+                block.source_id = source_id
+                block.pfb_id = chan
+                block_id = "%s" % uuid.uuid4()
+                self.channels[block_id] = block   # keyed by block id (the reference keys by port here, Appendix C.4)
+                block.block_id = block_id
+                block.connect_source(stream.bin_stream(chan))   # self.connect((pfb, pfb_id), block)
+                block.start()
+            block.in_use = True
+            return block.block_id, port
 
     def pfb_bin_for(self, source_id, freq, target_size=400000):
         """rc_frontend/receiver.py:365-383 bin / residual arithmetic (row a4), with the negative-bin
         residual computed before the wrap (the reference subtracts the wrapped bin, Appendix C.4)."""
         src = self.sources[source_id]
-        num_channels = int(src["samp_rate"] // target_size)
+        num_channels = int(round(src["samp_rate"] / float(target_size)))
         offset = freq - src["center_freq"]
         chan = int(round(offset / float(target_size)))
         pfb_offset = offset - chan * target_size
-        if chan < 0:
-            chan += num_channels
+        chan %= num_channels   # negative bins wrap (:373-375); so does +N/2 of an even channel count
         edge = (pfb_offset < (-target_size / 2) or pfb_offset > (target_size / 2))
         return chan, pfb_offset, edge
 

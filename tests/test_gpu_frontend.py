@@ -55,6 +55,46 @@ def test_create_channel_rpc_delivers_oracle_samples(built_lib):
         tb.stop()
 
 
+def test_pfb_mode_two_stage_channel_matches_oracle(built_lib):
+    """frontend_mode = 'pfb' (rc_frontend/receiver.py:242-261, 343-423): pfb.channelizer_ccf with 400 kHz bins, then a
+    second-stage channel (59-tap xlating FIR, decimation 16) on the bin - both stages on the GPU, the bin rows never
+    leave the device.  Oracle = the same two GNU Radio blocks in float64."""
+    cfg = Cfg()
+    cfg.frontend_mode = "pfb"
+    cfg.sources = {0: dict(Cfg.sources[0])}
+    tb = receiver(config=cfg, sink="capture", use_zmq=False)
+    try:
+        assert tb.handler("connect") == "connect,0"
+        want = {855487500: (1, 37500.0),      # +437.5 kHz -> bin 1, +37.5 kHz
+                854987500: (0, -62500.0),     # -62.5 kHz  -> bin 0
+                854012500: (3, 162500.0)}     # -1.0375 MHz -> bin -3 -> wraps to bin 3 of 6, +162.5 kHz
+        chans = {}
+        for f, (b, off) in want.items():
+            r = tb.handler("create,0,12500,%d" % f).split(",")
+            assert r[0] == "create"
+            ch = tb.channels[r[1]]
+            assert ch.pfb_id == b and abs(ch.offset - off) < 1e-6 and ch.decim == 16 and len(ch.taps) == 59
+            chans[f] = ch
+        x, fs, offs = synth.cfg1(6 * 16 * 1500, seed=1)
+        for blk in np.array_split(x, 7):      # ragged blocks: frames are cut at arbitrary samples
+            tb.push(0, blk)
+        stream = tb.sources[0]["block"]
+        bins = gb.pfb_channelizer(x, np.asarray(stream.pfb_taps, np.float64), 6)
+        for f, (b, off) in want.items():
+            y = chans[f].sink.data()
+            ref = gb.freq_xlating_fir(bins[b], chans[f].taps, 16, off, 400000.0)
+            n = min(len(y), len(ref))
+            assert n >= 1490
+            assert gb.rel_l2(y[:n], ref[:n]) <= 1e-5, (f, gb.rel_l2(y[:n], ref[:n]))
+        # release + re-create inside the same bin reuses the parked second stage via set_offset (:386-394)
+        first = [k for k, v in tb.channels.items() if v is chans[855487500]][0]
+        assert tb.handler("release,0,%s" % first).startswith("release")
+        r = tb.handler("create,0,12500,855500000").split(",")
+        assert r[1] == first and abs(tb.channels[first].offset - 50000.0) < 1e-6
+    finally:
+        tb.stop()
+
+
 def test_fft_vector_and_peak_detection_mirror(engine, tmp_path):
     """fft_vector.py -> /tmp/fft_source_<i> -> fft_peak_detection.py, GPU vs oracle: identical peak indices."""
     from radiocapture_rf_b200.fft_peak_detection import detect_peaks, load_vector
