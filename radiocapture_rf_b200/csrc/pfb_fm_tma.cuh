@@ -39,14 +39,8 @@ struct PfbTmaGeom {
     static constexpr size_t tw_bytes = (size_t)N * 8;
     static constexpr size_t taps_bytes = (size_t)N * 4;
     static constexpr size_t smem_bytes = work_bytes + ring_bytes + tw_bytes + taps_bytes + 256;
-    // resident CTAs per SM the register allocation is tuned for (small transforms leave room for more warps)
-    static constexpr int MIN_CTAS_BASE = (2 * smem_bytes <= 227 * 1024 && W <= 8) ? 2 : 1;
-#ifdef RCB_OCC_EXPERIMENT
-    static constexpr int MIN_CTAS = (W == 8 && R == 8 && 4 * smem_bytes <= 227 * 1024) ? 4
-                                    : (W == 8 && R == 16 && 3 * smem_bytes <= 227 * 1024) ? 3 : MIN_CTAS_BASE;
-#else
-    static constexpr int MIN_CTAS = MIN_CTAS_BASE;
-#endif
+    // resident CTAs per SM the register allocation is tuned for (3-4 CTAs/SM for N = 64 / 256 were measured: no gain)
+    static constexpr int MIN_CTAS = (2 * smem_bytes <= 227 * 1024 && W <= 8) ? 2 : 1;
 };
 
 template <int R>
@@ -204,7 +198,7 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     const float4* tap4 = reinterpret_cast<const float4*>(taps_s);
-    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+    const uint64_t pol_stream = l2_policy_evict_first();  // (evict_last on the row loads and L2 prefetches: no gain)
 
     // ---- work distribution: a static contiguous run (7/8 of the even share) per CTA, then the tail of the
     // ---- launch is handed out dynamically in chunks of kTailChunk iterations (atomic counter).  SMs differ
@@ -213,11 +207,10 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
     // ---- that recomputes the frame before it (no Y / phase state is carried between ranges or launches).
     // log-power rows are independent: no warm-up iteration, single-iteration dynamic chunks
     constexpr int WARM = (MODE == PFB_LOGPOW) ? 0 : 1;
-    // (RCB_PFB_DEBUG bits 8-11 / 12-15 override the chunk length / the static share in 16ths: tuning experiments)
-    const int kTailChunk = ((p.debug_flags >> 8) & 15) ? ((p.debug_flags >> 8) & 15) : ((MODE == PFB_LOGPOW) ? 2 : 4);
+    // (chunk lengths 2..8 and static shares 12/16..15/16 were measured: all within 1 %)
+    constexpr int kTailChunk = (MODE == PFB_LOGPOW) ? 2 : 4;
     const int NI = (p.T + FPI - 1) / FPI;
-    const int stat16 = ((p.debug_flags >> 12) & 15) ? ((p.debug_flags >> 12) & 15) : 14;
-    const int stat = (int)(((long long)(NI / (int)gridDim.x) * stat16) / 16);
+    const int stat = (int)(((long long)(NI / (int)gridDim.x) * 7) / 8);
     const int tail0 = stat * (int)gridDim.x;
     __shared__ int s_next;
     int cur0, cur1;
@@ -266,14 +259,6 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
             constexpr int TBK = (FPI % 16 == 0 && N * (FPI / 16) >= THREADS) ? 16 : 8;
             constexpr int NX = TBK + PT - 1;
             constexpr int TASKS = N * (FPI / TBK) / THREADS;
-            if (p.debug_flags & 16) {  // experiment: pull the next iteration's new rows into L2 now
-                const long long nf = (long long)(it + 1) * FPI;
-                if (nf >= 0 && nf + FPI <= p.T) {
-                    const char* b = reinterpret_cast<const char*>(p.x + nf * N);
-#pragma unroll
-                    for (int u = 0; u < (FPI * N * 8) / (128 * THREADS); ++u) prefetch_l2(b + (size_t)(u * THREADS + tid) * 128);
-                }
-            }
 #pragma unroll 1
             for (int q = 0; q < TASKS; ++q) {
                 const int task = q * THREADS + tid;
@@ -283,13 +268,8 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
                 float2 xs[NX];
                 if (r0 >= 0 && f0 + TBK <= p.T) {
                     const float2* b = p.x + r0 * N + c;
-                    if (p.debug_flags & 4) {  // experiment: keep input rows in L2 until their last use as history
 #pragma unroll
-                        for (int j = 0; j < NX; ++j) xs[j] = ldg_f2_hint(b + (long long)j * N, pol_keep);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < NX; ++j) xs[j] = __ldg(b + (long long)j * N);
-                    }
+                    for (int j = 0; j < NX; ++j) xs[j] = __ldg(b + (long long)j * N);
                 } else {
 #pragma unroll
                     for (int j = 0; j < NX; ++j) xs[j] = __ldg(pfb_row_ptr<R>(p, r0 + j) + c);
