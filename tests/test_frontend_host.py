@@ -258,3 +258,28 @@ def test_unmodified_reference_frontend_connector_works_against_us():
         fc.exit()
         time.sleep(0.4)
         tb.stop()
+
+
+def test_pfb_mode_bin_arithmetic_and_host_fallback():
+    """frontend_mode 'pfb' (rc_frontend/receiver.py:365-383): bin / residual arithmetic incl. the negative-bin wrap
+    and non-integer bin widths; with an injected (CPU) engine the request is served by the DDC bank directly."""
+    cfg = Cfg()
+    cfg.frontend_mode = "pfb"
+    cfg.sources = {0: {"type": "push", "center_freq": 855050000, "samp_rate": 2400000},
+                   1: {"type": "push", "center_freq": 860000000, "samp_rate": 2850000}}
+    tb = receiver(config=cfg, sink="capture", engine_factory=FakeEngine, use_zmq=False)
+    try:
+        assert tb.pfb_bin_for(0, 855050000 + 437500) == (1, 37500, False)
+        assert tb.pfb_bin_for(0, 855050000 - 1037500) == (3, 162500, False)      # bin -3 wraps to 3 of 6
+        assert tb.pfb_bin_for(0, 855050000 + 1190000)[0] == 3                     # +3 is the same (Nyquist) bin
+        # 2.85 Msps: 7 bins of 407142.857 Hz (the reference divides by the nominal 400 kHz, Appendix C.4)
+        w = 2850000 / 7.0
+        chan, off, edge = tb.pfb_bin_for(1, 860000000 - 500000, w)
+        assert chan == 6 and abs(off - (-500000 + w)) < 1e-6 and not edge
+        assert tb.handler("connect") == "connect,0"
+        r = tb.handler("create,0,12500,855487500").split(",")
+        assert r[0] == "create"
+        ch = tb.channels[r[1]]
+        assert ch.source_id == 0 and ch.decim == 96 and ch.offset == 437500      # fallback: single-stage channel
+    finally:
+        tb.stop()
