@@ -253,10 +253,14 @@ def fft_vcc(frames, window, shift=True):
     return out
 
 
+def nlog10(v, n=1.0, k=0.0):
+    """blocks.nlog10_ff(n, vlen, k) (gr-blocks nlog10_ff_impl.cc; fft_vector.py:41): n*log10(max(v, 1e-18)) + k."""
+    return n * np.log10(np.maximum(np.asarray(v, np.float64), 1e-18)) + k
+
+
 def log_power(spec, n=1.0, k=1.0):
     """complex_to_mag_squared -> nlog10_ff(n, L, k): n*log10(max(|X|^2, 1e-18)) + k."""
-    p = spec.real ** 2 + spec.imag ** 2
-    return n * np.log10(np.maximum(p, 1e-18)) + k
+    return nlog10(spec.real ** 2 + spec.imag ** 2, n, k)
 
 
 def fft_vector_flowgraph(x, length, window, nframes=1000, avg=100):

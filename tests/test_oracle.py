@@ -92,6 +92,13 @@ def test_quadrature_demod_matches_gnuradio_qa_case():
         np.testing.assert_allclose(out[1:], 1.0, atol=1e-5)
 
 
+def test_nlog10_matches_gnuradio_qa_case():
+    """gr-blocks/python/blocks/qa_nlog10.py: nlog10_ff(10) of (-10, 0, 10, 100, 1000, 10000, 100000) is
+    (-180, -180, 10, 20, 30, 40, 50) - the 1e-18 clamp that fft_vector.py:41 relies on for empty bins."""
+    out = gb.nlog10([-10, 0, 10, 100, 1000, 10000, 100000], 10.0, 0.0)
+    np.testing.assert_allclose(out, [-180, -180, 10, 20, 30, 40, 50], atol=1e-9)
+
+
 def test_pfb_prototype_reference_shape():
     # rc_frontend/receiver.py:249-254: ~17-19 taps per arm for the 80 dB optfir prototype
     for n in (5, 20, 40):
