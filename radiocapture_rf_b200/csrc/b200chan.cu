@@ -222,7 +222,8 @@ int pfb_launch_tma(rcb_t* h, const PfbParams& p, bool query_only) {
         return RCB_OK;
     }
     if (OB8) {  // layout variants are picked per launch: opt in to the shared-memory size once
-        static bool attr_set = false;
+        static bool attr_dev[64] = {};
+        bool& attr_set = attr_dev[h->device & 63];
         if (!attr_set) {
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;

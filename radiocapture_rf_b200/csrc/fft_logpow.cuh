@@ -404,6 +404,14 @@ inline std::vector<float2> fft_tw_table(int R, int N) {
     return t;
 }
 
+// function attributes are per device: one flag / high-water mark per device ordinal (a receiver may place its sources
+// on several GPUs of one process)
+inline int fft_cur_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d & 63;
+}
+
 #define FCK(call)                              \
     do {                                       \
         if ((call) != cudaSuccess) return -3;  \
@@ -500,7 +508,8 @@ template <int R>
 inline int fft_launch_cols(const FftParams& p, int nfr, cudaStream_t st) {
     using G = FftGeom<R>;
     const size_t smem = G::a_smem(p.L);
-    static size_t attr = 0;  // the opt-in limit must cover the largest L used with this R
+    static size_t attr_dev[64] = {};  // the opt-in limit must cover the largest L used with this R
+    size_t& attr = attr_dev[fft_cur_device()];
     if (smem > attr) {
         FCK(cudaFuncSetAttribute(fft_cols_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
@@ -542,7 +551,8 @@ inline int fft_launch_cols_tma(const FftParams& p, int nfr, cudaStream_t st) {
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return 1;
-    static bool attr = false;
+    static bool attr_dev[64] = {};
+    bool& attr = attr_dev[fft_cur_device()];
     if (!attr) {
         FCK(cudaFuncSetAttribute(fft_cols_tma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem));
         attr = true;
@@ -589,7 +599,8 @@ template <int R>
 inline int fft_launch_rows(const FftParams& p, int nfr, cudaStream_t st) {
     using G = FftGeom<R>;
     const size_t smem = G::b_smem();
-    static size_t attr = 0;
+    static size_t attr_dev[64] = {};
+    size_t& attr = attr_dev[fft_cur_device()];
     if (smem > attr) {
         FCK(cudaFuncSetAttribute(fft_rows_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
