@@ -69,7 +69,11 @@ class channel(object):
         self._chan_id = None
         self._running = False
         if parent is not None:
-            self._bind(parent)
+            try:
+                self._bind(parent)
+            except Exception:   # unknown source / refused rcb_ddc_open: do not leak the bound PUB socket and its port
+                self.sink.close()
+                raise
         self.init_time = time.time()
         self.channel_close_time = 0
 

@@ -20,6 +20,7 @@
 #include "pfb_fm.cuh"
 #include "pfb_fm_tma.cuh"
 #include "pfb_fm_ws.cuh"
+#include "pfb_cl.cuh"
 
 using namespace rcb;
 
@@ -91,7 +92,9 @@ struct rcb_ctx {
         int blocks_per_sm = 0;
         size_t smem = 0;
         bool taps_smem = true;
-        int variant = 0;  // RCB_PFB_VARIANT (tuning experiments)
+        int variant = 0;  // RCB_PFB_VARIANT: tuning experiments, read only by -DRCB_EXPERIMENTS builds (never shipped)
+        float4* d_tw4 = nullptr;  // pfb_cl_kernel twiddles [CS][R/2][16]
+        bool use_cl = false;      // FM only, N in {256, 1024}, <= 16 taps per arm: cluster / register-window kernel
         int oblock_log2 = 0;  // rcb_pfb_set_out_block
         Stage st[kStages];
         size_t chunk_frames = 0;
@@ -112,7 +115,6 @@ struct rcb_ctx {
         DdcGroupDev* d_groups = nullptr;
         DdcGroupDev* h_groups = nullptr;  // pinned
         size_t groups_cap = 0;
-        size_t tile_smem_attr = 0;
     } ddc;
 
     // ---- FFT ----
@@ -178,7 +180,14 @@ int pfb_launch_t(rcb_t* h, const PfbParams& p, bool query_only) {
     auto kern = pfb_fm_kernel<R, MODE, TS, PT, PF>;
     const size_t smem = G::smem_bytes(p.P, TS);
     if (query_only) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // cudaFuncSetAttribute is per function and per DEVICE and a later, smaller value lowers the limit: several handles
+        // (other sources, pfb-mode bin engines) share a device, so the opt-in is tracked per device and only ever raised
+        static size_t attr_max[64] = {};
+        size_t& cur = attr_max[h->device & 63];
+        if (smem > cur) {
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cur = smem;
+        }
         int nb = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, G::THREADS, smem));
         h->pfb.blocks_per_sm = std::max(nb, 1);
@@ -263,6 +272,91 @@ int pfb_launch_ws(rcb_t* h, const PfbParams& p, bool query_only) {
     return RCB_OK;
 }
 
+// cluster / register-window kernel (pfb_cl.cuh).  Returns 1 when the TMA descriptors cannot describe this call
+// (misaligned buffers or strides, time blocks shorter than 16 frames): the caller then runs the round-1 kernels.
+template <int R, int PT>
+int pfb_launch_cl_t(rcb_t* h, const float2* d_x, const float2* d_hist, size_t frames, float* d_fm, size_t ostride) {
+    using G = PfbClGeom<R>;
+    auto& s = h->pfb;
+    constexpr int N = G::N;
+    const int kb = s.oblock_log2;
+    if (kb > 0 && kb < 4) return 1;
+    CUtensorMap tm_x, tm_hist, tm_out;
+    {
+        const uint64_t dims[3] = {(uint64_t)2 * R, (uint64_t)R, (uint64_t)frames};
+        const uint64_t str[2] = {(uint64_t)2 * R * 4, (uint64_t)N * 8};
+        const uint32_t box[3] = {32, (uint32_t)R, 1};
+        if (!tmap_encode_f32(&tm_x, 3, d_x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+        const uint64_t hd[3] = {(uint64_t)2 * R, (uint64_t)R, (uint64_t)s.P};
+        if (!tmap_encode_f32(&tm_hist, 3, d_hist, hd, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+    }
+    PfbClParams p{};
+    if (kb == 0) {
+        const uint64_t dims[3] = {(uint64_t)frames, (uint64_t)R, (uint64_t)R};
+        const uint64_t str[2] = {(uint64_t)ostride * 4, (uint64_t)ostride * 4 * R};
+        const uint32_t box[3] = {16, 16, (uint32_t)R};
+        if (ostride < frames || !tmap_encode_f32(&tm_out, 3, d_fm, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+        p.out_rank = 3;
+    } else {
+        const uint64_t blk = (uint64_t)1 << kb;
+        const uint64_t dims[4] = {blk, (uint64_t)R, (uint64_t)R, ((uint64_t)frames + blk - 1) >> kb};
+        const uint64_t str[3] = {blk * 4, blk * 4 * R, blk * 4 * N};
+        const uint32_t box[4] = {16, 16, (uint32_t)R, 1};
+        if (!tmap_encode_f32(&tm_out, 4, d_fm, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+        p.out_rank = 4;
+    }
+    p.taps_kc = s.d_taps_kc;
+    p.tw4 = s.d_tw4;
+    p.out_fm = d_fm;
+    p.ostride = (long long)ostride;
+    p.oblock_log2 = kb;
+    p.T = (int)frames;
+    p.P = s.P;
+    p.N = N;
+    p.gain = s.gain;
+    p.work_counter = s.d_counter;
+    auto kern = pfb_cl_kernel<R, PT>;
+    static bool attr_dev[64] = {};
+    bool& attr_set = attr_dev[h->device & 63];
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes));
+        attr_set = true;
+    }
+    const int NI = (int)((frames + 15) / 16);
+    const int ncl = std::max(1, std::min(NI, h->sm_count / G::CS));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(ncl * G::CS));
+    cfg.blockDim = dim3(G::THREADS);
+    cfg.dynamicSmemBytes = G::smem_bytes;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = G::CS;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, kern, tm_x, tm_hist, tm_out, p));
+    h->stats.kernel_launches++;
+    return RCB_OK;
+}
+template <int R>
+int pfb_launch_cl_r(rcb_t* h, const float2* d_x, const float2* d_hist, size_t frames, float* d_fm, size_t ostride) {
+    switch (h->pfb.PT) {
+        case 1: return pfb_launch_cl_t<R, 1>(h, d_x, d_hist, frames, d_fm, ostride);
+        case 2: return pfb_launch_cl_t<R, 2>(h, d_x, d_hist, frames, d_fm, ostride);
+        case 4: return pfb_launch_cl_t<R, 4>(h, d_x, d_hist, frames, d_fm, ostride);
+        case 8: return pfb_launch_cl_t<R, 8>(h, d_x, d_hist, frames, d_fm, ostride);
+        case 16: return pfb_launch_cl_t<R, 16>(h, d_x, d_hist, frames, d_fm, ostride);
+    }
+    return 1;
+}
+int pfb_launch_cl(rcb_t* h, const float2* d_x, const float2* d_hist, size_t frames, float* d_fm, size_t ostride) {
+    if (h->pfb.R == 32) return pfb_launch_cl_r<32>(h, d_x, d_hist, frames, d_fm, ostride);
+    if (h->pfb.R == 16) return pfb_launch_cl_r<16>(h, d_x, d_hist, frames, d_fm, ostride);
+    return 1;
+}
+
 // fast kernel dispatch: taps per arm (1, 2, 4, 8, 16) x output mode
 template <int R, int MODE>
 int pfb_launch_tma_pm(rcb_t* h, const PfbParams& p, bool q) {
@@ -332,6 +426,9 @@ void pfb_free(rcb_t* h) {
     s.d_tw_tma = nullptr;
     cudaFree(s.d_taps_kc);
     s.d_taps_kc = nullptr;
+    cudaFree(s.d_tw4);
+    s.d_tw4 = nullptr;
+    s.use_cl = false;
 
     cudaFree(s.d_hist[0]);
     cudaFree(s.d_hist[1]);
@@ -368,10 +465,6 @@ int pfb_run_device(rcb_t* h, const float2* d_x, size_t frames, float2* d_iq, flo
     p.taps = s.d_taps;
     p.twiddle = s.d_tw;
     p.zeros = s.d_zeros;
-    {
-        const char* dbg = getenv("RCB_PFB_DEBUG");
-        p.debug_flags = dbg ? atoi(dbg) : 0;
-    }
     p.out_fm = (s.mode & RCB_OUT_FM) ? d_fm : nullptr;
     p.out_iq = (s.mode & RCB_OUT_IQ) ? d_iq : nullptr;
     p.ostride = (long long)ostride;
@@ -380,7 +473,13 @@ int pfb_run_device(rcb_t* h, const float2* d_x, size_t frames, float2* d_iq, flo
     p.P = s.P;
     p.N = s.N;
     p.gain = s.gain;
-    if (s.R) {
+    int cl_rc = 1;
+    if (s.use_cl) {
+        cl_rc = pfb_launch_cl(h, d_x, s.d_hist[s.hist_cur], frames, d_fm, ostride);
+        if (cl_rc != RCB_OK && cl_rc != 1) return cl_rc;
+    }
+    if (cl_rc == RCB_OK) {
+    } else if (s.R) {
         int rc = pfb_launch_fast(h, p, false);
         if (rc) return rc;
     } else {
@@ -652,10 +751,14 @@ extern "C" int rcb_pfb_config(rcb_t* h, int nchans, const float* taps, int ntaps
     s.mode = out_mask;
     s.gain = fm_gain;
     s.R = (nchans == 64) ? 8 : (nchans == 256) ? 16 : (nchans == 1024) ? 32 : 0;
+#ifdef RCB_EXPERIMENTS
     {
         const char* v = getenv("RCB_PFB_VARIANT");
         s.variant = v ? atoi(v) : 0;
     }
+#else
+    s.variant = 0;
+#endif
     const int N = s.N, P = s.P, R = s.R;
     std::vector<float> hp((size_t)P * N, 0.f);
     for (int i = 0; i < ntaps; ++i) hp[i] = taps[i];
@@ -688,6 +791,29 @@ extern "C" int rcb_pfb_config(rcb_t* h, int nchans, const float* taps, int ntaps
                 for (int c = 0; c < N; ++c) kc[(size_t)k * N + c] = hp[(size_t)(N - 1 - c) + (size_t)k * N];
             CK(cudaMalloc(&s.d_taps_kc, kc.size() * sizeof(float)));
             CK(cudaMemcpy(s.d_taps_kc, kc.data(), kc.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
+        // FM only, N = 256 / 1024: cluster / register-window kernel (RCB_PFB_VARIANT=20 in experiment builds: round-1 kernels)
+        s.use_cl = (s.use_tma && (R == 16 || R == 32) && s.mode == RCB_OUT_FM && s.variant != 20);
+        if (s.use_cl) {
+            if (!s.d_taps_kc) {  // one tap per arm: the [PT][N] column-major table is just the reversed prototype
+                std::vector<float> kc((size_t)N, 0.f);
+                for (int c = 0; c < N; ++c) kc[c] = hp[(size_t)(N - 1 - c)];
+                CK(cudaMalloc(&s.d_taps_kc, kc.size() * sizeof(float)));
+                CK(cudaMemcpy(s.d_taps_kc, kc.data(), kc.size() * sizeof(float), cudaMemcpyHostToDevice));
+            }
+            const int CS = R / 16;
+            std::vector<float4> t4((size_t)CS * (R / 2) * 16);
+            for (int rk = 0; rk < CS; ++rk)
+                for (int c = 0; c < R / 2; ++c)
+                    for (int l = 0; l < 16; ++l) {
+                        const int ll = 16 * rk + l;
+                        const int q0 = ((R - 1 - ll) * (2 * c)) % N, q1 = ((R - 1 - ll) * (2 * c + 1)) % N;
+                        const double a0 = 2.0 * M_PI * (double)q0 / (double)N, a1 = 2.0 * M_PI * (double)q1 / (double)N;
+                        t4[((size_t)rk * (R / 2) + c) * 16 + l] =
+                            make_float4((float)cos(a0), (float)sin(a0), (float)cos(a1), (float)sin(a1));
+                    }
+            CK(cudaMalloc(&s.d_tw4, t4.size() * sizeof(float4)));
+            CK(cudaMemcpy(s.d_tw4, t4.data(), t4.size() * sizeof(float4), cudaMemcpyHostToDevice));
         }
         if (s.use_tma) {
             std::vector<float2> tt((size_t)N);
@@ -1097,12 +1223,19 @@ extern "C" int rcb_ddc_process(rcb_t* h, const void* iq, size_t nsamples, int in
                     const int opw = lone ? 16 : 4;
                     while (oq > 2 && (size_t)((opw * oq - 1) * decim + ntaps) * sizeof(float2) > 160 * 1024) oq >>= 1;
                     const size_t smem = (size_t)((opw * oq - 1) * decim + ntaps) * sizeof(float2);
-                    if (smem > d.tile_smem_attr) {
-                        CK(cudaFuncSetAttribute(ddc_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                        CK(cudaFuncSetAttribute(ddc_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                        CK(cudaFuncSetAttribute(ddc_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                        CK(cudaFuncSetAttribute(ddc_tile_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                        d.tile_smem_attr = smem;
+                    {
+                        // per function and per DEVICE (handles share devices): opt in once to the 160 KB cap the tile
+                        // sizes above are clamped to - a per-handle "largest so far" would be lowered by another handle
+                        static bool tile_attr_dev[64] = {};
+                        bool& done = tile_attr_dev[h->device & 63];
+                        if (!done) {
+                            const int cap = 160 * 1024 + 1024;
+                            CK(cudaFuncSetAttribute(ddc_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                            CK(cudaFuncSetAttribute(ddc_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                            CK(cudaFuncSetAttribute(ddc_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                            CK(cudaFuncSetAttribute(ddc_tile_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                            done = true;
+                        }
                     }
                     dim3 grid((unsigned)((nout + opw * oq - 1) / (opw * oq)), (unsigned)ng);
                     if (lone)

@@ -22,7 +22,7 @@
 
 #include <vector>
 
-#include <cuda.h>  // CUtensorMap (the encoder is fetched with cudaGetDriverEntryPoint: no libcuda link dependency)
+#include "tma_utils.cuh"
 
 #include "common.cuh"
 #include "fft_inreg.cuh"
@@ -519,28 +519,11 @@ inline int fft_launch_cols(const FftParams& p, int nfr, cudaStream_t st) {
     FCK(cudaGetLastError());
     return 0;
 }
-typedef CUresult (*rcb_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-inline rcb_tmap_encode_fn fft_tmap_encoder() {
-    static rcb_tmap_encode_fn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<rcb_tmap_encode_fn>(ptr);
-    }
-    return fn;
-}
-
 // TMA column pass over the nfr frames at p.x; returns 1 when it cannot run (no encoder / misaligned input)
 template <int R>
 inline int fft_launch_cols_tma(const FftParams& p, int nfr, cudaStream_t st) {
     using G = FftColsGeom<R>;
-    rcb_tmap_encode_fn enc = fft_tmap_encoder();
+    rcb_tmap_encode_fn enc = tmap_encoder();
     if (!enc || (reinterpret_cast<uintptr_t>(p.x) & 15)) return 1;
     CUtensorMap tm;
     const cuuint64_t gdim[2] = {(cuuint64_t)p.L2 * 2, (cuuint64_t)nfr * (cuuint64_t)p.L1};

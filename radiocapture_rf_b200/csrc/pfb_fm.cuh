@@ -41,8 +41,6 @@ struct PfbParams {
                             //   h[R*(R-1-jj) + (R-1-ll) + k*N];  generic path: taps[k*N + i] = h[i + k*N]
     const float* taps_kc;   // [P][N]: taps_kc[k*N + c] = h[(N-1-c) + k*N] (tap of column c; pfb_fm_tma_kernel, P > 1)
     const float2* zeros;    // N complex zeros (rows outside the stream)
-    int debug_flags;        // RCB_PFB_DEBUG (measurement experiments only): 1 = suppress FM stores, 8 = no evict_first on
-                            //   multi-tap stores, 32 = no consumer-side L2 prefetch (pfb_fm_ws_kernel)
     int* work_counter;      // zeroed before each launch: dynamic tail-chunk counter (pfb_fm_tma_kernel)
     const float2* twiddle;  // fast: [R][R+2]: tw[ll*(R+2) + m1] = W_N^{+(R-1-ll) m1};  generic: [N] W_N^{+q}
     float* out_fm;          // [N][ostride] floats (or null)

@@ -110,7 +110,7 @@ __device__ __forceinline__ void pfb_demod_from_y(const PfbParams& p, const float
                                     }
                                     st_global_v8(reinterpret_cast<float*>(dst + 4 * hh), o);
                                 }
-                            } else if (!(p.debug_flags & 1)) {
+                            } else {
 #pragma unroll
                                 for (int j = 0; j < 8; ++j)
                                     if (t0 + j < p.T) dst[j] = y[j + 1][c];
@@ -136,7 +136,7 @@ __device__ __forceinline__ void pfb_demod_from_y(const PfbParams& p, const float
                             float* dst = dst0 + (q0 + c) * rowstride;
                             if (full) {
                                 st_global_v8(dst, o[c]);
-                            } else if (!(p.debug_flags & 1)) {
+                            } else {
 #pragma unroll
                                 for (int j = 0; j < 8; ++j)
                                     if (t0 + j < p.T) dst[j] = o[c][j];
@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
             const long long t0 = (long long)it * FPI + 8 * g;
             int s = base_slot + 8 * g;
             s = (s >= NSLOT) ? s - NSLOT : s;
-            const bool full = (t0 + 8 <= p.T) && !(p.debug_flags & 1);  // RCB_PFB_DEBUG=1: measurement only
+            const bool full = (t0 + 8 <= p.T);
             // (m0, t0) -> element index; consecutive channels are `rowstride` apart in both layouts
             float* dst0 = (MODE & PFB_OUT_FM) ? p.out_fm + pfb_out_index(p, m0, t0) : nullptr;
             if constexpr (MODE == PFB_LOGPOW) {  // t = f * L1 + k1 (ostride = L1), bin m = k2 -> vals[f][fftshift(k2)][k1]
@@ -509,9 +509,9 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
             for (int q = 0; q < CPT; ++q) {
                 float* dst = dst0 + q * MSTR * rowstride;
                 if (full) {
-                    if (PT > 1 && !(p.debug_flags & 8)) st_global_v8_hint(dst, o[q], pol_stream);  // keeps the input rows in L2 (+6 %)
+                    if (PT > 1) st_global_v8_hint(dst, o[q], pol_stream);  // keeps the input rows in L2 (+6 %)
                     else st_global_v8(dst, o[q]);
-                } else if (!(p.debug_flags & 1) || o[q][0] == 123456.789f) {
+                } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         if (t0 + j < p.T) dst[j] = o[q][j];

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__((8 + PW) * 32, 1) pfb_fm_ws_kernel(const PfbPa
         for (int it = it0 - 1; it < it1; ++it, ++k) {
             const int s = k & 1;
             float2* wf = work_all + (size_t)s * CW * G::WORK + warp * G::WORK + fr * FSW;
-            if (PT == 16 && !(p.debug_flags & 32)) {  // (measured: +7 % at 16 taps per arm, -4 % at 8)
+            if (PT == 16) {  // (measured: +7 % at 16 taps per arm, -4 % at 8)
                 // the consumers have slack: pull the new rows the producers will need two iterations from now into L2,
                 // so the FIR loads (the critical path) pay an L2 instead of an HBM latency
                 const long long nf = (long long)(it + 2) * FPI;

@@ -266,6 +266,22 @@ class DdcBank(object):
         p = d_in.ptr if isinstance(d_in, DeviceBuffer) else d_in
         check(self.e.lib.rcb_ddc_process(self.e.h, p, int(nsamples), MEM_DEVICE), "rcb_ddc_process", self.e.h)
 
+    def nout(self, chan, which=OUT_IQ):
+        """Items the last process() call produced for this channel."""
+        n = C.c_size_t(0)
+        st = self.e.lib.rcb_ddc_pull(self.e.h, int(chan), int(which), None, 0, MEM_HOST, C.byref(n))
+        if st not in (0, _lib.RCB_ERANGE):
+            check(st, "rcb_ddc_pull", self.e.h)
+        return n.value
+
+    def pull_device(self, chan, d_dst, cap_items, which=OUT_IQ):
+        """Copy the channel's last outputs into device memory (chaining stages on the GPU).  Returns the item count."""
+        n = C.c_size_t(0)
+        p = d_dst.ptr if isinstance(d_dst, DeviceBuffer) else d_dst
+        check(self.e.lib.rcb_ddc_pull(self.e.h, int(chan), int(which), p, int(cap_items), MEM_DEVICE, C.byref(n)),
+              "rcb_ddc_pull", self.e.h)
+        return n.value
+
     def pull(self, chan, which=OUT_IQ):
         n = C.c_size_t(0)
         # first ask for the size (dst NULL is only legal when there is nothing to fetch)

@@ -52,8 +52,20 @@ def _sinc_lowpass(gain, fs, fc, ntaps, w):
     return (taps.astype(np.float64) * (gain / fmax)).astype(np.float32)
 
 
+def max_attenuation(win_type, beta=6.76):
+    """gr::fft::window::max_attenuation: fixed per window, beta / 0.1102 + 8.7 for Kaiser."""
+    if win_type == WIN_KAISER:
+        return beta / 0.1102 + 8.7
+    return _MAX_ATTEN[win_type]
+
+
+def compute_ntaps(sampling_freq, transition_width, win_type=WIN_HAMMING, beta=6.76):
+    """firdes::compute_ntaps: int(A fs / (22 tw)), made odd."""
+    return _odd(int(max_attenuation(win_type, beta) * sampling_freq / (22.0 * transition_width)))
+
+
 def low_pass(gain, sampling_freq, cutoff_freq, transition_width, win_type=WIN_HAMMING, beta=6.76):
-    ntaps = _odd(int(_MAX_ATTEN[win_type] * sampling_freq / (22.0 * transition_width)))
+    ntaps = compute_ntaps(sampling_freq, transition_width, win_type, beta)
     return _sinc_lowpass(gain, sampling_freq, cutoff_freq, ntaps, window(win_type, ntaps, beta))
 
 

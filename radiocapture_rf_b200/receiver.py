@@ -53,6 +53,7 @@ class SourceStream(object):
         self.samples_in = 0
         self._thread = None
         self._stop = threading.Event()
+        self.post_push = []         # callables run at the end of push() under the lock (split2 feeds its halves here)
         channel_mod.register_source(self.address, self)
 
     # ---- channel management (called by channel objects) ------------------------------------------
@@ -87,6 +88,8 @@ class SourceStream(object):
             self.samples_in += len(iq)
             for cid, ch in list(self.channels.items()):
                 ch.deliver(self.bank.pull(cid, OUT_IQ))
+            for hook in self.post_push:
+                hook()
 
     def _reader(self):
         kind = self.cfg.get("type")
@@ -152,6 +155,8 @@ class SourceStream(object):
         if self._thread is not None:
             self._thread.join(timeout=2.0)
         channel_mod.unregister_source(self.address)
+        for _, child in getattr(self, "split_children", []):
+            child.stop()
         with self.lock:
             self.engine.close()
 
@@ -194,6 +199,9 @@ class BinStream(object):
         self.bank.process_device(d_ptr, nsamples)
         for cid, ch in list(self.channels.items()):
             ch.deliver(self.bank.pull(cid, OUT_IQ))
+        # the parent reuses (or frees) the PFB output row after this call: nothing of this bin may still be reading it
+        # (rcb_ddc_pull returns without a sync when a block produced no output)
+        self.engine.sync()
 
     def close(self):
         self.engine.close()
@@ -213,6 +221,8 @@ class PfbSourceStream(SourceStream):
             raise NotImplementedError("pfb mode needs the GPU engine")
         SourceStream.__init__(self, source_id, cfg, device=device, block_samples=block_samples)
         self.device = device
+        if self.samp_rate % self.target_size and not cfg.get("pfb_allow_odd_rate", False):
+            raise Exception("samp_rate not round enough")   # rc_frontend/receiver.py:245-246
         self.num_channels = int(self.samp_rate // self.target_size)
         if self.num_channels < 1:
             raise ValueError("samp_rate %s is below one %s Hz pfb bin" % (self.samp_rate, self.target_size))
@@ -260,9 +270,14 @@ class PfbSourceStream(SourceStream):
                     bs.push_device(self._d_iq.ptr + m * nfr * 8, nfr)
 
     def stop(self):
-        for bs in list(self.bins.values()):
-            bs.close()
-        self.bins = {}
+        # reader first (it pushes into the bins), then the bin engines under the lock, then the parent engine
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2.0)
+        with self.lock:
+            for bs in list(self.bins.values()):
+                bs.close()
+            self.bins = {}
         SourceStream.stop(self)
 
 
@@ -273,7 +288,7 @@ def _default_generator(src, n0, n):
 
 class receiver(object):
     def __init__(self, index=None, config=None, sink="zmq", devices=None, bind="tcp://0.0.0.0:0",
-                 engine_factory=None, publisher=None, start=True, use_zmq=True):
+                 engine_factory=None, publisher=None, start=True, use_zmq=True, redis_client=None):
         self.log = logging.getLogger("frontend" if index is None else "frontend-%s" % (index,))
         self.index = index
         self.sink_kind = sink
@@ -301,10 +316,7 @@ class receiver(object):
             for i in list(self.realsources):
                 if i != int(index):
                     del self.realsources[i]
-        if getattr(config, "receiver_split2", False):
-            # rc_frontend/receiver.py:205-237 (legacy; raises KeyError in today's xlat mode, Appendix C.2)
-            raise NotImplementedError("receiver_split2 is legacy; open two decim-2 DdcBank channels instead "
-                                      "(tests/test_gpu_ddc.py::test_split2_half_band_pair)")
+        self.receiver_split2 = bool(getattr(config, "receiver_split2", False))
         ndev = len(devices) if devices else 1
         self.sources = {}
         numsources = 0
@@ -317,8 +329,15 @@ class receiver(object):
                 stream = SourceStream(source, cfg, device=dev, engine_factory=engine_factory)
             cfg["block"] = stream
             cfg["source_id"] = source
-            self.sources[numsources] = cfg
             self.realsources[source]["block"] = stream
+            if self.receiver_split2:
+                # rc_frontend/receiver.py:205-237: two half-band DDCs (+-fs/4, decimation 2) become two fs/2 sources
+                from .split2 import split_source
+                for half in split_source(stream, cfg, device=dev, engine_factory=engine_factory):
+                    self.sources[numsources] = half
+                    numsources += 1
+                continue
+            self.sources[numsources] = cfg
             numsources += 1
         self.channels = {}
         self.clients = {}
@@ -327,6 +346,14 @@ class receiver(object):
         self.start_time = time.time()
         self.instance_uuid = "%s" % uuid.uuid4()
         self.publisher = publisher
+        self.redis_channel_publisher = None
+        if redis_client is not None or publisher == "redis":
+            # rc_frontend/receiver.py:268: SADD channelizers / SET <uuid> every second from a background thread
+            from .redis_channel_publisher import redis_channel_publisher
+            self.publisher = None
+            self.redis_channel_publisher = redis_channel_publisher(
+                sources=self.sources, channels=self.channels, zmq_socket=self.zmq_socket, index=index,
+                client=redis_client, instance_uuid=self.instance_uuid)
         self._serving = False
         if start:
             self.start()
@@ -338,6 +365,8 @@ class receiver(object):
 
     def stop(self):
         self._serving = False
+        if self.redis_channel_publisher is not None:
+            self.redis_channel_publisher.stop()
         with self.access_lock:
             for c in list(self.channels):
                 self.channels[c].destroy()
@@ -402,7 +431,7 @@ class receiver(object):
                     try:
                         block = channel(stream, port, channel_rate, source_samp_rate, offset, sink=self.sink_kind)
                         break
-                    except RuntimeError:
+                    except RuntimeError:   # port in use, unknown source, or a refused rcb_ddc_open (B200ChanError)
                         self.log.error("Failed to build channel on port: %s attempt: %s" % (port, x))
                         block = None
                 if block is None:

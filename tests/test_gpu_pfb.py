@@ -81,6 +81,54 @@ def test_pfb_fm_only_multi_tap_split_invariance(engine, n, tpa):
     assert np.array_equal(a_fm, b_fm)
 
 
+@pytest.mark.parametrize("n,tpa,frames", [(1024, 16, 1), (1024, 16, 15), (1024, 16, 16), (1024, 16, 17), (1024, 1, 33),
+                                          (1024, 0.25, 48), (256, 16, 1), (256, 16, 31), (256, 1, 32), (256, 8, 49),
+                                          (1024, 16, 2500), (256, 16, 5000)])
+def test_pfb_cluster_kernel_iteration_edges(engine, n, tpa, frames):
+    """pfb_cl_kernel works in 16-frame iterations with one warm-up iteration per CTA run, TMA-fed rows (zero fill
+    outside the stream) and TMA tile stores: block lengths around the iteration size, single frames, and blocks long
+    enough that every cluster owns a run (2500 frames = 157 iterations over 74 clusters)."""
+    taps = fd.pfb_prototype(n, tpa)
+    _check(engine, n, taps, frames, seed=2000 + n + frames, mode=OUT_FM)
+
+
+@pytest.mark.parametrize("n,tpa,block", [(1024, 16, 16), (1024, 1, 32), (256, 16, 16), (256, 4, 1024)])
+def test_pfb_cluster_kernel_blocked_layouts(engine, n, tpa, block):
+    """Time-blocked output through the 4-D TMA store (block >= 16 frames), ragged last block, vs the plain layout."""
+    taps = fd.pfb_prototype(n, tpa)
+    frames = 1000 + 7
+    x, _ = synth.pfb_stream(n * frames, 1.0e6 * n / 4.0, n, 23)
+    ch = PfbChannelizer(engine, n, taps, OUT_FM, 5.0)
+    _, fm_ref = ch.process(x)
+    ch.reset()
+    ch.set_out_block(block)
+    nb = -(-frames // block)
+    d_in = engine.to_device(x)
+    d_fm = engine.dev_alloc(nb * n * block * 4)
+    assert ch.process_device(d_in, len(x), None, d_fm, 0) == frames
+    engine.sync()
+    fm = PfbChannelizer.unblock(engine.to_host(d_fm, (nb * n * block,), np.float32), n, frames, block)
+    assert np.array_equal(fm, fm_ref)
+
+
+def test_pfb_cluster_kernel_unaligned_output_falls_back(engine):
+    """An output row stride that is not a multiple of 16 bytes cannot be described by a TMA tensor map: the call is
+    served by the round-1 kernel and must give the same samples."""
+    n, frames = 1024, 100
+    taps = fd.pfb_prototype(n, 4)
+    x, _ = synth.pfb_stream(n * frames, 1.0e6 * n / 4.0, n, 29)
+    ch = PfbChannelizer(engine, n, taps, OUT_FM, 5.0)
+    _, fm_ref = ch.process(x)
+    ch.reset()
+    d_in = engine.to_device(x)
+    stride = frames + 1
+    d_fm = engine.dev_alloc(n * stride * 4)
+    assert ch.process_device(d_in, len(x), None, d_fm, stride) == frames
+    engine.sync()
+    fm = engine.to_host(d_fm, (n, stride), np.float32)[:, :frames]
+    np.testing.assert_allclose(fm, fm_ref, rtol=0, atol=2e-5 * 5.0)
+
+
 def test_pfb_cfg3_literal_256_taps_1024_channels(engine):
     """BASELINE config 3, literal reading: 256-tap prototype, 1024 channels -> 1 tap/arm, 768 zero arms."""
     taps = fd.pfb_prototype(4, 64)  # any 256-tap low-pass
