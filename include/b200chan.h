@@ -131,6 +131,43 @@ enum { RCB_FMT_U8 = 1, RCB_FMT_S8 = 2, RCB_FMT_S16 = 3 };
 int rcb_convert_iq(rcb_t* h, const void* src, int fmt, float offset, float scale, size_t nsamples, int src_mem,
                    void* dst, int dst_mem);
 
+/* ---- K6: post-demod data-parallel stages, batched over channel rows -------------
+ * Everything the backend demods run between the frontend's narrowband complex64 stream and their first
+ * sample-serial loop (fsk4_demod_ff, clock recovery, vocoders: out of scope):
+ *   RCB_POST_P25_C4FM  p25_control_demod.py:106-133, logging_receiver.py:229-245
+ *       freq_xlating_fir_filter_ccc(1, taps0, 0, rate)  ->  analog.quadrature_demod_cf(gain)  ->
+ *       fir_filter_fff(1, taps1)   [taps1 = (1/sps,)*sps symbol filter]         -> out (float, n per row)
+ *       and the AFC probe  moving_average_ff(probe_len, 1, ..) -> multiply_const(probe_scale) -> probe_signal_f
+ *       on the demod output (p25_control_demod.py:123-127): `probe[r]` = its value after this block.
+ *   RCB_POST_ANALOG_FM  logging_receiver.py:210-222
+ *       analog.pwr_squelch_cc(squelch_db, squelch_alpha, 0, squelch_gate) -> analog.fm_demod_cf = quadrature_demod_cf
+ *       (gain) -> fm_deemph = iir_filter_ffd([deemph_b0, deemph_b1], [1, deemph_a1]) -> fir_filter_fff(1, taps0)
+ *       [audio low-pass] -> fir_filter_fff(1, taps1) [300 Hz high-pass] -> rational_resampler_fff(interp, decim, taps2)
+ *       -> out (float, nout[r] per row: depends on the resampling ratio and on what the squelch gated away).
+ * One chain = `rows` channels with identical parameters, each with its own streaming state (filter histories,
+ * IIR / squelch state, resampler phase), so any split of the streams into calls gives the same samples.
+ * Input: rows of n complex64 at iq + row_map[r] * in_stride (row_map NULL = identity; host array) - e.g. rows of a
+ * device-resident rcb_pfb_process IQ output, so channelised samples never leave the GPU before the symbol filter.
+ * Output: row r at out + r * out_stride (floats), nout[r] items (host int array of `rows`). */
+enum { RCB_POST_P25_C4FM = 1, RCB_POST_ANALOG_FM = 2 };
+typedef struct rcb_post_cfg {
+    int kind;
+    int rows;
+    float gain;                        /* quadrature demod gain */
+    const float* taps0; int ntaps0;    /* P25: channel prefilter       ANALOG: audio low-pass  */
+    const float* taps1; int ntaps1;    /* P25: symbol filter           ANALOG: high-pass       */
+    const float* taps2; int ntaps2;    /*                              ANALOG: resampler prototype */
+    int interp, decim;                 /*                              ANALOG: resampler ratio (reduced) */
+    double squelch_db, squelch_alpha;  /*                              ANALOG */
+    int squelch_gate;
+    double deemph_b0, deemph_b1, deemph_a1;
+    int probe_len; float probe_scale;  /* P25: AFC probe (0 = none) */
+} rcb_post_cfg;
+int rcb_post_open(rcb_t* h, const rcb_post_cfg* cfg, int* chain_id);
+int rcb_post_process(rcb_t* h, int chain_id, const void* iq, size_t n, size_t in_stride, const int* row_map,
+                     int in_mem, void* out, size_t out_stride, int out_mem, int* nout, float* probe);
+int rcb_post_close(rcb_t* h, int chain_id);
+
 /* ---- K3: streaming windowed FFT + log-power accumulation ---------------------------------------
  * Replaces stream_to_vector -> fft.fft_vcc(L, True, window, True) -> complex_to_mag_squared ->
  * nlog10_ff(1, L, 1) -> moving_average_ff(avg, 1, ...)             fft_vector.py:37-60.

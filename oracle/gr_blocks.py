@@ -324,6 +324,93 @@ def pfb_bin_for_offset(offset_hz, bin_hz, num_channels):
     return int(chan), pfb_offset
 
 
+# ---------------------------------------------------------------------------------------------
+# post-demod data-parallel stages: p25_control_demod.py:106-133, logging_receiver.py:210-222
+# ---------------------------------------------------------------------------------------------
+def fir_filter_fff(x, taps, decim=1, history=None):
+    """gr-filter fir_filter_fff(decim, taps): y[i] = sum_k h[k] x[i D - k], zero history (or the ntaps-1 samples given).
+    Symbol filter (1/5,)*5 (p25_control_demod.py:130-133), audio LPF / 300 Hz HPF (logging_receiver.py:214-215)."""
+    h = np.asarray(taps, dtype=np.float64)
+    nt = len(h)
+    x = np.asarray(x, dtype=np.float64)
+    hist = np.zeros(nt - 1) if history is None else np.asarray(history, dtype=np.float64)
+    assert len(hist) == nt - 1
+    xx = np.concatenate([hist, x])
+    full = np.convolve(xx, h)[nt - 1:nt - 1 + len(x)]
+    return full[::decim]
+
+
+def rational_resampler_fff(x, interp, decim, taps):
+    """gr-filter rational_resampler_base: zero-stuff by I, FIR, keep every D-th: y[m] = sum_n x[n] h[m D - n I]
+    (phase ctr starts at 0, filter history zero).  Outputs produced while input remains: m D / I < len(x)."""
+    h = np.asarray(taps, dtype=np.float64)
+    x = np.asarray(x, dtype=np.float64)
+    nout = (len(x) * interp + decim - 1) // decim
+    up = np.zeros(len(x) * interp)
+    up[::interp] = x
+    full = np.convolve(up, h)
+    return full[np.arange(nout) * decim]
+
+
+def iir_filter_ffd(x, btaps, ataps, state=None):
+    """gr-filter iir_filter_ffd(fftaps, fbtaps, oldstyle=False), first order: y[n] = b0 x[n] + b1 x[n-1] - a1 y[n-1]
+    in double precision, float output (the fm_deemph block).  state = (x[-1], y[-1])."""
+    b0, b1 = float(btaps[0]), float(btaps[1])
+    a1 = float(ataps[1])
+    xp, yp = (0.0, 0.0) if state is None else state
+    x = np.asarray(x, dtype=np.float64)
+    y = np.empty(len(x))
+    for n in range(len(x)):
+        yp = b0 * x[n] + b1 * xp - a1 * yp
+        xp = x[n]
+        y[n] = yp
+    return y
+
+
+def pwr_squelch_cc(x, db, alpha=0.0001, ramp=0, gate=False):
+    """gr-analog pwr_squelch_cc (squelch_base_cc, ramp 0): d_pwr = single_pole_iir(alpha)(|x|^2) updated per sample,
+    muted while d_pwr < 10^(db/10); unmuted samples pass, muted ones are dropped (gate) or zeroed.
+    logging_receiver.py:211: pwr_squelch_cc(-100, 0.01, 0, True).  Returns (output, keep_mask)."""
+    assert ramp == 0
+    thr = 10.0 ** (db / 10.0)
+    x = np.asarray(x, dtype=np.complex128)
+    pw = x.real * x.real + x.imag * x.imag
+    p = 0.0
+    keep = np.zeros(len(x), dtype=bool)
+    for n in range(len(x)):
+        p = alpha * pw[n] + (1.0 - alpha) * p
+        keep[n] = not (p < thr)
+    if gate:
+        return x[keep], keep
+    return np.where(keep, x, 0.0), keep
+
+
+def p25_c4fm_front(x, prefilter_taps, gain, sps=5):
+    """p25_control_demod.py:106-133 up to the symbol filter: 1x prefilter (freq_xlating, no shift) -> quadrature demod
+    -> boxcar (1/sps,)*sps.  Returns (prefiltered, fm, symbol_filtered)."""
+    z = freq_xlating_fir(x, prefilter_taps, 1, 0.0, 1.0)
+    fm = quadrature_demod(z, gain)
+    sym = fir_filter_fff(fm, np.full(sps, 1.0 / sps))
+    return z, fm, sym
+
+
+def analog_fm_chain(x, rate, squelch_db=-100.0, squelch_alpha=0.01, deviation=15000.0, gain=8.0, tau=75e-6,
+                    audio_taps=None, hp_taps=None, resamp=None):
+    """logging_receiver.py:210-222 `analog`: pwr_squelch_cc(gate) -> fm_demod_cf (quad demod k = rate/(2 pi dev),
+    fm_deemph(tau), audio LPF) -> 300 Hz high pass -> rational_resampler_fff(8000, rate).  Taps are explicit inputs
+    (audio_taps, hp_taps, resamp = (I, D, taps)) so design differences cannot contaminate kernel parity."""
+    from . import gr_firdes as fd
+    y, keep = pwr_squelch_cc(x, squelch_db, squelch_alpha, 0, True)
+    fm = quadrature_demod(y, rate / (2.0 * math.pi * deviation))
+    b, a = fd.fm_deemph_taps(rate, tau)
+    de = iir_filter_ffd(fm, b, a)
+    lp = fir_filter_fff(de, audio_taps)
+    hp = fir_filter_fff(lp, hp_taps)
+    i, d, rt = resamp
+    out = rational_resampler_fff(hp, i, d, rt)
+    return dict(keep=keep, fm=fm, deemph=de, lpf=lp, hpf=hp, audio=out)
+
+
 def rel_l2(a, b):
     """||a-b||2 / ||b||2 (the parity metric of SURVEY 8(d))."""
     a = np.asarray(a)

@@ -71,9 +71,9 @@ def blackmanharris(ntaps):
     return window(WIN_BLACKMAN_HARRIS, ntaps)
 
 
-def compute_ntaps(sampling_freq, transition_width, win_type):
-    """firdes::compute_ntaps(): int(a*fs/(22*tw)), made odd."""
-    a = _MAX_ATTEN[win_type]
+def compute_ntaps(sampling_freq, transition_width, win_type, beta=6.76):
+    """firdes::compute_ntaps(): int(a*fs/(22*tw)), made odd; a = window::max_attenuation (Kaiser: beta/0.1102 + 8.7)."""
+    a = (beta / 0.1102 + 8.7) if win_type == WIN_KAISER else _MAX_ATTEN[win_type]
     ntaps = int(a * sampling_freq / (22.0 * transition_width))
     if (ntaps & 1) == 0:
         ntaps += 1
@@ -107,7 +107,7 @@ def _windowed_sinc_lowpass(gain, sampling_freq, cutoff_freq, ntaps, w):
 
 def low_pass(gain, sampling_freq, cutoff_freq, transition_width, win_type=WIN_HAMMING, beta=6.76):
     """firdes::low_pass()."""
-    ntaps = compute_ntaps(sampling_freq, transition_width, win_type)
+    ntaps = compute_ntaps(sampling_freq, transition_width, win_type, beta)
     return _windowed_sinc_lowpass(gain, sampling_freq, cutoff_freq, ntaps, window(win_type, ntaps, beta))
 
 
@@ -120,7 +120,7 @@ def low_pass_2(gain, sampling_freq, cutoff_freq, transition_width, attenuation_d
 
 def high_pass(gain, sampling_freq, cutoff_freq, transition_width, win_type=WIN_HAMMING, beta=6.76):
     """firdes::high_pass() (logging_receiver.py:215, 300 Hz audio HPF)."""
-    ntaps = compute_ntaps(sampling_freq, transition_width, win_type)
+    ntaps = compute_ntaps(sampling_freq, transition_width, win_type, beta)
     w = window(win_type, ntaps, beta)
     m = (ntaps - 1) // 2
     fwt0 = 2.0 * math.pi * cutoff_freq / sampling_freq
@@ -229,3 +229,44 @@ def pfb_prototype(nchans, taps_per_arm=None, atten_db=80.0):
     h = h * _bh(ntaps, sym=True)
     h = h / h.sum()
     return h.astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# post-demod chain designs
+# ---------------------------------------------------------------------------------------------
+def fm_deemph_taps(fs, tau=75e-6):
+    """gr-analog/python/analog/fm_emph.py fm_deemph (3.8): bilinear transform of H(s) = w_ca / (s + w_ca) with the
+    corner prewarped; returns (btaps, ataps) of iir_filter_ffd(btaps, ataps, oldstyle=False):
+    y[n] = b0 x[n] + b1 x[n-1] - a1 y[n-1]   (logging_receiver.py:214 via fm_demod_cf(tau=75e-6))."""
+    w_c = 1.0 / tau
+    w_ca = 2.0 * fs * math.tan(w_c / (2.0 * fs))
+    k = -w_ca / (2.0 * fs)
+    z1 = -1.0
+    p1 = (1.0 + k) / (1.0 - k)
+    b0 = -k / (1.0 - k)
+    return [b0 * 1.0, b0 * -z1], [1.0, -p1]
+
+
+def rational_resampler_taps(interpolation, decimation, fractional_bw=0.4):
+    """gr-filter/python/filter/rational_resampler.py design_filter (3.8), after the gcd reduction the block applies
+    when no taps are given (logging_receiver.py:216-221: 8000 / input_rate)."""
+    g = math.gcd(int(interpolation), int(decimation))
+    interpolation, decimation = int(interpolation) // g, int(decimation) // g
+    if fractional_bw >= 0.5 or fractional_bw <= 0:
+        raise ValueError("Invalid fractional_bandwidth, must be in (0, 0.5)")
+    beta = 7.0
+    halfband = 0.5
+    rate = float(interpolation) / float(decimation)
+    if rate >= 1.0:
+        trans_width = halfband - fractional_bw
+        mid_transition_band = halfband - trans_width / 2.0
+    else:
+        trans_width = rate * (halfband - fractional_bw)
+        mid_transition_band = rate * halfband - trans_width / 2.0
+    taps = low_pass(interpolation, interpolation, mid_transition_band, trans_width, WIN_KAISER, beta)
+    return interpolation, decimation, taps
+
+
+def fm_demod_audio_taps(channel_rate, audio_pass, audio_stop, gain):
+    """gr-analog fm_demod_cf: optfir.low_pass(gain, channel_rate, audio_pass, audio_stop, 0.1, 60)."""
+    return optfir_low_pass(gain, channel_rate, audio_pass, audio_stop, 0.1, 60)

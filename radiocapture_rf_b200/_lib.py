@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200chan.so")
+# RCB_LIBRARY points at an alternative build of the same C ABI (e.g. an -DRCB_EXPERIMENTS tuning build)
+LIB_PATH = os.environ.get("RCB_LIBRARY") or os.path.join(_HERE, "libb200chan.so")
 
 RCB_OK = 0
 RCB_EINVAL = -1
@@ -34,6 +35,21 @@ COPY_D2D = 3
 class rcb_stats_t(C.Structure):
     _fields_ = [("samples_in", C.c_uint64), ("channel_samples", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
+POST_P25_C4FM = 1
+POST_ANALOG_FM = 2
+
+
+class rcb_post_cfg(C.Structure):
+    _fields_ = [("kind", C.c_int), ("rows", C.c_int), ("gain", C.c_float),
+                ("taps0", C.c_void_p), ("ntaps0", C.c_int),
+                ("taps1", C.c_void_p), ("ntaps1", C.c_int),
+                ("taps2", C.c_void_p), ("ntaps2", C.c_int),
+                ("interp", C.c_int), ("decim", C.c_int),
+                ("squelch_db", C.c_double), ("squelch_alpha", C.c_double), ("squelch_gate", C.c_int),
+                ("deemph_b0", C.c_double), ("deemph_b1", C.c_double), ("deemph_a1", C.c_double),
+                ("probe_len", C.c_int), ("probe_scale", C.c_float)]
 
 
 class B200ChanError(RuntimeError):
@@ -81,6 +97,9 @@ _PROTOTYPES = {
     "rcb_quad_demod": (C.c_int, [_vp, _vp, _sz, _sz, _sz, C.c_float, _vp, _vp, _sz, C.c_int]),
     "rcb_probe_mean": (C.c_int, [_vp, _vp, _sz, _sz, _sz, _sz, C.c_float, _vp, C.c_int]),
     "rcb_convert_iq": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_float, _sz, C.c_int, _vp, C.c_int]),
+    "rcb_post_open": (C.c_int, [_vp, C.POINTER(rcb_post_cfg), C.POINTER(C.c_int)]),
+    "rcb_post_process": (C.c_int, [_vp, C.c_int, _vp, _sz, _sz, _vp, C.c_int, _vp, _sz, C.c_int, _vp, _vp]),
+    "rcb_post_close": (C.c_int, [_vp, C.c_int]),
     "rcb_fft_config": (C.c_int, [_vp, C.c_int, _vp, C.c_int]),
     "rcb_fft_reset": (C.c_int, [_vp]),
     "rcb_fft_process": (C.c_int, [_vp, _vp, _sz, C.c_int, _vp, _sz, C.c_int, C.POINTER(_sz)]),

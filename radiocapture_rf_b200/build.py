@@ -1,26 +1,48 @@
-"""In-tree build of libb200chan.so for sm_100a (nvcc cross-compiles without a GPU)."""
+"""In-tree build of libb200chan.so for sm_100a (nvcc cross-compiles without a GPU).
+
+Every csrc/*.cu is one translation unit; they are compiled in parallel and linked into the one shared library the
+C ABI (include/b200chan.h) lives in."""
 import os
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(_HERE, "csrc", "b200chan.cu")
+CSRC = os.path.join(_HERE, "csrc")
+OBJ_DIR = os.path.join(_HERE, "csrc", "_obj")
 OUT = os.path.join(_HERE, "libb200chan.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
-              "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
+
+
+def _sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
 def _newest_src():
     t = 0.0
-    for root in (os.path.join(_HERE, "csrc"), os.path.join(_HERE, "..", "include")):
+    for root in (CSRC, os.path.join(_HERE, "..", "include")):
         for f in os.listdir(root):
-            t = max(t, os.path.getmtime(os.path.join(root, f)))
+            p = os.path.join(root, f)
+            if os.path.isfile(p):
+                t = max(t, os.path.getmtime(p))
     return t
 
 
-def build_library(force=False, verbose=False):
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _newest_src():
-        return OUT
+def build_library(force=False, verbose=False, extra_flags=(), out=None):
+    out = out or OUT
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= _newest_src():
+        return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
-    subprocess.check_call(cmd)
-    return OUT
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    tag = os.path.splitext(os.path.basename(out))[0]
+    flags = NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, "%s.%s.o" % (tag, os.path.splitext(os.path.basename(src))[0]))
+        subprocess.check_call([nvcc] + flags + ["-c", "-o", obj, src])
+        return obj
+
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        objs = list(ex.map(compile_one, _sources()))
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs)
+    return out

@@ -21,6 +21,7 @@
 #include "pfb_fm_tma.cuh"
 #include "pfb_fm_ws.cuh"
 #include "pfb_cl.cuh"
+#include "internal.h"
 
 using namespace rcb;
 
@@ -94,6 +95,8 @@ struct rcb_ctx {
         bool taps_smem = true;
         int variant = 0;  // RCB_PFB_VARIANT: tuning experiments, read only by -DRCB_EXPERIMENTS builds (never shipped)
         float4* d_tw4 = nullptr;  // pfb_cl_kernel twiddles [CS][R/2][16]
+        float* d_taps_gen = nullptr;   // generic-kernel tables, also built for the fast shapes (fallback for
+        float2* d_tw_gen = nullptr;    // output buffers the sector-store / TMA kernels cannot address)
         bool use_cl = false;      // FM only, N in {256, 1024}, <= 16 taps per arm: cluster / register-window kernel
         int oblock_log2 = 0;  // rcb_pfb_set_out_block
         Stage st[kStages];
@@ -123,7 +126,23 @@ struct rcb_ctx {
     // generic staging for small host-side helpers
     void* d_tmp[2] = {nullptr, nullptr};
     size_t d_tmp_cap[2] = {0, 0};
+
+    void* post_state = nullptr;  // K6 chains (postdemod_api.cu)
 };
+
+// ---- cross-translation-unit accessors (internal.h) ----
+int rcb_internal_device(rcb_t* h) { return h->device; }
+cudaStream_t rcb_internal_stream(rcb_t* h) { return h->stream; }
+int rcb_internal_fail(rcb_t* h, cudaError_t e, const char* what) {
+    if (h) snprintf(h->err, sizeof(h->err), "%s: %s", what, cudaGetErrorString(e));
+    return RCB_ECUDA;
+}
+void rcb_internal_count(rcb_t* h, int launches, size_t h2d_bytes, size_t d2h_bytes) {
+    h->stats.kernel_launches += (uint64_t)launches;
+    h->stats.h2d_bytes += h2d_bytes;
+    h->stats.d2h_bytes += d2h_bytes;
+}
+void** rcb_internal_post_slot(rcb_t* h) { return &h->post_state; }
 
 namespace {
 
@@ -285,7 +304,7 @@ int pfb_launch_cl_t(rcb_t* h, const float2* d_x, const float2* d_hist, size_t fr
     {
         const uint64_t dims[3] = {(uint64_t)2 * R, (uint64_t)R, (uint64_t)frames};
         const uint64_t str[2] = {(uint64_t)2 * R * 4, (uint64_t)N * 8};
-        const uint32_t box[3] = {32, (uint32_t)R, 1};
+        const uint32_t box[3] = {32, (uint32_t)G::M2W, 1};  // one FIR warp's slice of a row: 16 columns x R/8 groups
         if (!tmap_encode_f32(&tm_x, 3, d_x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
         const uint64_t hd[3] = {(uint64_t)2 * R, (uint64_t)R, (uint64_t)s.P};
         if (!tmap_encode_f32(&tm_hist, 3, d_hist, hd, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
@@ -294,14 +313,14 @@ int pfb_launch_cl_t(rcb_t* h, const float2* d_x, const float2* d_hist, size_t fr
     if (kb == 0) {
         const uint64_t dims[3] = {(uint64_t)frames, (uint64_t)R, (uint64_t)R};
         const uint64_t str[2] = {(uint64_t)ostride * 4, (uint64_t)ostride * 4 * R};
-        const uint32_t box[3] = {16, 16, (uint32_t)R};
+        const uint32_t box[3] = {16, 16, (uint32_t)G::M2W};  // one FIR warp's slice of the tile
         if (ostride < frames || !tmap_encode_f32(&tm_out, 3, d_fm, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
         p.out_rank = 3;
     } else {
         const uint64_t blk = (uint64_t)1 << kb;
         const uint64_t dims[4] = {blk, (uint64_t)R, (uint64_t)R, ((uint64_t)frames + blk - 1) >> kb};
         const uint64_t str[3] = {blk * 4, blk * 4 * R, blk * 4 * N};
-        const uint32_t box[4] = {16, 16, (uint32_t)R, 1};
+        const uint32_t box[4] = {16, 16, (uint32_t)G::M2W, 1};
         if (!tmap_encode_f32(&tm_out, 4, d_fm, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
         p.out_rank = 4;
     }
@@ -428,6 +447,10 @@ void pfb_free(rcb_t* h) {
     s.d_taps_kc = nullptr;
     cudaFree(s.d_tw4);
     s.d_tw4 = nullptr;
+    cudaFree(s.d_taps_gen);
+    cudaFree(s.d_tw_gen);
+    s.d_taps_gen = nullptr;
+    s.d_tw_gen = nullptr;
     s.use_cl = false;
 
     cudaFree(s.d_hist[0]);
@@ -478,8 +501,12 @@ int pfb_run_device(rcb_t* h, const float2* d_x, size_t frames, float2* d_iq, flo
         cl_rc = pfb_launch_cl(h, d_x, s.d_hist[s.hist_cur], frames, d_fm, ostride);
         if (cl_rc != RCB_OK && cl_rc != 1) return cl_rc;
     }
+    // the round-1 fast kernels emit 32-byte sector stores (st.global.v8 / two of them per complex row piece): they need
+    // 32-byte aligned output rows; anything else takes the generic path
+    const bool aligned32 = (s.oblock_log2 > 0 || (ostride % 8) == 0) && (!d_fm || ((uintptr_t)d_fm & 31) == 0) &&
+                           (!d_iq || ((uintptr_t)d_iq & 31) == 0);
     if (cl_rc == RCB_OK) {
-    } else if (s.R) {
+    } else if (s.R && aligned32) {
         int rc = pfb_launch_fast(h, p, false);
         if (rc) return rc;
     } else {
@@ -493,6 +520,10 @@ int pfb_run_device(rcb_t* h, const float2* d_x, size_t frames, float2* d_iq, flo
         }
         const int grid = (int)std::min<size_t>(frames + 1, (size_t)h->sm_count * 8);
         const int threads = std::min(256, std::max(32, ((s.N + 31) / 32) * 32));
+        if (s.R) {  // a fast shape on the generic path: its own table layouts
+            p.taps = s.d_taps_gen;
+            p.twiddle = s.d_tw_gen;
+        }
         pfb_generic_kernel<<<grid, threads, 2 * (size_t)s.N * sizeof(float2), h->stream>>>(p, s.d_ys, (long long)frames + 1);
         CKL(h);
         dim3 g2((unsigned)((frames + 255) / 256), (unsigned)s.N);
@@ -595,6 +626,7 @@ extern "C" int rcb_close(rcb_t* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     pfb_free(h);
+    rcb_post_free_all(h);
     for (auto& kv : h->ddc.chans) {
         cudaFree(kv.second.d_ctaps_rev);
         cudaFree(kv.second.d_ctaps4_rev);
@@ -836,6 +868,17 @@ extern "C" int rcb_pfb_config(rcb_t* h, int nchans, const float* taps, int ntaps
             tw[q] = make_float2((float)cos(a), (float)sin(a));
         }
         if (2 * (size_t)N * sizeof(float2) > 48 * 1024) return RCB_EUNSUPPORTED;
+    }
+    if (R) {
+        std::vector<float2> twg((size_t)N);
+        for (int q = 0; q < N; ++q) {
+            const double a = 2.0 * M_PI * (double)q / (double)N;
+            twg[q] = make_float2((float)cos(a), (float)sin(a));
+        }
+        CK(cudaMalloc(&s.d_taps_gen, hp.size() * sizeof(float)));
+        CK(cudaMalloc(&s.d_tw_gen, twg.size() * sizeof(float2)));
+        CK(cudaMemcpy(s.d_taps_gen, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(s.d_tw_gen, twg.data(), twg.size() * sizeof(float2), cudaMemcpyHostToDevice));
     }
     CK(cudaMalloc(&s.d_taps, tperm.size() * sizeof(float)));
     CK(cudaMalloc(&s.d_tw, tw.size() * sizeof(float2)));

@@ -1,5 +1,5 @@
 // K1 (FM-only, 1..16 taps per arm)  pfb_cl : polyphase channelizer + fused FM demod with a REGISTER-RESIDENT arm
-// FIR window, a TMA-fed raw-row ring, a dense output tile emitted by TMA tensor stores and - for N = 1024 - the
+// FIR window, a TMA-fed raw-row ring, dense output tiles emitted by TMA tensor stores and - for N = 1024 - the
 // frame split over a 2-CTA thread-block cluster with the transpose between the two radix-32 passes exchanged through
 // distributed shared memory.
 //
@@ -19,22 +19,25 @@
 //   * 8 FIR warps: a thread owns NC/256 adjacent columns for the whole run of its CTA, keeps their last PT samples
 //     (register ring, statically indexed: the 16-frame iteration is fully unrolled) and their PT taps in registers;
 //     per frame it reads its NEW sample(s) from the raw-row ring (one LDS.64/128), runs PT packed FFMA2 per column
-//     and writes the filtered sample(s) to the frame buffers: every input byte crosses L2 -> SM exactly once;
+//     and writes the filtered sample(s) to a ring of three 8-frame buffer sets: every input byte crosses L2 -> SM once;
 //   * the raw-row ring (8 rows) is filled by cp.async.bulk.tensor (SASS UTMALDG) issued by one lane six rows ahead;
 //     rows before the block (streaming history) come from the hist tensor, rows outside the stream are zero-filled
 //     by the TMA unit (out-of-bounds coordinates);
-//   * 8 FFT warps, two frames each (half-warp per frame, lane = ll mod 16): first packed radix-R pass over the
-//     columns ll + R jj, twiddle, transpose IN PLACE in the frame buffer - for N = 1024 the half of the first-pass
-//     outputs that belongs to the other CTA's bins (m1 = m mod 32 in its half) is written straight into the peer's
-//     frame buffer with st.shared::cluster and handed over with remote mbarrier arrives - then the second pass over
-//     ll for the CTA's own 16 values of m1, packed atan2 and the angle ring (16 slots);
-//   * demod: thread = (NC/256 channels) x 16 consecutive frames, previous angle carried in registers; the 16 x NC
-//     float results overwrite the ring region as a dense [m2][m1][16] tile (64 B per channel, 64B-swizzled so the
-//     STS.128 stay conflict free) and ONE cp.async.bulk.tensor store (SASS UTMASTG) per iteration and CTA writes
-//     it to the channel-major output - no per-thread sector stores, no LSU store wavefronts.
+//   * 8 FFT warps in two groups of four that take alternate 8-frame sets (so the groups run half an iteration apart
+//     and hide each other's latencies), two frames per warp (half-warp per frame, lane = ll mod 16): first packed
+//     radix-R pass over the columns ll + R jj, twiddle, transpose IN PLACE in the frame buffer - for N = 1024 the half
+//     of the first-pass outputs that belongs to the other CTA's bins (m1 = m mod 32 in its half) is written straight
+//     into the peer's frame buffer with st.shared::cluster and handed over with remote mbarrier arrives - then the
+//     second pass over ll for the CTA's own 16 values of m1, packed atan2, and the angles go into one of two
+//     [m2][m1][16 frames] tiles (64 B per channel, CU_TENSOR_MAP_SWIZZLE_64B layout);
+//   * demod + store run on the FIR warps (they have the issue slots to spare): a thread owns NC/256 channel rows of
+//     the tile, replaces the 16 angles of a row by gain * wrap(difference) IN PLACE (previous angle carried in a
+//     register - read set == write set, so no barrier), and each warp emits its 4 KB slice of the tile with one
+//     cp.async.bulk.tensor store (SASS UTMASTG) - no per-thread sector stores, no LSU store wavefronts.
+// There is no CTA-wide barrier in the steady state: all hand-overs are mbarriers (full / empty per buffer).
 // One iteration = 16 frames; a run starts with one warm-up iteration that refills the register windows and the
 // previous angles (no state is carried between CTAs or launches, so any split of a stream is bit exact).
-// Shared memory (N = 1024): 32 KB raw ring + 2 x 64 KB frame sets + 32 KB ring/tile + 4 KB twiddles = 196 KB.
+// Shared memory (N = 1024): 2 x 32 KB tiles + 32 KB raw ring + 3 x 32 KB frame sets + 4 KB twiddles = 196 KB.
 #pragma once
 #include "pfb_fm_tma.cuh"
 #include "tma_utils.cuh"
@@ -68,30 +71,32 @@ struct PfbClGeom {
     static constexpr int NC = N / CS;  // columns and channels per CTA (16 R)
     static constexpr int FPI = 16;     // frames per iteration
     static constexpr int THREADS = 512;
-    static constexpr int CPF = NC / 256;  // columns per FIR thread = channels per demod thread
-    static constexpr int RS = 8;          // raw-row ring slots
-    static constexpr int LAG = 2;         // a slot is refilled LAG rows after its last use (prefetch distance RS - LAG)
+    static constexpr int CPF = NC / 256;  // columns per FIR thread = channel rows per demod thread
+    static constexpr int RS = 8;          // raw-row ring slots PER FIR WARP (each warp streams its own 16 x R/8 columns)
+    static constexpr int M2W = R / 8;     // m2 rows of the tile owned (demodulated and stored) by one FIR warp = jj
+                                          //   rows of a frame owned by one FIR warp
     static constexpr size_t row_bytes = (size_t)NC * 8;
-    static constexpr size_t tile_bytes = (size_t)FPI * NC * 4;  // angle ring == output tile
+    static constexpr size_t slice_bytes = row_bytes / 8;         // one FIR warp's part of a row
+    static constexpr size_t tile_bytes = (size_t)FPI * NC * 4;  // [R m2][16 m1][16 t] floats
     static constexpr size_t raw_bytes = RS * row_bytes;
-    static constexpr size_t set_bytes = FPI * row_bytes;
+    static constexpr size_t hset_bytes = 8 * row_bytes;         // one 8-frame buffer set
     static constexpr size_t tw_bytes = (size_t)(R / 2) * 16 * 16;
-    static constexpr size_t off_raw = tile_bytes;
+    static constexpr size_t off_raw = 2 * tile_bytes;
     static constexpr size_t off_sets = off_raw + raw_bytes;
-    static constexpr size_t off_tw = off_sets + 2 * set_bytes;
+    static constexpr size_t off_tw = off_sets + 3 * hset_bytes;
     static constexpr size_t off_bar = off_tw + tw_bytes;
-    static constexpr size_t smem_bytes = off_bar + 512 + 1024;  // + barriers + alignment slack
+    static constexpr size_t smem_bytes = off_bar + 1024 + 1024;  // + barriers + alignment slack
 };
 
 enum {  // mbarrier slots (8 B each) behind off_bar
-    CLB_RAW_FULL = 0,    // [8]  TMA -> FIR warps
-    CLB_RAW_EMPTY = 8,   // [8]  FIR warps -> TMA issuer
-    CLB_SET_FULL = 16,   // [2]  FIR -> FFT
-    CLB_SET_EMPTY = 18,  // [2]  FFT -> FIR
-    CLB_T_FREE = 20,     // [8]  peer FFT warp w has read its frames: its buffer may receive my first-pass outputs
-    CLB_T_FULL = 28,     // [8]  peer FFT warp w has written its half of my transpose buffer
-    CLB_RING_FREE = 36,  // [1]  output tile read by the TMA store: the ring may be rewritten
-    CLB_COUNT = 37
+    CLB_SET_FULL = 0,     // [3]  FIR -> FFT group: 8 filtered frames
+    CLB_SET_EMPTY = 3,    // [3]  FFT group (4 warps) -> FIR
+    CLB_T_FREE = 6,       // [8]  peer FFT warp w has read its frames: its buffer may receive my first-pass outputs
+    CLB_T_FULL = 14,      // [8]  my half of the transpose buffer of warp w is complete (local arrive + peer's st.async bytes)
+    CLB_RING_FULL = 22,   // [2]  FFT warps (8) -> demod: the 16 angle columns of an iteration are in the tile
+    CLB_RING_FREE = 24,   // [2]  demod warps (8) -> FFT: the tile has been read by the TMA stores
+    CLB_RAW_FULL = 26,    // [8 warps][RS]  TMA -> the FIR warp that owns the slice
+    CLB_COUNT = 26 + 8 * 8
 };
 
 template <int R, int PT>
@@ -99,13 +104,14 @@ __global__ void __launch_bounds__(512, 1)
     pfb_cl_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hist,
                   const __grid_constant__ CUtensorMap tm_out, const PfbClParams p) {
     using G = PfbClGeom<R>;
-    constexpr int CS = G::CS, N = G::N, NC = G::NC, CPF = G::CPF, RS = G::RS, LAG = G::LAG;
+    constexpr int CS = G::CS, N = G::N, CPF = G::CPF, RS = G::RS, M2W = G::M2W;
+    static_assert(CLB_COUNT * 8 <= 1024, "barrier area");
     static_assert(R == 16 || R == 32, "N = 256 (one CTA) or N = 1024 (cluster of two)");
     static_assert(PT >= 1 && PT <= 16 && (PT & (PT - 1)) == 0, "taps per arm rounded up to a power of two");
     extern __shared__ unsigned char smem_cl_raw[];
     const uint32_t base = (smem_addr_u32(smem_cl_raw) + 1023u) & ~1023u;  // swizzled TMA tiles want their pattern aligned
     const uint32_t a_tile = base, a_raw = base + (uint32_t)G::off_raw, a_sets = base + (uint32_t)G::off_sets;
-    const uint32_t a_tw = base + (uint32_t)G::off_tw, a_bar = base + (uint32_t)G::off_bar;
+    const uint32_t a_bar = base + (uint32_t)G::off_bar;
     unsigned char* gbase = smem_cl_raw + (base - smem_addr_u32(smem_cl_raw));
     auto bar = [&](int i) { return a_bar + 8u * (uint32_t)i; };
 
@@ -128,19 +134,19 @@ __global__ void __launch_bounds__(512, 1)
         for (int i = tid; i < (R / 2) * 16; i += G::THREADS) dst[i] = src[i];
     }
     if (tid == 0) {
-        for (int i = 0; i < RS; ++i) {
-            mbar_init_a(bar(CLB_RAW_FULL + i), 1);
-            mbar_init_a(bar(CLB_RAW_EMPTY + i), 8);
-        }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 8 * RS; ++i) mbar_init_a(bar(CLB_RAW_FULL + i), 1);
+        for (int i = 0; i < 3; ++i) {
             mbar_init_a(bar(CLB_SET_FULL + i), 8);
-            mbar_init_a(bar(CLB_SET_EMPTY + i), 8);
+            mbar_init_a(bar(CLB_SET_EMPTY + i), 4);
         }
         for (int i = 0; i < 8; ++i) {
             mbar_init_a(bar(CLB_T_FREE + i), 1);
-            mbar_init_a(bar(CLB_T_FULL + i), 32);
+            mbar_init_a(bar(CLB_T_FULL + i), 1);
         }
-        mbar_init_a(bar(CLB_RING_FREE), 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init_a(bar(CLB_RING_FULL + i), 8);
+            mbar_init_a(bar(CLB_RING_FREE + i), 8);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&tm_x);
         prefetch_tmap(&tm_hist);
@@ -152,7 +158,7 @@ __global__ void __launch_bounds__(512, 1)
     const int nrows = nit * 16;
 
     if (warp < 8) {
-        // =============================== FIR warps ===============================
+        // =============================== FIR + demod warps ===============================
         const int ft = tid;  // 0..255
         float hk[CPF][PT];
         float2 win[CPF][PT];
@@ -166,31 +172,107 @@ __global__ void __launch_bounds__(512, 1)
                 win[q][k] = make_float2(0.f, 0.f);
             }
         }
-        const bool issuer = (tid == 0);
-        auto issue_row = [&](int g) {  // row g of the run -> slot g % RS
-            const int slot = g & (RS - 1);
+        // demod ownership: R = 32: tile rows m2 = 2 (ft >> 4) + {0, 1};  R = 16: m2 = ft >> 4;  m1 = ft & 15
+        const int dm1 = ft & 15, dmh = ft >> 4;
+        float prev[CPF];
+#pragma unroll
+        for (int q = 0; q < CPF; ++q) prev[q] = 0.f;
+
+        // this warp's private ring of raw row slices: lane 0 keeps RS rows in flight, refilling a slot as soon as the warp
+        // has read it (no coupling to the other warps, and the prefetch keeps running while the warp demodulates)
+        const uint32_t a_wraw = a_raw + (uint32_t)warp * (uint32_t)(RS * G::slice_bytes);
+        const int rbar0 = CLB_RAW_FULL + warp * RS;
+        auto issue_row = [&](int g, int slot) {  // row g of the run
             const long long f = fbase + g;
-            const uint32_t dst = a_raw + (uint32_t)slot * (uint32_t)G::row_bytes;
-            mbar_expect_tx_a(bar(CLB_RAW_FULL + slot), (uint32_t)G::row_bytes);
+            const uint32_t dst = a_wraw + (uint32_t)slot * (uint32_t)G::slice_bytes;
+            mbar_expect_tx_a(bar(rbar0 + slot), (uint32_t)G::slice_bytes);
             if (f >= 0 || f < -(long long)p.P)
-                tma_load_3d(dst, &tm_x, 32 * (int)rank, 0, (f >= 0) ? (int)f : -1, bar(CLB_RAW_FULL + slot));
+                tma_load_3d(dst, &tm_x, 32 * (int)rank, M2W * warp, (f >= 0) ? (int)f : -1, bar(rbar0 + slot));
             else
-                tma_load_3d(dst, &tm_hist, 32 * (int)rank, 0, (int)(f + p.P), bar(CLB_RAW_FULL + slot));
+                tma_load_3d(dst, &tm_hist, 32 * (int)rank, M2W * warp, (int)(f + p.P), bar(rbar0 + slot));
         };
-        if (issuer) {
-            for (int g = 0; g < RS && g < nrows; ++g) issue_row(g);
+        if (lane == 0) {
+            for (int g = 0; g < RS && g < nrows; ++g) issue_row(g, g);
         }
+        // demod of iteration j (runs one iteration behind the FIR): in place in tile j & 1, then this warp's slice of
+        // the tile goes out with one TMA store
+        auto demod = [&](int j) {
+            const int it = it0 - 1 + j;
+            const int buf = j & 1;
+            if (lane == 0 && j >= 1) {  // the slice stored an iteration ago has been read: its tile may be rewritten
+                tma_store_wait_read();
+                mbar_arrive_a(bar(CLB_RING_FREE + ((j - 1) & 1)));
+            }
+            mbar_wait_a(bar(CLB_RING_FULL + buf), (uint32_t)((j >> 1) & 1));
+            const uint32_t tile = a_tile + (uint32_t)buf * (uint32_t)G::tile_bytes;
+            const uint32_t sw = (uint32_t)((dm1 >> 1) & 3);
+            const long long t0 = (long long)it * 16;
+            const bool live = (it >= it0);
+            const bool full = live && (t0 + 16 <= p.T);
+#pragma unroll
+            for (int q = 0; q < CPF; ++q) {
+                const int m2 = (CPF == 2) ? 2 * dmh + q : dmh;
+                const uint32_t rowa = tile + (uint32_t)(m2 * 16 + dm1) * 64u;
+                float a[16];
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4)
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                 : "=f"(a[4 * j4]), "=f"(a[4 * j4 + 1]), "=f"(a[4 * j4 + 2]), "=f"(a[4 * j4 + 3])
+                                 : "r"(rowa + ((uint32_t)(j4 ^ sw) << 4)));
+                float o[16];
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    float d = a[t] - (t == 0 ? prev[q] : a[t - 1]);
+                    const float kk = (d * 0.15915494309189535f + 12582912.0f) - 12582912.0f;
+                    d = fmaf(kk, -6.283185307179586f, d);
+                    d *= p.gain;
+                    o[t] = (d != d) ? 0.0f : d;
+                }
+                prev[q] = a[15];
+                if (full) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4)
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rowa + ((uint32_t)(j4 ^ sw) << 4)), "f"(o[4 * j4]),
+                                     "f"(o[4 * j4 + 1]), "f"(o[4 * j4 + 2]), "f"(o[4 * j4 + 3])
+                                     : "memory");
+                } else if (live) {  // ragged tail of the block: guarded scalar stores straight from the registers
+                    const int m = 16 * (int)rank + dm1 + R * m2;
+#pragma unroll
+                    for (int t = 0; t < 16; ++t)
+                        if (t0 + t < p.T) p.out_fm[pfb_cl_out_index(p, m, t0 + t)] = o[t];
+                }
+            }
+            if (full) {
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    const uint32_t src = tile + (uint32_t)(M2W * warp) * 1024u;
+                    if (p.out_rank == 3) {
+                        tma_store_3d(&tm_out, (int)t0, 16 * (int)rank, M2W * warp, src);
+                    } else {
+                        const int kb = p.oblock_log2;
+                        tma_store_4d(&tm_out, (int)(t0 & ((1LL << kb) - 1)), 16 * (int)rank, M2W * warp, (int)(t0 >> kb), src);
+                    }
+                    tma_store_commit();
+                }
+            }
+        };
 #pragma unroll 1
         for (int k = 0; k < nit; ++k) {
-            const int s = k & 1;
-            if (k >= 2) mbar_wait_a(bar(CLB_SET_EMPTY + s), (uint32_t)(((k >> 1) - 1) & 1));
-            const uint32_t a_set = a_sets + (uint32_t)s * (uint32_t)G::set_bytes;
+            uint32_t a_set = 0;
+            int sb = 0;
 #pragma unroll
             for (int t = 0; t < 16; ++t) {
-                const int slot = t & (RS - 1);
-                const int use = k * (16 / RS) + t / RS;  // how often this slot has been used before
-                mbar_wait_a(bar(CLB_RAW_FULL + slot), (uint32_t)(use & 1));
-                const uint32_t src = a_raw + (uint32_t)slot * (uint32_t)G::row_bytes + (uint32_t)ft * (8u * CPF);
+                if ((t & 7) == 0) {  // next 8-frame set of the ring of three
+                    const int h = 2 * k + (t >> 3);
+                    sb = h % 3;
+                    if (h >= 3) mbar_wait_a(bar(CLB_SET_EMPTY + sb), (uint32_t)((h / 3 - 1) & 1));
+                    a_set = a_sets + (uint32_t)sb * (uint32_t)G::hset_bytes;
+                }
+                const int rs = t & (RS - 1);                       // static: the iteration is unrolled, RS divides 16
+                const uint32_t rpar = (uint32_t)((k * (16 / RS) + t / RS) & 1);
+                mbar_wait_a(bar(rbar0 + rs), rpar);
+                const uint32_t src = a_wraw + (uint32_t)rs * (uint32_t)G::slice_bytes + (uint32_t)lane * (8u * CPF);
                 float2 x[CPF];
                 if constexpr (CPF == 2) {
                     float4 v;
@@ -201,15 +283,11 @@ __global__ void __launch_bounds__(512, 1)
                     asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(x[0].x), "=f"(x[0].y) : "r"(src));
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive_a(bar(CLB_RAW_EMPTY + slot));
-                if (issuer) {  // refill the slot that was last used LAG rows ago
-                    const int g = k * 16 + t;
-                    const int gd = g - LAG;          // row whose slot is recycled
-                    const int gn = gd + RS;          // row that goes into it
-                    if (gd >= 0 && gn < nrows) {
-                        mbar_wait_a(bar(CLB_RAW_EMPTY + (gd & (RS - 1))), (uint32_t)((gd / RS) & 1));
+                if (lane == 0) {  // the slot has been read by the whole warp: refill it with the row RS ahead
+                    const int gn = k * 16 + t + RS;
+                    if (gn < nrows) {
                         fence_async_smem();
-                        issue_row(gn);
+                        issue_row(gn, rs);
                     }
                 }
                 float2 y[CPF];
@@ -230,43 +308,41 @@ __global__ void __launch_bounds__(512, 1)
                         y[q] = p2add(a0, a1);
                     }
                 }
-                const uint32_t dst = a_set + (uint32_t)t * (uint32_t)G::row_bytes + (uint32_t)ft * (8u * CPF);
+                const uint32_t dst = a_set + (uint32_t)(t & 7) * (uint32_t)G::row_bytes + (uint32_t)ft * (8u * CPF);
                 if constexpr (CPF == 2) {
                     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "f"(y[0].x), "f"(y[0].y), "f"(y[1].x), "f"(y[1].y) : "memory");
                 } else {
                     asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(dst), "f"(y[0].x), "f"(y[0].y) : "memory");
                 }
+                if ((t & 7) == 7) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_a(bar(CLB_SET_FULL + sb));
+                }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive_a(bar(CLB_SET_FULL + s));
+            if (k >= 1) demod(k - 1);
         }
+        demod(nit - 1);
+        if (lane == 0) tma_store_wait_all();
     } else {
-        // =============================== FFT / demod warps ===============================
-        const int w = warp - 8, dt = tid - 256;
+        // =============================== FFT warps ===============================
+        const int w = warp - 8;
+        const int g = w >> 2, wq = w & 3;  // group g takes the 8-frame sets 2k + g; frames 2 wq + {0, 1} of a set
         const int fr = lane >> 4, l = lane & 15;
         const int ll = 16 * (int)rank + l;  // this lane's column residue (pass 1) and bin residue m1 (pass 2)
         const float4* tws = reinterpret_cast<const float4*>(gbase + G::off_tw);
-        float* ring = reinterpret_cast<float*>(gbase);
         const uint32_t peer_tfree = (CS == 2) ? dsmem_map(bar(CLB_T_FREE + w), peer) : 0u;
         const uint32_t peer_tfull = (CS == 2) ? dsmem_map(bar(CLB_T_FULL + w), peer) : 0u;
-        // demod ownership: R = 32: bins m2 = 2 kk + {0,1}, kk = dt >> 4;  R = 16: bin m2 = dt >> 4;  m1 = 16 rank + (dt & 15)
-        const int dm1 = dt & 15, dmh = dt >> 4;
-        float prev[CPF];
-#pragma unroll
-        for (int q = 0; q < CPF; ++q) prev[q] = 0.f;
+        const int tcol = 8 * g + 2 * wq + fr;  // this lane's frame inside the iteration = tile column
+        const uint32_t tile_lane = (uint32_t)l * 64u + ((uint32_t)((tcol >> 2) ^ ((l >> 1) & 3)) << 4) + (uint32_t)(tcol & 3) * 4u;
 
 #pragma unroll 1
         for (int k = 0; k < nit; ++k) {
-            const int it = it0 - 1 + k;
-            const int s = k & 1;
-            const uint32_t a_fr = a_sets + (uint32_t)s * (uint32_t)G::set_bytes + (uint32_t)(2 * w + fr) * (uint32_t)G::row_bytes;
-            const float2* wf = reinterpret_cast<const float2*>(gbase + G::off_sets + (size_t)s * G::set_bytes +
-                                                               (size_t)(2 * w + fr) * G::row_bytes);
-            if (dt == 0 && k >= 1) {  // the previous iteration's tile has been read by the TMA unit: release the ring
-                tma_store_wait_read();
-                mbar_arrive_a(bar(CLB_RING_FREE));
-            }
-            mbar_wait_a(bar(CLB_SET_FULL + s), (uint32_t)((k >> 1) & 1));
+            const int h = 2 * k + g;
+            const int sb = h % 3;
+            const size_t fr_off = G::off_sets + (size_t)sb * G::hset_bytes + (size_t)(2 * wq + fr) * G::row_bytes;
+            const uint32_t a_fr = base + (uint32_t)fr_off;
+            const float2* wf = reinterpret_cast<const float2*>(gbase + fr_off);
+            mbar_wait_a(bar(CLB_SET_FULL + sb), (uint32_t)((h / 3) & 1));
             float2 pr[R / 2], pi[R / 2];
             {
                 auto get = [&](auto j) { return wf[(R - 1 - decltype(j)::value) * 16 + l]; };
@@ -275,8 +351,9 @@ __global__ void __launch_bounds__(512, 1)
             }
             __syncwarp();  // both frames of this warp are in registers: the buffer becomes the transpose scratch
             if constexpr (CS == 2) {
-                if (lane == 0) mbar_arrive_remote(peer_tfree);          // the peer may write its half into my buffer
-                mbar_wait_cluster_a(bar(CLB_T_FREE + w), (uint32_t)(k & 1));  // and I may write mine into the peer's
+                // (relaxed: the only accesses to order are this warp's loads above, already consumed by the transform)
+                if (lane == 0) mbar_arrive_remote_relaxed(peer_tfree);  // the peer may write its half into my buffer
+                mbar_wait_a(bar(CLB_T_FREE + w), (uint32_t)(k & 1));     // and I may write mine into the peer's
             }
             {
                 // row ll of the destination's [R rows][8 chunks of 16 B] buffer, 16-byte chunks XOR-swizzled by row
@@ -291,14 +368,15 @@ __global__ void __launch_bounds__(512, 1)
                     if (CS == 1 || (uint32_t)(c >> 3) == rank) {
                         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a_fr + off), "f"(b0.x), "f"(b0.y), "f"(b1.x), "f"(b1.y) : "memory");
                     } else {
-                        dsmem_st_v4(peer_fr + off, b0.x, b0.y, b1.x, b1.y);
+                        dsmem_st_async_v4(peer_fr + off, b0.x, b0.y, b1.x, b1.y, peer_tfull);  // + 16 bytes of complete_tx
                     }
                 }
             }
             if constexpr (CS == 2) {
-                mbar_arrive_remote(peer_tfull);  // every lane: its remote stores are released to the peer
-                __syncwarp();
-                mbar_wait_cluster_a(bar(CLB_T_FULL + w), (uint32_t)(k & 1));
+                __syncwarp();  // local half written
+                // my buffer is complete when the peer's R/2 x 256 bytes of st.async have landed as well
+                if (lane == 0) mbar_expect_tx_a(bar(CLB_T_FULL + w), (uint32_t)(32 * (R / 4) * 16));
+                mbar_wait_a(bar(CLB_T_FULL + w), (uint32_t)(k & 1));
             } else {
                 __syncwarp();
             }
@@ -311,7 +389,7 @@ __global__ void __launch_bounds__(512, 1)
                     asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(u[R - 1 - l2].x), "=f"(u[R - 1 - l2].y) : "r"(a));
                 }
                 __syncwarp();  // frame buffers of this warp fully consumed: hand the set back to the FIR warps
-                if (lane == 0) mbar_arrive_a(bar(CLB_SET_EMPTY + s));
+                if (lane == 0) mbar_arrive_a(bar(CLB_SET_EMPTY + sb));
                 auto get = [&](auto j) { return u[decltype(j)::value]; };
                 auto tap = [&](auto) { return 1.0f; };
                 fft_packed<R, +1, false>(pr, pi, get, tap);  // (pr[q], pi[q]) = Y[ll + R*(2q)], Y[ll + R*(2q+1)]
@@ -319,86 +397,20 @@ __global__ void __launch_bounds__(512, 1)
             float2 ph[R / 2];
 #pragma unroll
             for (int q = 0; q < R / 2; ++q) ph[q] = atan2_nan_p2(pi[q], pr[q]);
-            if (k >= 1) mbar_wait_a(bar(CLB_RING_FREE), (uint32_t)((k - 1) & 1));
+            const int buf = k & 1;
+            if (k >= 2) mbar_wait_a(bar(CLB_RING_FREE + buf), (uint32_t)(((k >> 1) - 1) & 1));
             {
-                // ring[slot][kk = m2 / 2][m1 (16)][2]
-                float2* rb = reinterpret_cast<float2*>(ring) + (size_t)(2 * w + fr) * (NC / 2) + l;
+                // angle of (bin m2, m1 = l) at frame tcol -> tile[m2][l][tcol] (64B-swizzled rows)
+                const uint32_t ta = a_tile + (uint32_t)buf * (uint32_t)G::tile_bytes + tile_lane;
 #pragma unroll
-                for (int q = 0; q < R / 2; ++q) rb[q * 16] = ph[q];
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // FFT warps only: the 16 angle rows of this iteration are in the ring
-            float o[CPF][16];
-            {
-                float a[16][CPF];
-                if constexpr (CPF == 2) {
-                    const float2* rp = reinterpret_cast<const float2*>(ring) + dmh * 16 + dm1;
-#pragma unroll
-                    for (int t = 0; t < 16; ++t) {
-                        const float2 v = rp[(size_t)t * (NC / 2)];
-                        a[t][0] = v.x;
-                        a[t][1] = v.y;
-                    }
-                } else {
-                    const float* rp = ring + (dmh >> 1) * 32 + dm1 * 2 + (dmh & 1);
-#pragma unroll
-                    for (int t = 0; t < 16; ++t) a[t][0] = rp[(size_t)t * NC];
-                }
-#pragma unroll
-                for (int q = 0; q < CPF; ++q) {
-#pragma unroll
-                    for (int t = 0; t < 16; ++t) {
-                        float d = a[t][q] - (t == 0 ? prev[q] : a[t - 1][q]);
-                        const float kk = (d * 0.15915494309189535f + 12582912.0f) - 12582912.0f;
-                        d = fmaf(kk, -6.283185307179586f, d);
-                        d *= p.gain;
-                        o[q][t] = (d != d) ? 0.0f : d;
-                    }
-                    prev[q] = a[15][q];
+                for (int q = 0; q < R / 2; ++q) {
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(ta + (uint32_t)(2 * q) * 1024u), "f"(ph[q].x) : "memory");
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(ta + (uint32_t)(2 * q + 1) * 1024u), "f"(ph[q].y) : "memory");
                 }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // every ring read is done: the region becomes the output tile
-            if (it >= it0) {
-                const long long t0 = (long long)it * 16;
-                const bool full = (t0 + 16 <= p.T);  // (a 16-frame group never straddles a time block of 2^k >= 16 frames)
-                if (full) {
-                    // tile [m2][m1 (16)][t (16)] floats, CU_TENSOR_MAP_SWIZZLE_64B: 16-byte chunk j of a 64-byte row
-                    // lands at j ^ (address bits 8:7) = j ^ ((m1 >> 1) & 3)
-#pragma unroll
-                    for (int q = 0; q < CPF; ++q) {
-                        const int m2 = (CPF == 2) ? 2 * dmh + q : dmh;
-                        const uint32_t rowa = a_tile + (uint32_t)(m2 * 16 + dm1) * 64u;
-                        const uint32_t sw = (uint32_t)((dm1 >> 1) & 3);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rowa + ((uint32_t)(j ^ sw) << 4)), "f"(o[q][4 * j]),
-                                         "f"(o[q][4 * j + 1]), "f"(o[q][4 * j + 2]), "f"(o[q][4 * j + 3])
-                                         : "memory");
-                    }
-                    fence_async_smem();
-                } else {
-                    // ragged tail of the block: guarded scalar stores straight from the registers
-#pragma unroll
-                    for (int q = 0; q < CPF; ++q) {
-                        const int m2 = (CPF == 2) ? 2 * dmh + q : dmh;
-                        const int m = 16 * (int)rank + dm1 + R * m2;
-#pragma unroll
-                        for (int t = 0; t < 16; ++t)
-                            if (t0 + t < p.T) p.out_fm[pfb_cl_out_index(p, m, t0 + t)] = o[q][t];
-                    }
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (dt == 0 && full) {
-                    if (p.out_rank == 3) {
-                        tma_store_3d(&tm_out, (int)t0, 16 * (int)rank, 0, a_tile);
-                    } else {
-                        const int kb = p.oblock_log2;
-                        tma_store_4d(&tm_out, (int)(t0 & ((1LL << kb) - 1)), 16 * (int)rank, 0, (int)(t0 >> kb), a_tile);
-                    }
-                    tma_store_commit();
-                }
-            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(bar(CLB_RING_FULL + buf));
         }
-        if (dt == 0) tma_store_wait_all();
     }
     if constexpr (CS == 2) cluster_sync_all();
 }

@@ -93,15 +93,17 @@ __device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
     asm volatile("{\n\t.reg .b64 t;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
                  : "memory");
 }
+// (the suspend-time hint lets the hardware park the warp instead of returning to a spin loop: the try_wait / branch
+// pairs of short polls were 25 % of the issued instructions of pfb_cl_kernel, profiles/r02_pfb_cl_v2_*)
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
     uint32_t done;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(0x989680u)
             : "memory");
     } while (!done);
 }
@@ -136,6 +138,19 @@ __device__ __forceinline__ void dsmem_st_v4(uint32_t addr, float a, float b, flo
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// remote arrive without a memory fence: for "my buffer may be overwritten" notifications whose only prior accesses
+// are loads already consumed by arithmetic (a release at cluster scope costs an ERRBAR / membar stall per use)
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// 16-byte store into a peer CTA's shared memory that signals `cluster_bar` (an mbarrier in the SAME peer CTA) with
+// complete_tx of its 16 bytes: the receiver posts expect_tx and waits on a plain (cta-scope) try_wait - no release
+// fence on the sender, no cluster-scope acquire (CCTL.IVALL) on the receiver.
+__device__ __forceinline__ void dsmem_st_async_v4(uint32_t addr, float a, float b, float c, float d, uint32_t cluster_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr),
+                 "f"(a), "f"(b), "f"(c), "f"(d), "r"(cluster_bar)
+                 : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");

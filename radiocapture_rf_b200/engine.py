@@ -296,6 +296,104 @@ class DdcBank(object):
         return out
 
 
+class PostDemod(object):
+    """K6: the data-parallel post-demod stages of the backend demods over `rows` channels (rcb_post_*).
+
+    PostDemod.p25_c4fm(...)  = p25_control_demod.py:106-133 / logging_receiver.py:229-245 up to the symbol filter
+    PostDemod.analog_fm(...) = logging_receiver.py:210-222 (squelch, fm_demod_cf, 300 Hz high-pass, resampler to 8 kHz)
+    Taps default to the reference's own designs (firdes.py) and can be passed explicitly."""
+
+    def __init__(self, engine, cfg, keep):
+        self.e = engine
+        self.rows = cfg.rows
+        self.kind = cfg.kind
+        self._keep = keep     # tap arrays referenced by cfg during rcb_post_open
+        cid = C.c_int(0)
+        check(self.e.lib.rcb_post_open(self.e.h, C.byref(cfg), C.byref(cid)), "rcb_post_open", self.e.h)
+        self.id = cid.value
+        self._keep = None
+        self.interp, self.decim = max(cfg.interp, 1), max(cfg.decim, 1)
+
+    @classmethod
+    def p25_c4fm(cls, engine, rows, channel_rate=25000.0, symbol_rate=4800, symbol_deviation=600.0, prefilter_taps=None,
+                 symbol_taps=None, probe_len=10000, probe_scale=1e-4):
+        from . import firdes
+        if prefilter_taps is None:   # p25_control_demod.py:107
+            prefilter_taps = firdes.low_pass_2(1.0, channel_rate, channel_rate / 4.0, 500.0, 30.0, firdes.WIN_BLACKMAN)
+        if symbol_taps is None:      # p25_control_demod.py:130-133
+            sps = int(channel_rate // symbol_rate)
+            symbol_taps = np.full(sps, 1.0 / sps, np.float32)
+        t0 = np.ascontiguousarray(prefilter_taps, np.float32)
+        t1 = np.ascontiguousarray(symbol_taps, np.float32)
+        cfg = _lib.rcb_post_cfg()
+        cfg.kind, cfg.rows = _lib.POST_P25_C4FM, int(rows)
+        cfg.gain = float(channel_rate / (2.0 * np.pi * symbol_deviation))   # p25_control_demod.py:120
+        cfg.taps0, cfg.ntaps0 = t0.ctypes.data, len(t0)
+        cfg.taps1, cfg.ntaps1 = t1.ctypes.data, len(t1)
+        cfg.probe_len, cfg.probe_scale = int(probe_len), float(probe_scale)
+        return cls(engine, cfg, (t0, t1))
+
+    @classmethod
+    def analog_fm(cls, engine, rows, input_rate=25000.0, audio_rate=8000, deviation=15000.0, gain=8.0, tau=75e-6,
+                  squelch_db=-100.0, squelch_alpha=0.01, squelch_gate=True, audio_taps=None, hp_taps=None, resampler=None):
+        from . import firdes
+        if audio_taps is None:   # fm_demod_cf: optfir.low_pass(gain, rate, audio_pass, audio_stop, 0.1, 60)
+            audio_taps = firdes.optfir_low_pass(gain, input_rate, input_rate * 0.25, input_rate * 0.25 + 2000, 0.1, 60)
+        if hp_taps is None:      # logging_receiver.py:215
+            hp_taps = firdes.high_pass(1, input_rate, 300, 30, firdes.WIN_HAMMING, 6.76)
+        if resampler is None:    # logging_receiver.py:216-221
+            resampler = firdes.rational_resampler_design(int(audio_rate), int(input_rate))
+        interp, decim, rt = resampler
+        t0 = np.ascontiguousarray(audio_taps, np.float32)
+        t1 = np.ascontiguousarray(hp_taps, np.float32)
+        t2 = np.ascontiguousarray(rt, np.float32)
+        b0, b1, a1 = firdes.fm_deemph(input_rate, tau)
+        cfg = _lib.rcb_post_cfg()
+        cfg.kind, cfg.rows = _lib.POST_ANALOG_FM, int(rows)
+        cfg.gain = float(input_rate / (2.0 * np.pi * deviation))
+        cfg.taps0, cfg.ntaps0 = t0.ctypes.data, len(t0)
+        cfg.taps1, cfg.ntaps1 = t1.ctypes.data, len(t1)
+        cfg.taps2, cfg.ntaps2 = t2.ctypes.data, len(t2)
+        cfg.interp, cfg.decim = int(interp), int(decim)
+        cfg.squelch_db, cfg.squelch_alpha, cfg.squelch_gate = float(squelch_db), float(squelch_alpha), int(bool(squelch_gate))
+        cfg.deemph_b0, cfg.deemph_b1, cfg.deemph_a1 = float(b0), float(b1), float(a1)
+        return cls(engine, cfg, (t0, t1, t2))
+
+    def _cap(self, n):
+        return int(n) * self.interp // self.decim + 2
+
+    def process(self, iq_rows, want_probe=False):
+        """iq_rows: complex64 [rows][n] on the host.  Returns a list of float32 arrays (one per row) [, probe]."""
+        x = np.ascontiguousarray(iq_rows, dtype=np.complex64)
+        assert x.ndim == 2 and x.shape[0] == self.rows
+        n = x.shape[1]
+        cap = self._cap(n)
+        out = np.empty((self.rows, cap), np.float32)
+        nout = (C.c_int * self.rows)()
+        probe = (C.c_float * self.rows)()
+        check(self.e.lib.rcb_post_process(self.e.h, self.id, x.ctypes.data, n, n, None, MEM_HOST, out.ctypes.data, cap,
+                                          MEM_HOST, nout, probe), "rcb_post_process", self.e.h)
+        res = [out[r, :nout[r]].copy() for r in range(self.rows)]
+        return (res, np.array(probe[:], np.float32)) if want_probe else res
+
+    def process_device(self, d_iq, n, in_stride, d_out, out_stride, row_map=None):
+        """Rows resident on the device (e.g. rows of a PFB IQ output).  Returns the per-row output counts."""
+        def _p(x):
+            return x.ptr if isinstance(x, DeviceBuffer) else x
+        rm = None
+        if row_map is not None:
+            rm = (C.c_int * self.rows)(*[int(v) for v in row_map])
+        nout = (C.c_int * self.rows)()
+        check(self.e.lib.rcb_post_process(self.e.h, self.id, _p(d_iq), int(n), int(in_stride), rm, MEM_DEVICE, _p(d_out),
+                                          int(out_stride), MEM_DEVICE, nout, None), "rcb_post_process", self.e.h)
+        return list(nout)
+
+    def close(self):
+        if self.id:
+            check(self.e.lib.rcb_post_close(self.e.h, self.id), "rcb_post_close", self.e.h)
+            self.id = 0
+
+
 class FftScanner(object):
     """K3: windowed streaming FFT + log-power block sums (fft_vector.py flowgraph)."""
 

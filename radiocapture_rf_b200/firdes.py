@@ -105,3 +105,50 @@ def optfir_low_pass(gain, Fs, freq1, freq2, passband_ripple_db, stopband_atten_d
 def pfb_prototype(num_channels):
     """rc_frontend/receiver.py:249-254: optfir.low_pass(1, N, 0.5, 0.5+0.2, 0.1, 80)."""
     return optfir_low_pass(1.0, float(num_channels), 0.5, 0.7, 0.1, 80.0)
+
+
+# ---- designs used by the post-demod chains (K6, SURVEY 8(f) row 3) ------------------------------------------------
+def high_pass(gain, sampling_freq, cutoff_freq, transition_width, win_type=WIN_HAMMING, beta=6.76):
+    """firdes::high_pass - the 300 Hz audio high-pass of logging_receiver.py:215 (2007 taps at 25 kHz)."""
+    ntaps = compute_ntaps(sampling_freq, transition_width, win_type, beta)
+    w = window(win_type, ntaps, beta).astype(np.float64)
+    m = (ntaps - 1) // 2
+    n = np.arange(-m, m + 1, dtype=np.float64)
+    fwt0 = 2.0 * math.pi * cutoff_freq / sampling_freq
+    with np.errstate(divide="ignore", invalid="ignore"):
+        h = np.where(n == 0, 1.0 - fwt0 / math.pi, -np.sin(n * fwt0) / (n * math.pi))
+    taps = (h * w).astype(np.float32)
+    k = np.arange(1, m + 1, dtype=np.float64)
+    fmax = float(taps[m]) + 2.0 * float((taps[m + 1:].astype(np.float64) * np.cos(k * math.pi)).sum())
+    return (taps.astype(np.float64) * (gain / fmax)).astype(np.float32)
+
+
+def fm_deemph(fs, tau=75e-6):
+    """analog.fm_deemph(fs, tau) -> (b0, b1, a1) of y[n] = b0 x[n] + b1 x[n-1] - a1 y[n-1] (iir_filter_ffd, fp64):
+    bilinear transform of H(s) = w_ca / (s + w_ca) with the corner prewarped (gr-analog fm_emph.py, 3.8)."""
+    w_c = 1.0 / tau
+    w_ca = 2.0 * fs * math.tan(w_c / (2.0 * fs))
+    k = -w_ca / (2.0 * fs)
+    p1 = (1.0 + k) / (1.0 - k)
+    b0 = -k / (1.0 - k)
+    return b0, b0, -p1
+
+
+def rational_resampler_design(interpolation, decimation, fractional_bw=0.4):
+    """rational_resampler_fff(interpolation, decimation, taps=None, fractional_bw=None) -> (I, D, taps): the gcd
+    reduction and design_filter of gr-filter's rational_resampler.py (Kaiser beta 7 low-pass, gain I)."""
+    g = math.gcd(int(interpolation), int(decimation))
+    interpolation, decimation = int(interpolation) // g, int(decimation) // g
+    if fractional_bw >= 0.5 or fractional_bw <= 0:
+        raise ValueError("Invalid fractional_bandwidth, must be in (0, 0.5)")
+    beta = 7.0
+    halfband = 0.5
+    rate = float(interpolation) / float(decimation)
+    if rate >= 1.0:
+        trans_width = halfband - fractional_bw
+        mid_transition_band = halfband - trans_width / 2.0
+    else:
+        trans_width = rate * (halfband - fractional_bw)
+        mid_transition_band = rate * halfband - trans_width / 2.0
+    return interpolation, decimation, low_pass(interpolation, interpolation, mid_transition_band, trans_width,
+                                               WIN_KAISER, beta)
