@@ -69,6 +69,10 @@ int rcb_memset(rcb_t* h, void* dev, int value, size_t bytes);
 int rcb_l2_flush(rcb_t* h);                     /* overwrite a > L2-sized scratch buffer */
 int rcb_timer_start(rcb_t* h);                  /* cudaEventRecord on the compute stream */
 int rcb_timer_stop(rcb_t* h, float* ms);        /* record + synchronize + elapsed */
+/* Bare pinned-host <-> device copy rate (H2D of h2d_bytes and D2H of d2h_bytes running concurrently, `iters`
+ * rounds, no kernels): the ceiling of every host-facing figure on this box.  GB/s per direction and wall seconds. */
+int rcb_copy_ceiling(rcb_t* h, size_t h2d_bytes, size_t d2h_bytes, int iters, double* h2d_gbs, double* d2h_gbs,
+                     double* wall_s);
 
 /* ---- K1: polyphase channelizer + fused FM demod -------------------------------------------------
  * Replaces  pfb.channelizer_ccf(nchans, taps, 1.0, ...)           rc_frontend/receiver.py:249-261
@@ -86,7 +90,9 @@ int rcb_pfb_reset(rcb_t* h);
  * [N][out_stride]): element (m, n) at ((n / frames) * nchans + m) * frames + n % frames.  Each channel is then
  * delivered as contiguous `frames`-sample messages - the unit a zeromq.pub_sink sends (channel.py:36) - and the
  * rows one kernel iteration writes stay within a few MB (TLB / DRAM page locality).  The output buffer must hold
- * ceil(nout / frames) * nchans * frames elements; out_stride is ignored.  Device-resident outputs only.
+ * ceil(nout / frames) * nchans * frames elements; out_stride is ignored.  Host outputs use the same layout (the
+ * internal H2D | kernel | D2H pipeline then moves whole blocks: one contiguous copy per 4 Mi-sample chunk instead of
+ * nchans row pieces); a time block must then fit one pipeline chunk (frames * nchans <= 2^22) or be the chunk.
  * frames = 8 is the kernel's native granularity (one CTA iteration = one contiguous nchans*8-element piece,
  * full-line stores: +7 % on the 1024-channel FM path) for consumers that run on the GPU themselves. */
 int rcb_pfb_set_out_block(rcb_t* h, int frames);

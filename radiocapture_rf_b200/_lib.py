@@ -83,6 +83,8 @@ _PROTOTYPES = {
     "rcb_l2_flush": (C.c_int, [_vp]),
     "rcb_timer_start": (C.c_int, [_vp]),
     "rcb_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "rcb_copy_ceiling": (C.c_int, [_vp, _sz, _sz, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                   C.POINTER(C.c_double)]),
     "rcb_pfb_config": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_float]),
     "rcb_pfb_reset": (C.c_int, [_vp]),
     "rcb_pfb_set_out_block": (C.c_int, [_vp, C.c_int]),

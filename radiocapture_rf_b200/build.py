@@ -46,3 +46,9 @@ def build_library(force=False, verbose=False, extra_flags=(), out=None):
         objs = list(ex.map(compile_one, _sources()))
     subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs)
     return out
+
+
+def build_experiments(force=True):
+    """Tuning build (never shipped, never loaded by default): -DRCB_EXPERIMENTS makes the library read RCB_PFB_VARIANT /
+    RCB_FFT_VARIANT so kernel variants can be A/B-ed on the GPU box in one visit.  Select it with RCB_LIBRARY=<path>."""
+    return build_library(force=force, extra_flags=["-DRCB_EXPERIMENTS"], out=os.path.join(_HERE, "libb200chan_exp.so"))

@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <map>
@@ -21,6 +22,7 @@
 #include "pfb_fm_tma.cuh"
 #include "pfb_fm_ws.cuh"
 #include "pfb_cl.cuh"
+#include "pfb_fm1.cuh"
 #include "internal.h"
 
 using namespace rcb;
@@ -304,7 +306,7 @@ int pfb_launch_cl_t(rcb_t* h, const float2* d_x, const float2* d_hist, size_t fr
     {
         const uint64_t dims[3] = {(uint64_t)2 * R, (uint64_t)R, (uint64_t)frames};
         const uint64_t str[2] = {(uint64_t)2 * R * 4, (uint64_t)N * 8};
-        const uint32_t box[3] = {32, (uint32_t)G::M2W, 1};  // one FIR warp's slice of a row: 16 columns x R/8 groups
+        const uint32_t box[3] = {32, (uint32_t)R, 2};  // a pair of rows of the CTA's 16 R columns
         if (!tmap_encode_f32(&tm_x, 3, d_x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
         const uint64_t hd[3] = {(uint64_t)2 * R, (uint64_t)R, (uint64_t)s.P};
         if (!tmap_encode_f32(&tm_hist, 3, d_hist, hd, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
@@ -376,6 +378,49 @@ int pfb_launch_cl(rcb_t* h, const float2* d_x, const float2* d_hist, size_t fram
     return 1;
 }
 
+// single-tap 1024-channel FM kernel with the TMA tile store (pfb_fm1.cuh).  Returns 1 when the output cannot be
+// described by a tensor map (misaligned base / stride): the caller falls back.
+int pfb_launch_fm1(rcb_t* h, const PfbParams& p0, size_t frames, float* d_fm, size_t ostride) {
+    using G = PfbFm1Geom;
+    auto& s = h->pfb;
+    const int kb = s.oblock_log2;
+    CUtensorMap tm_out;
+    int out_rank;
+    if (kb == 0) {
+        const uint64_t dims[2] = {(uint64_t)frames, (uint64_t)G::N};
+        const uint64_t str[1] = {(uint64_t)ostride * 4};
+        const uint32_t box[2] = {8, 256};
+        if (ostride < frames || !tmap_encode_f32(&tm_out, 2, d_fm, dims, str, box, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+        out_rank = 2;
+    } else {
+        const uint64_t blk = (uint64_t)1 << kb;
+        const uint64_t dims[3] = {blk, (uint64_t)G::N, ((uint64_t)frames + blk - 1) >> kb};
+        const uint64_t str[2] = {blk * 4, blk * 4 * G::N};
+        const uint32_t box[3] = {8, 256, 1};
+        if (!tmap_encode_f32(&tm_out, 3, d_fm, dims, str, box, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+        out_rank = 3;
+    }
+    static bool attr_dev[64] = {};
+    static int per_sm[64] = {};
+    const int di = h->device & 63;
+    if (!attr_dev[di]) {
+        CK(cudaFuncSetAttribute(pfb_fm1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes));
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pfb_fm1_kernel, G::THREADS, G::smem_bytes));
+        per_sm[di] = std::max(nb, 1);
+        attr_dev[di] = true;
+    }
+    PfbParams q = p0;
+    q.twiddle = s.d_tw_tma;
+    q.work_counter = s.d_counter;
+    const int NI = (int)((frames + G::FPI - 1) / G::FPI);
+    const int grid = std::max(1, std::min(NI, per_sm[di] * h->sm_count));
+    CK(cudaMemsetAsync(s.d_counter, 0, sizeof(int), h->stream));
+    pfb_fm1_kernel<<<grid, G::THREADS, G::smem_bytes, h->stream>>>(tm_out, q, out_rank);
+    CKL(h);
+    return RCB_OK;
+}
+
 // fast kernel dispatch: taps per arm (1, 2, 4, 8, 16) x output mode
 template <int R, int MODE>
 int pfb_launch_tma_pm(rcb_t* h, const PfbParams& p, bool q) {
@@ -437,6 +482,23 @@ int pfb_launch_fast(rcb_t* h, const PfbParams& p, bool q) {
     return RCB_EUNSUPPORTED;
 }
 
+void pfb_free_stages(rcb_t* h) {
+    auto& s = h->pfb;
+    cudaStreamSynchronize(h->stream);
+    cudaStreamSynchronize(h->s_in);
+    cudaStreamSynchronize(h->s_out);
+    for (auto& st : s.st) {
+        cudaFree(st.d_in);
+        cudaFree(st.d_fm);
+        cudaFree(st.d_iq);
+        if (st.ev_in) cudaEventDestroy(st.ev_in);
+        if (st.ev_k) cudaEventDestroy(st.ev_k);
+        if (st.ev_out) cudaEventDestroy(st.ev_out);
+        st = Stage{};
+    }
+    s.chunk_frames = 0;
+}
+
 void pfb_free(rcb_t* h) {
     auto& s = h->pfb;
     cudaFree(s.d_taps);
@@ -460,15 +522,7 @@ void pfb_free(rcb_t* h) {
     s.d_zeros = nullptr;
     cudaFree(s.d_counter);
     s.d_counter = nullptr;
-    for (auto& st : s.st) {
-        cudaFree(st.d_in);
-        cudaFree(st.d_fm);
-        cudaFree(st.d_iq);
-        if (st.ev_in) cudaEventDestroy(st.ev_in);
-        if (st.ev_k) cudaEventDestroy(st.ev_k);
-        if (st.ev_out) cudaEventDestroy(st.ev_out);
-        st = Stage{};
-    }
+    pfb_free_stages(h);
     s.d_taps = nullptr;
     s.d_tw = nullptr;
     s.d_hist[0] = s.d_hist[1] = nullptr;
@@ -497,7 +551,14 @@ int pfb_run_device(rcb_t* h, const float2* d_x, size_t frames, float2* d_iq, flo
     p.N = s.N;
     p.gain = s.gain;
     int cl_rc = 1;
-    if (s.use_cl) {
+    // 1024 channels, one tap per arm: the TMA-store variant of the round-1 headline kernel (2 CTAs / SM, 16 FFT warps);
+    // everything else with FM-only output on N = 256 / 1024: the cluster / register-window kernel
+    // (experiment builds: RCB_PFB_VARIANT=21 runs the cluster kernel for one tap per arm too)
+    if (s.use_cl && s.R == 32 && s.PT == 1 && s.variant != 21) {
+        cl_rc = pfb_launch_fm1(h, p, frames, d_fm, ostride);
+        if (cl_rc != RCB_OK && cl_rc != 1) return cl_rc;
+    }
+    if (cl_rc == 1 && s.use_cl) {
         cl_rc = pfb_launch_cl(h, d_x, s.d_hist[s.hist_cur], frames, d_fm, ostride);
         if (cl_rc != RCB_OK && cl_rc != 1) return cl_rc;
     }
@@ -548,6 +609,10 @@ int pfb_ensure_stages(rcb_t* h) {
     if (s.chunk_frames) return RCB_OK;
     size_t cf = std::max<size_t>(8, kChunkSamples / (size_t)s.N);
     cf = (cf + 31) / 32 * 32;
+    if (s.oblock_log2) {  // whole time blocks per chunk (a block larger than the default chunk becomes the chunk)
+        const size_t blk = (size_t)1 << s.oblock_log2;
+        cf = std::max(blk, cf / blk * blk);
+    }
     for (auto& st : s.st) {
         CK(cudaMalloc(&st.d_in, cf * s.N * sizeof(float2)));
         if (s.mode & RCB_OUT_FM) CK(cudaMalloc(&st.d_fm, cf * s.N * sizeof(float)));
@@ -766,6 +831,80 @@ extern "C" int rcb_timer_stop(rcb_t* h, float* ms) {
     return RCB_OK;
 }
 
+// Bare host<->device copy rate of this handle's device: `iters` rounds of an H2D copy of h2d_bytes and a D2H copy of
+// d2h_bytes running CONCURRENTLY on the two copy streams from / to pinned memory, no kernels.  This is the ceiling of
+// every host-facing (e2e) figure: bench.py reports e2e as a fraction of it.
+extern "C" int rcb_copy_ceiling(rcb_t* h, size_t h2d_bytes, size_t d2h_bytes, int iters, double* h2d_gbs, double* d2h_gbs,
+                                double* wall_s) {
+    if (!h || iters < 1 || (!h2d_bytes && !d2h_bytes)) return RCB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    void *hin = nullptr, *hout = nullptr, *din = nullptr, *dout = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, f0 = nullptr, f1 = nullptr;
+    int rc = RCB_OK;
+    auto cleanup = [&]() {
+        if (hin) cudaFreeHost(hin);
+        if (hout) cudaFreeHost(hout);
+        cudaFree(din);
+        cudaFree(dout);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (f0) cudaEventDestroy(f0);
+        if (f1) cudaEventDestroy(f1);
+    };
+#define CCK(call)                                   \
+    do {                                            \
+        cudaError_t e__ = (call);                   \
+        if (e__ != cudaSuccess) {                   \
+            rc = fail_cuda(h, e__, #call);          \
+            cleanup();                              \
+            return rc;                              \
+        }                                           \
+    } while (0)
+    if (h2d_bytes) {
+        CCK(cudaHostAlloc(&hin, h2d_bytes, cudaHostAllocDefault));
+        memset(hin, 1, h2d_bytes);  // first touch on the calling thread's NUMA node
+        CCK(cudaMalloc(&din, h2d_bytes));
+    }
+    if (d2h_bytes) {
+        CCK(cudaHostAlloc(&hout, d2h_bytes, cudaHostAllocDefault));
+        memset(hout, 1, d2h_bytes);
+        CCK(cudaMalloc(&dout, d2h_bytes));
+    }
+    CCK(cudaEventCreate(&e0));
+    CCK(cudaEventCreate(&e1));
+    CCK(cudaEventCreate(&f0));
+    CCK(cudaEventCreate(&f1));
+    // one untimed round, then the timed ones
+    if (h2d_bytes) CCK(cudaMemcpyAsync(din, hin, h2d_bytes, cudaMemcpyHostToDevice, h->s_in));
+    if (d2h_bytes) CCK(cudaMemcpyAsync(hout, dout, d2h_bytes, cudaMemcpyDeviceToHost, h->s_out));
+    CCK(cudaStreamSynchronize(h->s_in));
+    CCK(cudaStreamSynchronize(h->s_out));
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    CCK(cudaEventRecord(e0, h->s_in));
+    CCK(cudaEventRecord(f0, h->s_out));
+    for (int i = 0; i < iters; ++i) {
+        if (h2d_bytes) CCK(cudaMemcpyAsync(din, hin, h2d_bytes, cudaMemcpyHostToDevice, h->s_in));
+        if (d2h_bytes) CCK(cudaMemcpyAsync(hout, dout, d2h_bytes, cudaMemcpyDeviceToHost, h->s_out));
+    }
+    CCK(cudaEventRecord(e1, h->s_in));
+    CCK(cudaEventRecord(f1, h->s_out));
+    CCK(cudaStreamSynchronize(h->s_in));
+    CCK(cudaStreamSynchronize(h->s_out));
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    float ms_in = 0.f, ms_out = 0.f;
+    CCK(cudaEventElapsedTime(&ms_in, e0, e1));
+    CCK(cudaEventElapsedTime(&ms_out, f0, f1));
+    if (h2d_gbs) *h2d_gbs = (h2d_bytes && ms_in > 0) ? (double)h2d_bytes * iters / (ms_in * 1e-3) / 1e9 : 0.0;
+    if (d2h_gbs) *d2h_gbs = (d2h_bytes && ms_out > 0) ? (double)d2h_bytes * iters / (ms_out * 1e-3) / 1e9 : 0.0;
+    if (wall_s) *wall_s = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    h->stats.h2d_bytes += h2d_bytes * (size_t)(iters + 1);
+    h->stats.d2h_bytes += d2h_bytes * (size_t)(iters + 1);
+#undef CCK
+    cleanup();
+    return RCB_OK;
+}
+
 // =================================================================================================
 // K1  PFB + FM
 // =================================================================================================
@@ -908,12 +1047,15 @@ extern "C" int rcb_pfb_set_out_block(rcb_t* h, int frames) {
     if (!h) return RCB_EINVAL;
     if (!h->pfb.configured) return RCB_ESTATE;
     if (frames == 0) {
+        if (h->pfb.oblock_log2) pfb_free_stages(h);
         h->pfb.oblock_log2 = 0;
         return RCB_OK;
     }
     if (frames < 8 || (frames & (frames - 1))) return RCB_EINVAL;  // power of two >= 8
+    if (frames > (1 << 24)) return RCB_ERANGE;
     int k = 0;
     while ((1 << k) < frames) ++k;
+    if (k != h->pfb.oblock_log2) pfb_free_stages(h);  // the host pipeline's chunk is a whole number of blocks
     h->pfb.oblock_log2 = k;
     return RCB_OK;
 }
@@ -953,10 +1095,14 @@ extern "C" int rcb_pfb_process(rcb_t* h, const void* iq, size_t nsamples, int in
     }
 
     // host-facing path: chunked 3-stage pipeline  H2D (s_in) | kernel (stream) | D2H (s_out)
-    if (s.oblock_log2) return RCB_ESTATE;  // the blocked layout is for device-resident outputs only
+    // Blocked layout (rcb_pfb_set_out_block) with host outputs: the pipeline chunk is a whole number of time blocks, a
+    // chunk's staging buffer is then bit-for-bit the piece of the host buffer it belongs to, and the D2H is ONE
+    // contiguous copy per chunk (instead of a 2-D copy of nchans row pieces).
+    const size_t blk = s.oblock_log2 ? ((size_t)1 << s.oblock_log2) : 0;
     int rc = pfb_ensure_stages(h);
     if (rc) return rc;
     const size_t cf = s.chunk_frames;
+    if (blk && (cf % blk)) return RCB_EUNSUPPORTED;
     size_t done = 0;
     int si = 0;
     while (done < frames) {
@@ -982,6 +1128,10 @@ extern "C" int rcb_pfb_process(rcb_t* h, const void* iq, size_t nsamples, int in
             d_iq = st.d_iq;
             d_fm = st.d_fm;
             dstride = cf;
+        } else if (blk) {  // device output, blocked: this chunk starts at block done / blk
+            d_iq = out_iq ? (float2*)out_iq + (done / blk) * s.N * blk : nullptr;
+            d_fm = out_fm ? (float*)out_fm + (done / blk) * s.N * blk : nullptr;
+            dstride = out_stride;
         } else {
             d_iq = out_iq ? (float2*)out_iq + done : nullptr;
             d_fm = out_fm ? (float*)out_fm + done : nullptr;
@@ -992,15 +1142,27 @@ extern "C" int rcb_pfb_process(rcb_t* h, const void* iq, size_t nsamples, int in
         CK(cudaEventRecord(st.ev_k, h->stream));
         if (out_mem == RCB_MEM_HOST) {
             CK(cudaStreamWaitEvent(h->s_out, st.ev_k, 0));
-            if (s.mode & RCB_OUT_FM) {
-                CK(cudaMemcpy2DAsync((float*)out_fm + done, out_stride * sizeof(float), st.d_fm, cf * sizeof(float),
-                                     f * sizeof(float), s.N, cudaMemcpyDeviceToHost, h->s_out));
-                h->stats.d2h_bytes += f * s.N * sizeof(float);
-            }
-            if (s.mode & RCB_OUT_IQ) {
-                CK(cudaMemcpy2DAsync((float2*)out_iq + done, out_stride * sizeof(float2), st.d_iq, cf * sizeof(float2),
-                                     f * sizeof(float2), s.N, cudaMemcpyDeviceToHost, h->s_out));
-                h->stats.d2h_bytes += f * s.N * sizeof(float2);
+            if (blk) {
+                const size_t nb = (f + blk - 1) / blk, off = (done / blk) * s.N * blk, cnt = nb * s.N * blk;
+                if (s.mode & RCB_OUT_FM) {
+                    CK(cudaMemcpyAsync((float*)out_fm + off, st.d_fm, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+                    h->stats.d2h_bytes += cnt * sizeof(float);
+                }
+                if (s.mode & RCB_OUT_IQ) {
+                    CK(cudaMemcpyAsync((float2*)out_iq + off, st.d_iq, cnt * sizeof(float2), cudaMemcpyDeviceToHost, h->s_out));
+                    h->stats.d2h_bytes += cnt * sizeof(float2);
+                }
+            } else {
+                if (s.mode & RCB_OUT_FM) {
+                    CK(cudaMemcpy2DAsync((float*)out_fm + done, out_stride * sizeof(float), st.d_fm, cf * sizeof(float),
+                                         f * sizeof(float), s.N, cudaMemcpyDeviceToHost, h->s_out));
+                    h->stats.d2h_bytes += f * s.N * sizeof(float);
+                }
+                if (s.mode & RCB_OUT_IQ) {
+                    CK(cudaMemcpy2DAsync((float2*)out_iq + done, out_stride * sizeof(float2), st.d_iq, cf * sizeof(float2),
+                                         f * sizeof(float2), s.N, cudaMemcpyDeviceToHost, h->s_out));
+                    h->stats.d2h_bytes += f * s.N * sizeof(float2);
+                }
             }
             CK(cudaEventRecord(st.ev_out, h->s_out));
         }

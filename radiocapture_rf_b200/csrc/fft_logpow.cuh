@@ -435,13 +435,15 @@ inline int fft_config(FftState& s, int L, const float* window, int avg, cudaStre
     s.L1 = r1 * r1;
     s.L2 = r2 * r2;
     s.avg = avg;
+    // sub-batch: keep scratch (8 B) + vals (4 B) per sample under ~48 MB so they stay in L2
+    size_t budget_mb = 48;
+#ifdef RCB_EXPERIMENTS  // tuning builds only (radiocapture_rf_b200.build.build_experiments): never in the shipped library
     if (const char* e = getenv("RCB_FFT_VARIANT")) {
         s.cols_tma = (atoi(e) != 1);
         s.rows_k1 = (atoi(e) == 3);
     }
-    // sub-batch: keep scratch (8 B) + vals (4 B) per sample under ~48 MB so they stay in L2
-    size_t budget_mb = 48;
     if (const char* e = getenv("RCB_FFT_SCRATCH_MB")) budget_mb = (size_t)std::max(1, atoi(e));
+#endif
     s.sb = (int)std::max<size_t>(1, std::min<size_t>((budget_mb << 20) / ((size_t)L * 12), 4096));
     FCK(cudaMalloc(&s.d_window, sizeof(float) * L));
     FCK(cudaMemcpyAsync(s.d_window, window, sizeof(float) * L, cudaMemcpyHostToDevice, st));

@@ -72,11 +72,10 @@ struct PfbClGeom {
     static constexpr int FPI = 16;     // frames per iteration
     static constexpr int THREADS = 512;
     static constexpr int CPF = NC / 256;  // columns per FIR thread = channel rows per demod thread
-    static constexpr int RS = 8;          // raw-row ring slots PER FIR WARP (each warp streams its own 16 x R/8 columns)
+    static constexpr int RS = 8;          // raw-row ring: 4 slots of a row PAIR (one TMA box = 2 rows of the CTA's columns)
     static constexpr int M2W = R / 8;     // m2 rows of the tile owned (demodulated and stored) by one FIR warp = jj
                                           //   rows of a frame owned by one FIR warp
     static constexpr size_t row_bytes = (size_t)NC * 8;
-    static constexpr size_t slice_bytes = row_bytes / 8;         // one FIR warp's part of a row
     static constexpr size_t tile_bytes = (size_t)FPI * NC * 4;  // [R m2][16 m1][16 t] floats
     static constexpr size_t raw_bytes = RS * row_bytes;
     static constexpr size_t hset_bytes = 8 * row_bytes;         // one 8-frame buffer set
@@ -95,8 +94,8 @@ enum {  // mbarrier slots (8 B each) behind off_bar
     CLB_T_FULL = 14,      // [8]  my half of the transpose buffer of warp w is complete (local arrive + peer's st.async bytes)
     CLB_RING_FULL = 22,   // [2]  FFT warps (8) -> demod: the 16 angle columns of an iteration are in the tile
     CLB_RING_FREE = 24,   // [2]  demod warps (8) -> FFT: the tile has been read by the TMA stores
-    CLB_RAW_FULL = 26,    // [8 warps][RS]  TMA -> the FIR warp that owns the slice
-    CLB_COUNT = 26 + 8 * 8
+    CLB_RAW_FULL = 26,    // [4]  TMA -> FIR warps: a row pair has landed
+    CLB_COUNT = 30        // (+ 4 int consumer counters of the row-pair slots behind the barriers)
 };
 
 template <int R, int PT>
@@ -114,6 +113,7 @@ __global__ void __launch_bounds__(512, 1)
     const uint32_t a_bar = base + (uint32_t)G::off_bar;
     unsigned char* gbase = smem_cl_raw + (base - smem_addr_u32(smem_cl_raw));
     auto bar = [&](int i) { return a_bar + 8u * (uint32_t)i; };
+    int* raw_cnt = reinterpret_cast<int*>(gbase + G::off_bar + 8 * CLB_COUNT);  // consumers (FIR warps) done with a slot
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = (CS == 2) ? cluster_ctarank() : 0u;
@@ -134,7 +134,10 @@ __global__ void __launch_bounds__(512, 1)
         for (int i = tid; i < (R / 2) * 16; i += G::THREADS) dst[i] = src[i];
     }
     if (tid == 0) {
-        for (int i = 0; i < 8 * RS; ++i) mbar_init_a(bar(CLB_RAW_FULL + i), 1);
+        for (int i = 0; i < RS / 2; ++i) {
+            mbar_init_a(bar(CLB_RAW_FULL + i), 1);
+            raw_cnt[i] = 0;
+        }
         for (int i = 0; i < 3; ++i) {
             mbar_init_a(bar(CLB_SET_FULL + i), 8);
             mbar_init_a(bar(CLB_SET_EMPTY + i), 4);
@@ -178,21 +181,20 @@ __global__ void __launch_bounds__(512, 1)
 #pragma unroll
         for (int q = 0; q < CPF; ++q) prev[q] = 0.f;
 
-        // this warp's private ring of raw row slices: lane 0 keeps RS rows in flight, refilling a slot as soon as the warp
-        // has read it (no coupling to the other warps, and the prefetch keeps running while the warp demodulates)
-        const uint32_t a_wraw = a_raw + (uint32_t)warp * (uint32_t)(RS * G::slice_bytes);
-        const int rbar0 = CLB_RAW_FULL + warp * RS;
-        auto issue_row = [&](int g, int slot) {  // row g of the run
+        // shared ring of 4 row pairs.  Each FIR warp counts itself off a slot after reading it (shared-memory atomic);
+        // the LAST warp to do so refills the slot with the pair 8 rows ahead - one TMA per two rows and CTA, issued by
+        // whichever warp is slowest, so no warp ever waits for another one before it can go on.
+        auto issue_pair = [&](int g, int slot) {  // rows g, g + 1 of the run (g even)
             const long long f = fbase + g;
-            const uint32_t dst = a_wraw + (uint32_t)slot * (uint32_t)G::slice_bytes;
-            mbar_expect_tx_a(bar(rbar0 + slot), (uint32_t)G::slice_bytes);
-            if (f >= 0 || f < -(long long)p.P)
-                tma_load_3d(dst, &tm_x, 32 * (int)rank, M2W * warp, (f >= 0) ? (int)f : -1, bar(rbar0 + slot));
-            else
-                tma_load_3d(dst, &tm_hist, 32 * (int)rank, M2W * warp, (int)(f + p.P), bar(rbar0 + slot));
+            const uint32_t dst = a_raw + (uint32_t)slot * (uint32_t)(2 * G::row_bytes);
+            mbar_expect_tx_a(bar(CLB_RAW_FULL + slot), (uint32_t)(2 * G::row_bytes));
+            if (f >= 0)
+                tma_load_3d(dst, &tm_x, 32 * (int)rank, 0, (int)f, bar(CLB_RAW_FULL + slot));  // rows >= T: zero filled
+            else  // streaming history; rows before it are out of bounds of the hist tensor = zero filled
+                tma_load_3d(dst, &tm_hist, 32 * (int)rank, 0, (int)(f + p.P), bar(CLB_RAW_FULL + slot));
         };
-        if (lane == 0) {
-            for (int g = 0; g < RS && g < nrows; ++g) issue_row(g, g);
+        if (tid == 0) {
+            for (int g = 0; g < RS && g < nrows; g += 2) issue_pair(g, g >> 1);
         }
         // demod of iteration j (runs one iteration behind the FIR): in place in tile j & 1, then this warp's slice of
         // the tile goes out with one TMA store
@@ -262,59 +264,74 @@ __global__ void __launch_bounds__(512, 1)
             uint32_t a_set = 0;
             int sb = 0;
 #pragma unroll
-            for (int t = 0; t < 16; ++t) {
+            for (int t = 0; t < 16; t += 2) {
                 if ((t & 7) == 0) {  // next 8-frame set of the ring of three
                     const int h = 2 * k + (t >> 3);
                     sb = h % 3;
                     if (h >= 3) mbar_wait_a(bar(CLB_SET_EMPTY + sb), (uint32_t)((h / 3 - 1) & 1));
                     a_set = a_sets + (uint32_t)sb * (uint32_t)G::hset_bytes;
                 }
-                const int rs = t & (RS - 1);                       // static: the iteration is unrolled, RS divides 16
-                const uint32_t rpar = (uint32_t)((k * (16 / RS) + t / RS) & 1);
-                mbar_wait_a(bar(rbar0 + rs), rpar);
-                const uint32_t src = a_wraw + (uint32_t)rs * (uint32_t)G::slice_bytes + (uint32_t)lane * (8u * CPF);
-                float2 x[CPF];
-                if constexpr (CPF == 2) {
-                    float4 v;
-                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src));
-                    x[0] = make_float2(v.x, v.y);
-                    x[1] = make_float2(v.z, v.w);
-                } else {
-                    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(x[0].x), "=f"(x[0].y) : "r"(src));
+                const int ps = (t >> 1) & 3;                                 // static: the iteration is unrolled
+                mbar_wait_a(bar(CLB_RAW_FULL + ps), (uint32_t)((2 * k + (t >> 3)) & 1));
+                const uint32_t src = a_raw + (uint32_t)ps * (uint32_t)(2 * G::row_bytes) + (uint32_t)ft * (8u * CPF);
+                float2 x[2][CPF];
+#pragma unroll
+                for (int r2 = 0; r2 < 2; ++r2) {
+                    if constexpr (CPF == 2) {
+                        float4 v;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                                     : "r"(src + (uint32_t)r2 * (uint32_t)G::row_bytes));
+                        x[r2][0] = make_float2(v.x, v.y);
+                        x[r2][1] = make_float2(v.z, v.w);
+                    } else {
+                        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];"
+                                     : "=f"(x[r2][0].x), "=f"(x[r2][0].y)
+                                     : "r"(src + (uint32_t)r2 * (uint32_t)G::row_bytes));
+                    }
                 }
                 __syncwarp();
-                if (lane == 0) {  // the slot has been read by the whole warp: refill it with the row RS ahead
+                // count this warp off the slot now, look at the answer after the arithmetic below (a shared-memory atomic
+                // with a used result is a ~60-cycle stall: profiles/r02_pfb_cl_v4_p16_summary.txt)
+                int seen = 0;
+                if (lane == 0) seen = atomicAdd(&raw_cnt[ps], 1);
+#pragma unroll
+                for (int r2 = 0; r2 < 2; ++r2) {
+                    const int tt = t + r2;
+                    float2 y[CPF];
+#pragma unroll
+                    for (int q = 0; q < CPF; ++q) {
+                        win[q][tt % PT] = x[r2][q];
+                        if constexpr (PT == 1) {
+                            y[q] = p2muls(x[r2][q], hk[q][0]);
+                        } else {
+                            // two interleaved partial sums (even / odd taps) keep four FFMA2 chains per thread in flight
+                            float2 a0 = p2muls(win[q][tt % PT], hk[q][0]);
+                            float2 a1 = p2muls(win[q][(tt + PT - 1) % PT], hk[q][1]);
+#pragma unroll
+                            for (int kk = 2; kk < PT; kk += 2) {
+                                a0 = p2fmas(win[q][(tt + PT - kk) % PT], hk[q][kk], a0);
+                                a1 = p2fmas(win[q][(tt + PT - kk - 1) % PT], hk[q][kk + 1], a1);
+                            }
+                            y[q] = p2add(a0, a1);
+                        }
+                    }
+                    const uint32_t dst = a_set + (uint32_t)(tt & 7) * (uint32_t)G::row_bytes + (uint32_t)ft * (8u * CPF);
+                    if constexpr (CPF == 2) {
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "f"(y[0].x), "f"(y[0].y), "f"(y[1].x), "f"(y[1].y) : "memory");
+                    } else {
+                        asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(dst), "f"(y[0].x), "f"(y[0].y) : "memory");
+                    }
+                }
+                if (lane == 0 && seen == 7) {  // every FIR warp has read the pair: this warp refills the slot
+                    raw_cnt[ps] = 0;
                     const int gn = k * 16 + t + RS;
                     if (gn < nrows) {
                         fence_async_smem();
-                        issue_row(gn, rs);
+                        issue_pair(gn, ps);
                     }
                 }
-                float2 y[CPF];
-#pragma unroll
-                for (int q = 0; q < CPF; ++q) {
-                    win[q][t % PT] = x[q];
-                    if constexpr (PT == 1) {
-                        y[q] = p2muls(x[q], hk[q][0]);
-                    } else {
-                        // two interleaved partial sums (even / odd taps) keep four FFMA2 chains per thread in flight
-                        float2 a0 = p2muls(win[q][t % PT], hk[q][0]);
-                        float2 a1 = p2muls(win[q][(t + PT - 1) % PT], hk[q][1]);
-#pragma unroll
-                        for (int kk = 2; kk < PT; kk += 2) {
-                            a0 = p2fmas(win[q][(t + PT - kk) % PT], hk[q][kk], a0);
-                            a1 = p2fmas(win[q][(t + PT - kk - 1) % PT], hk[q][kk + 1], a1);
-                        }
-                        y[q] = p2add(a0, a1);
-                    }
-                }
-                const uint32_t dst = a_set + (uint32_t)(t & 7) * (uint32_t)G::row_bytes + (uint32_t)ft * (8u * CPF);
-                if constexpr (CPF == 2) {
-                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "f"(y[0].x), "f"(y[0].y), "f"(y[1].x), "f"(y[1].y) : "memory");
-                } else {
-                    asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(dst), "f"(y[0].x), "f"(y[0].y) : "memory");
-                }
-                if ((t & 7) == 7) {
+                if ((t & 7) == 6) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive_a(bar(CLB_SET_FULL + sb));
                 }

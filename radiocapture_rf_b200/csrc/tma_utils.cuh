@@ -93,17 +93,16 @@ __device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
     asm volatile("{\n\t.reg .b64 t;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
                  : "memory");
 }
-// (the suspend-time hint lets the hardware park the warp instead of returning to a spin loop: the try_wait / branch
-// pairs of short polls were 25 % of the issued instructions of pfb_cl_kernel, profiles/r02_pfb_cl_v2_*)
+// (a suspend-time hint operand was tried: ptxas then wraps the TRYWAIT in a NANOSLEEP loop - more instructions, slower)
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
     uint32_t done;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity), "r"(0x989680u)
+            : "r"(bar), "r"(parity)
             : "memory");
     } while (!done);
 }

@@ -169,6 +169,15 @@ class Engine(object):
         return out[0] if x.ndim == 1 else out
 
 
+def copy_ceiling(engine, h2d_bytes, d2h_bytes, iters=4):
+    """Bare pinned host <-> device copy rate of the engine's GPU (both directions concurrently, no kernels):
+    returns (h2d GB/s, d2h GB/s, wall seconds)."""
+    a, b, w = C.c_double(0), C.c_double(0), C.c_double(0)
+    check(engine.lib.rcb_copy_ceiling(engine.h, int(h2d_bytes), int(d2h_bytes), int(iters), C.byref(a), C.byref(b),
+                                      C.byref(w)), "rcb_copy_ceiling", engine.h)
+    return a.value, b.value, w.value
+
+
 class PfbChannelizer(object):
     """K1: N-channel critically sampled polyphase channelizer with fused FM demod."""
 
@@ -197,15 +206,19 @@ class PfbChannelizer(object):
         return np.ascontiguousarray(a.transpose(1, 0, 2).reshape(nchans, nb * block)[:, :frames])
 
     def process(self, iq, out_iq=None, out_fm=None):
-        """iq: complex64 host array, len multiple of nchans.  Returns (iq_out [N][T] or None, fm_out or None)."""
+        """iq: complex64 host array, len multiple of nchans.  Returns (iq_out, fm_out) (None where not produced):
+        [N][T] arrays, or - after set_out_block(b) - [ceil(T / b)][N][b] arrays (each channel as contiguous b-sample
+        messages; `unblock` gives the [N][T] view back)."""
         iq = np.ascontiguousarray(iq, dtype=np.complex64)
         if len(iq) % self.nchans:
             raise ValueError("nsamples must be a multiple of nchans")
         t = len(iq) // self.nchans
+        b = getattr(self, "out_block", 0)
+        shape = (-(-t // b), self.nchans, b) if b else (self.nchans, t)
         if (self.out_mask & OUT_IQ) and out_iq is None:
-            out_iq = np.empty((self.nchans, t), dtype=np.complex64)
+            out_iq = np.empty(shape, dtype=np.complex64)
         if (self.out_mask & OUT_FM) and out_fm is None:
-            out_fm = np.empty((self.nchans, t), dtype=np.float32)
+            out_fm = np.empty(shape, dtype=np.float32)
         nout = C.c_size_t(0)
         check(self.e.lib.rcb_pfb_process(
             self.e.h, iq.ctypes.data, len(iq), MEM_HOST,

@@ -126,7 +126,32 @@ def test_pfb_cluster_kernel_unaligned_output_falls_back(engine):
     assert ch.process_device(d_in, len(x), None, d_fm, stride) == frames
     engine.sync()
     fm = engine.to_host(d_fm, (n, stride), np.float32)[:, :frames]
-    np.testing.assert_allclose(fm, fm_ref, rtol=0, atol=2e-5 * 5.0)
+    # different kernel, different (equally valid) float32 rounding: same parity bar as against the oracle
+    for m in range(1, n, 2):
+        assert _fm_err(fm[m], fm_ref[m].astype(np.float64), 5.0) <= 2e-5
+    assert _fm_err(fm, fm_ref.astype(np.float64), 5.0) <= 2e-4
+
+
+def test_pfb_host_pipeline_blocked_layout_spans_chunks(engine):
+    """Host in / host out through the chunked H2D | kernel | D2H pipeline with the blocked output layout: several
+    4 Mi-sample chunks, a ragged last block, against the plain layout of the same stream."""
+    n, frames, block = 1024, 3 * 4096 + 1000 + 5, 1024
+    taps = fd.pfb_prototype(4, 64)
+    x, _ = synth.pfb_stream(n * 2048, 1.0e6 * n / 4.0, n, 41, active_every=8)
+    x = np.tile(x, -(-frames // 2048))[:n * frames]
+    ch = PfbChannelizer(engine, n, taps, OUT_FM, 5.0)
+    _, ref = ch.process(x)
+    ch.reset()
+    ch.set_out_block(block)
+    _, got = ch.process(x)
+    assert got.shape == (-(-frames // block), n, block)
+    assert np.array_equal(PfbChannelizer.unblock(got, n, frames, block), ref)
+
+
+def test_copy_ceiling_reports_both_directions(engine):
+    from radiocapture_rf_b200.engine import copy_ceiling
+    h2d, d2h, wall = copy_ceiling(engine, 64 << 20, 32 << 20, iters=3)
+    assert h2d > 1.0 and d2h > 1.0 and wall > 0
 
 
 def test_pfb_cfg3_literal_256_taps_1024_channels(engine):
@@ -230,8 +255,13 @@ def test_pfb_blocked_device_output_layout(engine, n, tpa, mode, block):
     if mode & OUT_IQ:
         iq = PfbChannelizer.unblock(engine.to_host(d_iq, (nb * n * block,), np.complex64), n, frames, block)
         assert np.array_equal(iq, iq_ref)
-    with pytest.raises(Exception):
-        ch.process(x)            # host outputs are plain channel-major only
+    # host outputs use the same blocked layout (one contiguous D2H per pipeline chunk)
+    h_iq, h_fm = ch.process(x) if (ch.reset() or True) else (None, None)
+    if mode & OUT_FM:
+        assert h_fm.shape == (nb, n, block)
+        assert np.array_equal(PfbChannelizer.unblock(h_fm, n, frames, block), fm_ref)
+    if mode & OUT_IQ:
+        assert np.array_equal(PfbChannelizer.unblock(h_iq, n, frames, block), iq_ref)
     ch.set_out_block(0)
     with pytest.raises(Exception):
         ch.set_out_block(12)     # must be a power of two >= 8
