@@ -12,7 +12,11 @@ the fused quadrature FM demod, 2^28 complex64 samples per step resident in HBM (
   e2e        same metric through the C ABI with pinned HOST buffers (H2D + kernel + D2H pipelined inside)
   roofline   algorithmic bytes (12 B/sample: 8 read + 4 FM written) / kernel time vs measured HBM peak
   cpu_baseline  the GR-semantics C restatement (oracle/gr_cpu.c, kind "port") on a bounded sample
-  also       the same kernel at 16 taps/arm (reference-like prototype) for context
+  also       all three readings of "256-tap / 1024-channel" (256-tap prototype = 1 tap/arm [the headline,
+             an FFT-only upper bound: 768 of the 1024 arms are zero], 16 taps/arm [the reference's own filter shape],
+             256 taps/arm [compute bound, also quoted against the fp32 roofline]), the plain [N][T] output layout,
+             the same launch sustained for >= 2.5 s with clocks / power, fused integer ingest (sc16 / u8), and
+             BASELINE config 5 (8 x 256-channel streams per GPU)
 N > 1: one process per GPU (torchrun), independent streams per rank, no data-path collective ("weak").
 `--impl reference` times the CPU restatement only (GNU Radio itself is not installable here).
 """
@@ -37,6 +41,8 @@ WORKLOADS = {
                  desc="cfg3: 1024-channel PFB, 256-tap prototype, fused FM demod, one 200 Msps stream"),
     "cfg3_p16": dict(nchans=1024, ntaps=16384, out="fm", log2n=28, streams=1,
                      desc="cfg3 variant: 1024-channel PFB, 16 taps/arm (16384-tap prototype), fused FM demod"),
+    "cfg3_p256": dict(nchans=1024, ntaps=262144, out="fm", log2n=26, streams=1,
+                      desc="cfg3 variant: 1024-channel PFB, 256 taps/arm (262144-tap prototype), fused FM demod"),
     "cfg3_p8": dict(nchans=1024, ntaps=8192, out="fm", log2n=28, streams=1,
                     desc="cfg3 variant: 1024-channel PFB, 8 taps/arm (8192-tap prototype), fused FM demod"),
     "cfg3_iqfm_p16": dict(nchans=1024, ntaps=16384, out="iq+fm", log2n=27, streams=1,
@@ -66,6 +72,46 @@ def load_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def kernel_name(wl):
+    """The kernel that dominates a step of this workload (the dispatch of rcb_pfb_process / rcb_ddc_process /
+    rcb_fft_process, csrc/b200chan.cu)."""
+    cfg = WORKLOADS[wl]
+    if cfg.get("kind") == "fft":
+        return "fft_cols_tma_kernel+fft_rows_kernel"
+    if cfg.get("kind") == "ddc":
+        return "ddc_tile_kernel"
+    n, tpa = cfg["nchans"], -(-cfg["ntaps"] // cfg["nchans"])
+    pt = 1
+    while pt < tpa:
+        pt *= 2
+    if cfg["out"] == "fm" and n == 1024:
+        if pt == 1:
+            return "pfb_fm1_kernel"
+        if pt <= 8:
+            return "pfb_cl_kernel<32,%d>" % pt
+        if pt == 16:
+            return "pfb_fm_ws_kernel<32,16>"
+        return "pfb_fm_kernel<32>"
+    if n == 1024 and pt >= 8:
+        return "pfb_fm_ws_kernel<32,%d,IQ>" % pt
+    r = {64: 8, 256: 16, 1024: 32}[n]
+    return "pfb_fm_tma_kernel<%d,PT=%d,%s>" % (r, pt, cfg["out"]) if pt <= 16 else "pfb_fm_kernel<%d>" % r
+
+
+def config_dict(wl, world, out_block, log2n=None):
+    """The `config` object of the JSON line - identical for the b200 and the reference arm."""
+    cfg = WORKLOADS[wl]
+    n = 1 << (log2n or cfg["log2n"])
+    blocked = bool(out_block) and cfg.get("kind") is None
+    return {"workload": cfg["desc"], "nchans": cfg["nchans"], "ntaps": cfg["ntaps"], "out": cfg["out"],
+            "samples_per_step_per_gpu": n * cfg["streams"], "streams_per_gpu": cfg["streams"],
+            "channels_out": cfg["nchans"] * cfg["streams"] * world,
+            "out_layout": ("channel-major in blocks of %d frames (rcb_pfb_set_out_block), device and host outputs" % out_block)
+            if blocked else "channel-major [N][T]",
+            "l2": "inputs (%d MiB/step) larger than L2, no flush" % (n * cfg["streams"] * 8 >> 20),
+            "parallelism": "independent streams, %d GPU(s), no collective" % world}
 
 
 def load_traffic(workload):
@@ -110,6 +156,17 @@ class ClockSampler(object):
         except Exception:
             pass
 
+    def power(self, t0, t1):
+        pw = []
+        for ts, ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) >= 4 and t0 - 0.05 <= ts <= t1 + 0.15:
+                try:
+                    pw.append(float(f[3]))
+                except ValueError:
+                    pass
+        return max(pw) if pw else None
+
     def summary(self, t0, t1):
         sm, smax, reasons = [], 0.0, set()
         for ts, ln in self.lines:
@@ -147,6 +204,21 @@ def make_taps(nchans, ntaps):
     w = 0.35875 - 0.48829 * np.cos(2 * np.pi * k / m) + 0.14128 * np.cos(4 * np.pi * k / m) - 0.01168 * np.cos(6 * np.pi * k / m)
     h = h * w
     return (h / h.sum()).astype(np.float32)
+
+
+RAW_FORMATS = {   # name: (RCB_FMT_*, numpy dtype, offset, scale)   sample = (v + offset) * scale
+    "u8": (1, np.uint8, -127.4, 1.0 / 128.0),      # RTL-SDR (gr-osmosdr rtl_source_c)
+    "s8": (2, np.int8, 0.0, 1.0 / 128.0),          # UHD otw_format sc8 (configs/config_denver_usrp.py:20)
+    "sc16": (3, np.int16, 0.0, 1.0 / 32768.0),     # UHD otw_format sc16
+}
+
+
+def quantise(x, name):
+    """complex64 block -> interleaved integers of the named wire format (full scale = 1.0)."""
+    _, dt, off, scale = RAW_FORMATS[name]
+    v = np.round(x.view(np.float32) / np.float32(scale) - np.float32(off))
+    info = np.iinfo(dt)
+    return np.clip(v, info.min, info.max).astype(dt)
 
 
 def synth_block(n, nchans, seed):
@@ -190,7 +262,7 @@ def allreduce_max(dist, local, v):
 # -------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: GR-semantics C restatement on the host cores
 # -------------------------------------------------------------------------------------------------
-def cpu_run(wl, steps, warmup, log2n_cpu=None, budget_s=None):
+def cpu_run(wl, steps, warmup, log2n_cpu=None, budget_s=None, streams=1):
     from oracle import gr_cpu
     cfg = WORKLOADS[wl]
     if cfg.get("kind") == "fft":
@@ -239,23 +311,26 @@ def cpu_run(wl, steps, warmup, log2n_cpu=None, budget_s=None):
     x = np.tile(base, n // len(base)) if n > len(base) else base
     want_fm = "fm" in cfg["out"]
     threads = os.cpu_count() or gr_cpu.num_threads()   # torchrun exports OMP_NUM_THREADS=1: ask explicitly
-    hist = None
+    hist = [None] * streams
     want_iq = "iq" in cfg["out"]
     o_iq = np.zeros((nch, n // nch), np.complex64) if want_iq else None   # touched once: no page faults in the timed loop
     o_fm = np.zeros((nch, n // nch), np.float32) if want_fm else None
     for _ in range(max(warmup, 1)):
-        _, _, hist = gr_cpu.pfb_fm(x, nch, taps, 5.0, want_iq=want_iq, want_fm=want_fm, hist=hist, nthreads=threads,
-                                   out_iq=o_iq, out_fm=o_fm)
+        _, _, hist[0] = gr_cpu.pfb_fm(x, nch, taps, 5.0, want_iq=want_iq, want_fm=want_fm, hist=hist[0], nthreads=threads,
+                                      out_iq=o_iq, out_fm=o_fm)
+        if budget_s and n >= (1 << 26):
+            break   # one full-size warm-up pass is plenty (page faults, thread start-up)
     t0 = time.perf_counter()
     done = 0
     for s in range(steps):
-        _, _, hist = gr_cpu.pfb_fm(x, nch, taps, 5.0, want_iq=want_iq, want_fm=want_fm, hist=hist, nthreads=threads,
-                                   out_iq=o_iq, out_fm=o_fm)
+        for k in range(streams):   # independent streams: each with its own history, same host buffers
+            _, _, hist[k] = gr_cpu.pfb_fm(x, nch, taps, 5.0, want_iq=want_iq, want_fm=want_fm, hist=hist[k],
+                                          nthreads=threads, out_iq=o_iq, out_fm=o_fm)
         done += 1
         if budget_s and time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    msps = done * n / dt / 1e6
+    msps = done * n * streams / dt / 1e6
     return msps, threads, done, n, dt
 
 
@@ -265,19 +340,20 @@ def run_reference(args):
     if rank != 0:
         return 0
     cfg = WORKLOADS[args.workload]
-    # steps large enough that thread start-up does not understate the reference (2^24 samples = 128 MiB of IQ per
-    # step for the channelizer workloads; outputs preallocated and touched before the timed loop)
-    kind = cfg.get("kind")
-    msps, threads, done, n, dt = cpu_run(args.workload, args.steps, max(args.warmup, 1),
-                                         log2n_cpu=(25 if kind == "fft" else 24), budget_s=150.0)
-    sample = "%d steps x 2^%d samples of the %s stream (oracle/gr_cpu.c, OpenMP over frames)" % (
-        done, int(np.log2(n)), args.workload)
+    # the same step as the b200 arm: every stream's full block (2^28 samples for cfg3 = 2 GiB of IQ, ~0.6 s on 16
+    # cores), outputs preallocated and touched before the timed loop; bounded to ~2.5 minutes of wall clock
+    log2n = args.log2n or cfg["log2n"]
+    msps, threads, done, n, dt = cpu_run(args.workload, args.steps, max(args.warmup, 1), log2n_cpu=log2n, budget_s=150.0,
+                                         streams=cfg["streams"])
+    sample = "%d steps x %d stream(s) x 2^%d samples of the %s workload (oracle/gr_cpu.c, OpenMP over frames)" % (
+        done, cfg["streams"], int(np.log2(n)), args.workload)
     line = {
         "impl": "reference", "metric": METRIC, "value": msps, "unit": "Msps", "n_gpus": args.gpus,
         "steps": done, "warmup": args.warmup, "ms_per_step": dt / max(done, 1) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["desc"], "nchans": cfg["nchans"], "ntaps": cfg["ntaps"], "out": cfg["out"],
-                   "note": "GNU Radio 3.8 is not installable here; GR-semantics C restatement of its blocks"},
+        "config": config_dict(args.workload, max(args.gpus, 1), args.out_block, args.log2n),
+        "reference_note": "GNU Radio 3.8 is not installable here (DESIGN.md section 3): GR-semantics C restatement of its "
+                          "blocks on all host threads; one process regardless of --gpus; writes the plain [N][T] layout",
         "cpu_baseline": {"value": msps, "unit": "Msps", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": msps, "unit": "Msps", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -292,7 +368,7 @@ def run_reference(args):
 class StreamCtx(object):
     """One wideband stream resident on the GPU: engine + channelizer + device buffers."""
 
-    def __init__(self, device, wl, seed, log2n=None, ntaps=None, out_block=0):
+    def __init__(self, device, wl, seed, log2n=None, ntaps=None, out_block=0, in_fmt=None):
         from radiocapture_rf_b200.engine import Engine, PfbChannelizer, OUT_FM, OUT_IQ
         cfg = WORKLOADS[wl]
         self.cfg = cfg
@@ -307,14 +383,20 @@ class StreamCtx(object):
                                  (OUT_FM if self.fm else 0) | (OUT_IQ if self.iq else 0), 5.0)
         base_n = min(self.n, 1 << 24)
         base = synth_block(base_n, self.nch, seed)
-        self.d_in = self.e.dev_alloc(self.n * 8)
+        isz = 8
+        if in_fmt:   # the same stream in the SDR's wire format, read directly by the kernel
+            fmt, _, off, scale = RAW_FORMATS[in_fmt]
+            self.ch.set_input_format(fmt, off, scale)
+            base = quantise(base, in_fmt)
+            isz = base.itemsize * 2
+        self.d_in = self.e.dev_alloc(self.n * isz)
         check_copy = self.e.lib.rcb_memcpy
         from radiocapture_rf_b200._lib import COPY_H2D, check
         check(check_copy(self.e.h, self.d_in.ptr, base.ctypes.data, base.nbytes, COPY_H2D), "h2d", self.e.h)
         filled = base_n
         while filled < self.n:  # replicate on device
             c = min(filled, self.n - filled)
-            self.e.copy_d2d(self.d_in.ptr + filled * 8, self.d_in.ptr, c * 8)
+            self.e.copy_d2d(self.d_in.ptr + filled * isz, self.d_in.ptr, c * isz)
             filled += c
         self.base = base
         self.out_block = out_block
@@ -324,7 +406,7 @@ class StreamCtx(object):
         out_elems = nb * self.nch * out_block if out_block else self.n
         self.d_fm = self.e.dev_alloc(out_elems * 4) if self.fm else None
         self.d_iq = self.e.dev_alloc(out_elems * 8) if self.iq else None
-        self.bytes_per_sample = 8 + (4 if self.fm else 0) + (8 if self.iq else 0)
+        self.bytes_per_sample = isz + (4 if self.fm else 0) + (8 if self.iq else 0)
 
     def step(self):
         self.ch.process_device(self.d_in, self.n, self.d_iq, self.d_fm, self.frames)
@@ -416,7 +498,54 @@ def timed_loop(ctxs, steps, warmup, dist, local):
     return ms, launches, t0, t1
 
 
-def run_e2e(device, wl, steps, warmup, dist, local, log2n=26):
+def side_run(device, wl, world, dist, local, peak, steps, out_block, log2n=None, in_fmt=None, bytes_per_sample=None):
+    """One extra device-resident measurement of a PFB workload for the `also` object."""
+    cfg = WORKLOADS[wl]
+    ctxs = [StreamCtx(device, wl, seed=3 + i, log2n=log2n, out_block=out_block, in_fmt=in_fmt)
+            for i in range(cfg["streams"])]
+    ms, _, _, _ = timed_loop(ctxs, steps, 3, dist, local)
+    ms = allreduce_max(dist, local, ms)
+    tot = sum(c.n for c in ctxs) * steps
+    bps = bytes_per_sample or ctxs[0].bytes_per_sample
+    for c in ctxs:
+        c.close()
+    return {"workload": cfg["desc"], "kernel": kernel_name(wl), "unit": "Msps", "value": tot * world / (ms * 1e-3) / 1e6,
+            "algorithmic_bytes_per_sample": bps, "roofline_frac": tot * bps / (ms * 1e-3) / 1e9 / peak}
+
+
+def sustained_run(device, wl, dist, local, peak, out_block, log2n, seconds=2.5):
+    """The headline launch looped for >= `seconds` with the clock / power sampler running (burst vs sustained)."""
+    ctx = StreamCtx(device, wl, seed=3, log2n=log2n, out_block=out_block)
+    for _ in range(3):
+        ctx.step()
+    ctx.e.sync()
+    sampler = ClockSampler(device)
+    sampler.start()
+    time.sleep(0.25)
+    barrier(dist, local)
+    ctx.e.timer_start()
+    t0 = time.time()
+    steps = 0
+    while True:
+        for _ in range(50):
+            ctx.step()
+        steps += 50
+        ctx.e.sync()
+        if time.time() - t0 >= seconds:
+            break
+    ms = ctx.e.timer_stop()
+    t1 = time.time()
+    sampler.stop()
+    clk = sampler.summary(t0, t1)
+    pw = sampler.power(t0, t1)
+    n = ctx.n
+    bps = ctx.bytes_per_sample
+    ctx.close()
+    return {"seconds": ms * 1e-3, "steps": steps, "unit": "Msps", "value": n * steps / (ms * 1e-3) / 1e6,
+            "roofline_frac": n * steps * bps / (ms * 1e-3) / 1e9 / peak, "clocks": clk, "power_w_max": pw}
+
+
+def run_e2e(device, wl, steps, warmup, dist, local, log2n=26, out_block=0, in_fmt=None):
     """Same metric through the public host-buffer call: pinned host in -> H2D -> kernel -> D2H -> pinned host out."""
     from radiocapture_rf_b200.engine import Engine, PfbChannelizer, OUT_FM, OUT_IQ
     cfg = WORKLOADS[wl]
@@ -426,25 +555,37 @@ def run_e2e(device, wl, steps, warmup, dist, local, log2n=26):
     frames = n // nch
     e = Engine(device)
     ch = PfbChannelizer(e, nch, make_taps(nch, cfg["ntaps"]), (OUT_FM if fm else 0) | (OUT_IQ if iq else 0), 5.0)
-    hin = e.pinned((n,), np.complex64)
     base = synth_block(min(n, 1 << 22), nch, 5)
-    for i in range(0, n, len(base)):
-        hin[i:i + len(base)] = base[:min(len(base), n - i)]
-    hfm = e.pinned((nch, frames), np.float32) if fm else None
-    hiq = e.pinned((nch, frames), np.complex64) if iq else None
+    if in_fmt:
+        fmt, dt, off, scale = RAW_FORMATS[in_fmt]
+        ch.set_input_format(fmt, off, scale)
+        hin = e.pinned((2 * n,), dt)
+        rb = quantise(base, in_fmt)
+        for i in range(0, 2 * n, len(rb)):
+            hin[i:i + len(rb)] = rb[:min(len(rb), 2 * n - i)]
+    else:
+        hin = e.pinned((n,), np.complex64)
+        for i in range(0, n, len(base)):
+            hin[i:i + len(base)] = base[:min(len(base), n - i)]
+    if out_block:
+        ch.set_out_block(out_block)
+    shape = (-(-frames // out_block), nch, out_block) if out_block else (nch, frames)
+    hfm = e.pinned(shape, np.float32) if fm else None
+    hiq = e.pinned(shape, np.complex64) if iq else None
     for _ in range(warmup):
         ch.process(hin, out_iq=hiq, out_fm=hfm)
     barrier(dist, local)
     t0 = time.perf_counter()
     for _ in range(steps):
         ch.process(hin, out_iq=hiq, out_fm=hfm)   # returns after the D2H completed
-    dt = time.perf_counter() - t0
+    dt_s = time.perf_counter() - t0
     barrier(dist, local)
     hout = hfm if fm else hiq
-    chk = float(np.abs(hout[:, -8:]).sum())   # the result is really on the host
+    chk = float(np.abs(hout.reshape(-1)[-4096:]).sum())   # the result is really on the host
     d2h = (hfm.nbytes if fm else 0) + (hiq.nbytes if iq else 0)
+    h2d = hin.nbytes
     e.close()
-    return n * steps / dt / 1e6, n * 8, d2h, chk
+    return n * max(steps, 1) / max(dt_s, 1e-9) / 1e6, h2d, d2h, chk
 
 
 def run_e2e_ddc(device, wl, steps, dist, local, log2n=24):
@@ -496,6 +637,17 @@ def run_e2e_fft(device, wl, steps, dist, local, log2n=26):
     return n * steps / dt / 1e6, n * 8, int(out.nbytes), chk
 
 
+def copy_ceiling_line(device, h2d, d2h, dist, local):
+    """Bare pinned H2D || D2H of one e2e step's bytes on every rank at once (no kernels): the platform ceiling."""
+    from radiocapture_rf_b200.engine import Engine, copy_ceiling
+    e = Engine(device)
+    barrier(dist, local)
+    a, b, wall = copy_ceiling(e, h2d, d2h, iters=4)
+    barrier(dist, local)
+    e.close()
+    return a, b, wall
+
+
 def run_b200(args):
     world, rank, local, dist = dist_setup(args.gpus)
     device = local if world > 1 else 0
@@ -505,8 +657,10 @@ def run_b200(args):
 
     is_fft = cfg.get("kind") == "fft"
     is_ddc = cfg.get("kind") == "ddc"
+    is_pfb = not (is_fft or is_ddc)
+    out_block = args.out_block if is_pfb else 0
     Ctx = FftCtx if is_fft else (DdcCtx if is_ddc else StreamCtx)
-    ctxs = [Ctx(device, wl, seed=3 + 100 * rank + i, log2n=args.log2n, out_block=args.out_block)
+    ctxs = [Ctx(device, wl, seed=3 + 100 * rank + i, log2n=args.log2n, out_block=out_block)
             for i in range(cfg["streams"])]
     sampler = ClockSampler(device)
     sampler.start()
@@ -514,88 +668,113 @@ def run_b200(args):
     ms, launches, t0, t1 = timed_loop(ctxs, args.steps, args.warmup, dist, local)
     sampler.stop()
     clocks = sampler.summary(t0, t1)
+    clocks["power_w_max"] = sampler.power(t0, t1)
     ms = allreduce_max(dist, local, ms)
     samples_rank = sum(c.n for c in ctxs) * args.steps
     total = samples_rank * world
     msps = total / (ms * 1e-3) / 1e6
     bps = ctxs[0].bytes_per_sample
-    # dominant kernel = pfb_fm_kernel: one launch per stream per step (the other launch is a ~2 us history copy)
     n_launch_samples = ctxs[0].n
     kern_ms = ms / args.steps if cfg["streams"] == 1 else None
     achieved = (samples_rank * bps) / (ms * 1e-3) / 1e9
     tr = load_traffic(wl)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (tr * n_launch_samples) if tr else None, "peak_source": peak_src,
-                "kernel": "fft_cols_tma_kernel+fft_rows_kernel" if is_fft else ("ddc_tile_kernel" if is_ddc else "pfb_fm_tma_kernel"),
+                "kernel": kernel_name(wl),
+                "algorithmic_bytes_per_sample": bps,
                 "algorithmic_bytes_per_launch": n_launch_samples * bps,
                 "kernel_ms_per_launch": kern_ms}
+    spg = sum(c.n for c in ctxs)
     for c in ctxs:
         c.close()
 
     also = None
     if wl == "cfg3" and not args.no_also:
         also = {}
-        if args.out_block:  # the same launch with the plain [N][T] layout (rows 1 MB apart)
-            cp = StreamCtx(device, wl, seed=3, log2n=args.log2n, out_block=0)
-            msp, _, _, _ = timed_loop([cp], max(3, args.steps // 2), 3, dist, local)
-            msp = allreduce_max(dist, local, msp)
-            stp = max(3, args.steps // 2)
-            also["plain_layout"] = {"workload": cfg["desc"] + ", plain [N][T] output", "unit": "Msps",
-                                    "value": cp.n * stp * world / (msp * 1e-3) / 1e6,
-                                    "roofline_frac": cp.n * stp * 12 / (msp * 1e-3) / 1e9 / peak}
-            cp.close()
-        if args.out_block != 8:  # frame-major blocks of 8: each CTA iteration writes one contiguous 32 KB piece
-            c8 = StreamCtx(device, wl, seed=3, log2n=args.log2n, out_block=8)
-            ms8, _, _, _ = timed_loop([c8], max(3, args.steps // 2), 3, dist, local)
-            ms8 = allreduce_max(dist, local, ms8)
-            st8 = max(3, args.steps // 2)
-            also["out_block_8"] = {"workload": cfg["desc"] + ", output channel-major inside blocks of 8 frames",
-                                   "unit": "Msps", "value": c8.n * st8 * world / (ms8 * 1e-3) / 1e6,
-                                   "roofline_frac": c8.n * st8 * 12 / (ms8 * 1e-3) / 1e9 / peak}
-            c8.close()
-        c16 = StreamCtx(device, "cfg3_p16", seed=3, log2n=args.log2n, out_block=args.out_block)
-        ms16, _, _, _ = timed_loop([c16], max(3, args.steps // 2), 2, dist, local)
-        ms16 = allreduce_max(dist, local, ms16)
-        st16 = max(3, args.steps // 2)
-        a16 = c16.n * st16 * 12 / (ms16 * 1e-3) / 1e9
-        also["taps_per_arm_16"] = {"workload": WORKLOADS["cfg3_p16"]["desc"], "unit": "Msps",
-                                   "value": c16.n * st16 * world / (ms16 * 1e-3) / 1e6, "roofline_frac": a16 / peak}
-        c16.close()
+        half = max(3, args.steps // 2)
+        # ---- the three readings of "256-tap / 1024-channel"  ----
+        readings = {"prototype_256_taps_1_per_arm": {
+            "workload": cfg["desc"], "kernel": kernel_name(wl), "unit": "Msps", "value": msps, "roofline_frac": achieved / peak,
+            "note": "literal GNU Radio API reading (the headline): 768 of the 1024 arms have no tap - an FFT-only upper "
+                    "bound, not a working channel filter"}}
+        readings["16_taps_per_arm"] = side_run(device, "cfg3_p16", world, dist, local, peak, half, out_block, args.log2n)
+        readings["16_taps_per_arm"]["note"] = ("the reference's own filter shape (optfir.low_pass(1, N, 0.5, 0.7, 0.1, 80) is "
+                                               "17-19 taps per arm): 32 extra fp32 lane-operations per sample put the FP32 pipe, "
+                                               "not HBM, on the critical path (DESIGN.md section 5)")
+        r256 = side_run(device, "cfg3_p256", world, dist, local, peak, 3, out_block, min(args.log2n or 26, 26))
+        flops = 4.0 * 256 + 5.0 * 10 + 30.0     # FIR 4 P + FFT 5 log2 N + demod
+        r256["fp32_tflops"] = r256["value"] * 1e6 * flops / 1e12 / world
+        r256["fp32_roofline_frac"] = r256["fp32_tflops"] / 74.4   # 148 SMs x 128 FMA lanes x 2 x 1.965 GHz
+        r256["note"] = "256 taps PER ARM: compute bound (about 1100 flop per sample), quoted against the fp32 roofline too"
+        readings["256_taps_per_arm"] = r256
+        also["tap_readings"] = readings
+        also["taps_per_arm_16"] = readings["16_taps_per_arm"]
+        also["taps_per_arm_8"] = side_run(device, "cfg3_p8", world, dist, local, peak, half, out_block, args.log2n)
+        # ---- the plain [N][T] layout (rows 1 MB apart) ----
+        if out_block:
+            also["plain_layout"] = side_run(device, wl, world, dist, local, peak, half, 0, args.log2n)
+            also["plain_layout"]["workload"] += ", plain [N][T] output"
+        # ---- burst vs sustained ----
+        also["sustained"] = sustained_run(device, wl, dist, local, peak, out_block, args.log2n)
+        # ---- fused integer ingest: fewer HBM read bytes per sample (and fewer PCIe bytes on the host path) ----
+        for name, rd in (("sc16", 4), ("u8", 2)):
+            r = side_run(device, wl, world, dist, local, peak, half, out_block, args.log2n, in_fmt=name,
+                         bytes_per_sample=rd + 4)
+            r["workload"] += ", %s wire format read directly (rcb_pfb_set_input_format)" % name
+            ev, h2d_i, d2h_i, _ = run_e2e(device, wl, max(args.e2e_steps, 1), 1, dist, local, out_block=out_block,
+                                          in_fmt=name)
+            ev = ev * world if dist is None else allreduce_sum_min(dist, local, ev, world)
+            r["e2e"] = {"value": ev, "unit": "Msps", "h2d_bytes_per_step": h2d_i, "d2h_bytes_per_step": d2h_i}
+            also["ingest_" + name] = r
+        # ---- BASELINE config 5: 8 independent 256-channel streams per GPU (64 over 8 GPUs) ----
+        also["cfg5"] = side_run(device, "cfg5", world, dist, local, peak, half, out_block)
+        also["cfg5"]["streams_total"] = WORKLOADS["cfg5"]["streams"] * world
 
+    api = "rcb_pfb_process(host pinned in, host pinned out)"
     if is_fft:
         e2e_v, h2d, d2h, chk = run_e2e_fft(device, wl, args.e2e_steps, dist, local)
+        api = "rcb_fft_process(host pinned in, host out)"
     elif is_ddc:
         e2e_v, h2d, d2h, chk = run_e2e_ddc(device, wl, args.e2e_steps, dist, local)
+        api = "rcb_ddc_process(host pinned in) + rcb_ddc_pull(host out) per channel"
     else:
-        e2e_v, h2d, d2h, chk = run_e2e(device, wl, args.e2e_steps, 1, dist, local)
+        e2e_v, h2d, d2h, chk = run_e2e(device, wl, args.e2e_steps, 1, dist, local, out_block=out_block)
     e2e_v = e2e_v * world if dist is None else allreduce_sum_min(dist, local, e2e_v, world)
+    e2e = {"value": e2e_v, "unit": "Msps", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": api,
+           "checksum": chk}
+    if not args.no_ceiling:
+        # all ranks copy at once: the ceiling includes what they take from each other (host memory, PCIe switches)
+        a, b, wall = copy_ceiling_line(device, h2d, d2h, dist, local)
+        a_min = a if dist is None else allreduce_sum_min(dist, local, a, 1)
+        b_min = b if dist is None else allreduce_sum_min(dist, local, b, 1)
+        step_s = max(h2d / max(a_min, 1e-9), d2h / max(b_min, 1e-9)) / 1e9   # both directions overlap
+        n_e2e = h2d // 8 if is_pfb or is_fft or is_ddc else 0
+        ceil_msps = (n_e2e / step_s / 1e6) * world if step_s > 0 else None
+        e2e["pcie_ceiling"] = {"h2d_gbs_per_gpu_min": a_min, "d2h_gbs_per_gpu_min": b_min, "msps": ceil_msps,
+                               "frac": (e2e_v / ceil_msps) if ceil_msps else None,
+                               "how": "rcb_copy_ceiling: pinned H2D || D2H of one step's bytes on all ranks at once, no kernels"}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and not args.no_cpu:
         cm, threads, done, n, dt = cpu_run(wl, 100000, 1, log2n_cpu=(None if (is_fft or is_ddc) else 24), budget_s=12.0)
         cpu = {"value": cm, "unit": "Msps", "cores": threads, "kind": "port",
                "sample": "%d x 2^%d samples of the same workload (oracle/gr_cpu.c, %.1f s)" % (done, int(np.log2(n)), dt)}
+    barrier(dist, local)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": msps, "unit": "Msps", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["desc"], "nchans": cfg["nchans"], "ntaps": cfg["ntaps"], "out": cfg["out"],
-                       "samples_per_step_per_gpu": sum(c.n for c in ctxs), "streams_per_gpu": cfg["streams"],
-                       "channels_out": cfg["nchans"] * cfg["streams"] * world,
-                       "out_layout": ("channel-major in blocks of %d frames (rcb_pfb_set_out_block)" % args.out_block)
-                       if args.out_block else "channel-major [N][T]",
-                       "l2": "inputs (%d MiB/step) larger than L2, no flush" % (sum(c.n for c in ctxs) * 8 >> 20),
-                       "parallelism": "independent streams, %d GPU(s), no collective" % world},
+            "config": config_dict(wl, world, out_block, args.log2n),
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_v, "unit": "Msps", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "rcb_pfb_process(host pinned in, host pinned out)", "checksum": chk},
+            "e2e": e2e,
             "gpu_launches": launches,
             "clocks": clocks,
             "also": also,
         }
+        assert line["config"]["samples_per_step_per_gpu"] == spg
         emit(line)
     if dist is not None:
         dist.destroy_process_group()
@@ -639,6 +818,7 @@ def main():
     ap.add_argument("--out-block", type=int, default=1024,
                     help="device output layout: channel-major in blocks of this many frames (0 = plain [N][T])")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ceiling", action="store_true", help="skip the bare-copy ceiling measurement of the e2e path")
     ap.add_argument("--no-also", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

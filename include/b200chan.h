@@ -38,6 +38,7 @@ typedef enum {
 
 enum { RCB_MEM_HOST = 0, RCB_MEM_DEVICE = 1 };
 enum { RCB_OUT_IQ = 1, RCB_OUT_FM = 2 };
+enum { RCB_FMT_C64 = 0, RCB_FMT_U8 = 1, RCB_FMT_S8 = 2, RCB_FMT_S16 = 3 };  /* input sample formats */
 enum { RCB_COPY_H2D = 1, RCB_COPY_D2H = 2, RCB_COPY_D2D = 3 };
 
 typedef struct {
@@ -96,6 +97,13 @@ int rcb_pfb_reset(rcb_t* h);
  * frames = 8 is the kernel's native granularity (one CTA iteration = one contiguous nchans*8-element piece,
  * full-line stores: +7 % on the 1024-channel FM path) for consumers that run on the GPU themselves. */
 int rcb_pfb_set_out_block(rcb_t* h, int frames);
+/* Fused ingest: after this call `iq` of rcb_pfb_process is the SDR's wire format - interleaved
+ * integer I/Q, fmt = RCB_FMT_U8 (RTL-SDR: offset -127.4, scale 1/128), RCB_FMT_S8 / RCB_FMT_S16 (UHD otw_format sc8 /
+ * sc16, configs/config_denver_usrp.py:20), sample = (v + offset) * scale exactly like rcb_convert_iq - and nsamples
+ * still counts complex samples.  The 1024-channel one-tap-per-arm FM kernel converts inside its first FFT pass (2-4x
+ * fewer HBM read and PCIe bytes); every other shape converts the block once on the device.  fmt = 0 restores
+ * complex64.  Resets the streaming state. */
+int rcb_pfb_set_input_format(rcb_t* h, int fmt, float offset, float scale);
 int rcb_pfb_process(rcb_t* h, const void* iq, size_t nsamples, int in_mem,
                     void* out_iq, void* out_fm, size_t out_stride, int out_mem, size_t* nout);
 
@@ -133,7 +141,6 @@ int rcb_probe_mean(rcb_t* h, const void* x, size_t rows, size_t n, size_t stride
  * shipped rtlsdr config), RCB_FMT_S8 / RCB_FMT_S16 are UHD's sc8 / sc16 wire formats
  * (configs/config_denver_usrp.py:20 otw_format).  src holds 2*nsamples integers; dst nsamples complex64.
  * src_mem / dst_mem: RCB_MEM_HOST or RCB_MEM_DEVICE (host src = 2-4x fewer PCIe bytes than complex64). */
-enum { RCB_FMT_U8 = 1, RCB_FMT_S8 = 2, RCB_FMT_S16 = 3 };
 int rcb_convert_iq(rcb_t* h, const void* src, int fmt, float offset, float scale, size_t nsamples, int src_mem,
                    void* dst, int dst_mem);
 

@@ -7,6 +7,8 @@
  *                       + gr-analog quadrature_demod_cf_impl.cc per bin                  (moto_control_demod.py:105 ...)
  *   grc_xlating_fir     gr-filter freq_xlating_fir_filter_impl.cc + gr-blocks rotator.h   (rc_frontend/channel.py:35)
  *   grc_quad_demod      gr-analog quadrature_demod_cf_impl.cc + fast_atan2f.cc
+ *   grc_convert_iq      the host-side wire-format conversion GNU Radio's sources do before anything else: gr-osmosdr
+ *                       rtl_source_c ((u8 - 127.4) / 128), UHD convert sc8 / sc16 -> fc32 (configs/config_denver_usrp.py:20)
  *   grc_fft_logpow      gr-fft fft_vcc_fftw.cc + complex_to_mag_squared + nlog10_ff + moving sum (fft_vector.py:37-60)
  * Used ONLY by tests/ (checked against the float64 numpy oracle) and by bench.py's cpu_baseline /
  * --impl reference legs (timed on the host cores, OpenMP over frames / outputs; GNU Radio itself runs
@@ -212,6 +214,30 @@ int grc_xlating_fir(const cf* x, long n, const float* taps, int ntaps, int decim
     }
     free(ct);
     *nout_p = nout;
+    return 0;
+}
+
+/* out[i] = (v[i] + offset) * scale over 2*n interleaved integers.  fmt: 1 u8, 2 s8, 3 s16. */
+int grc_convert_iq(const void* src, int fmt, float offset, float scale, long n, float* out, int nthreads) {
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+    const long m = 2 * n;
+    if (fmt == 3) {
+        const short* v = (const short*)src;
+#pragma omp parallel for schedule(static)
+        for (long i = 0; i < m; ++i) out[i] = ((float)v[i] + offset) * scale;
+    } else if (fmt == 2) {
+        const signed char* v = (const signed char*)src;
+#pragma omp parallel for schedule(static)
+        for (long i = 0; i < m; ++i) out[i] = ((float)v[i] + offset) * scale;
+    } else if (fmt == 1) {
+        const unsigned char* v = (const unsigned char*)src;
+#pragma omp parallel for schedule(static)
+        for (long i = 0; i < m; ++i) out[i] = ((float)v[i] + offset) * scale;
+    } else {
+        return -1;
+    }
     return 0;
 }
 

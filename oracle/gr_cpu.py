@@ -33,6 +33,7 @@ def load():
         _lib.grc_xlating_fir.argtypes = [vp, ll, vp, C.c_int, C.c_int, C.c_double, C.c_double, vp, C.POINTER(ll), C.c_int]
         _lib.grc_quad_demod.argtypes = [vp, ll, C.c_float, C.c_float, C.c_float, vp]
         _lib.grc_fft_logpow.argtypes = [vp, C.c_int, vp, ll, vp, C.c_int]
+        _lib.grc_convert_iq.argtypes = [vp, C.c_int, C.c_float, C.c_float, ll, vp, C.c_int]
     return _lib
 
 
@@ -59,6 +60,19 @@ def pfb_fm(x, nchans, taps, gain, want_iq=True, want_fm=True, hist=None, nthread
                         hist.ctypes.data, nthreads)
     assert rc == 0
     return iq, fm, hist
+
+
+def convert_iq(raw, fmt, offset, scale, out=None, nthreads=0):
+    """Interleaved integer I/Q (fmt 1 u8, 2 s8, 3 s16) -> complex64 = (v + offset) * scale."""
+    lib = load()
+    raw = np.ascontiguousarray(raw).reshape(-1)
+    n = len(raw) // 2
+    if out is None:
+        out = np.empty(n, np.complex64)
+    assert out.dtype == np.complex64 and len(out) >= n
+    rc = lib.grc_convert_iq(raw.ctypes.data, int(fmt), float(offset), float(scale), n, out.ctypes.data, nthreads)
+    assert rc == 0
+    return out[:n]
 
 
 def xlating_fir(x, taps, decim, f0, fs, nthreads=0):

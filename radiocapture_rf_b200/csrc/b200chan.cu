@@ -97,6 +97,13 @@ struct rcb_ctx {
         bool taps_smem = true;
         int variant = 0;  // RCB_PFB_VARIANT: tuning experiments, read only by -DRCB_EXPERIMENTS builds (never shipped)
         float4* d_tw4 = nullptr;  // pfb_cl_kernel twiddles [CS][R/2][16]
+        // fused integer ingest (rcb_pfb_set_input_format): raw copy of the last P input rows + how many of them are real
+        int in_fmt = 0;
+        float in_off = 0.f, in_scale = 1.f;
+        void* d_hist_raw[2] = {nullptr, nullptr};
+        int hist_valid = 0;
+        float2* d_conv = nullptr;      // complex64 staging for kernels without the fused conversion
+        size_t conv_cap = 0;
         float* d_taps_gen = nullptr;   // generic-kernel tables, also built for the fast shapes (fallback for
         float2* d_tw_gen = nullptr;    // output buffers the sector-store / TMA kernels cannot address)
         bool use_cl = false;      // FM only, N in {256, 1024}, <= 16 taps per arm: cluster / register-window kernel
@@ -374,8 +381,7 @@ int pfb_launch_cl_r(rcb_t* h, const float2* d_x, const float2* d_hist, size_t fr
 }
 int pfb_launch_cl(rcb_t* h, const float2* d_x, const float2* d_hist, size_t frames, float* d_fm, size_t ostride) {
     if (h->pfb.R == 32) return pfb_launch_cl_r<32>(h, d_x, d_hist, frames, d_fm, ostride);
-    if (h->pfb.R == 16) return pfb_launch_cl_r<16>(h, d_x, d_hist, frames, d_fm, ostride);
-    return 1;
+    return 1;  // (the kernel also supports N = 256 as a single CTA; the round-1 kernels measured faster there)
 }
 
 // single-tap 1024-channel FM kernel with the TMA tile store (pfb_fm1.cuh).  Returns 1 when the output cannot be
@@ -400,23 +406,26 @@ int pfb_launch_fm1(rcb_t* h, const PfbParams& p0, size_t frames, float* d_fm, si
         if (!tmap_encode_f32(&tm_out, 3, d_fm, dims, str, box, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
         out_rank = 3;
     }
-    static bool attr_dev[64] = {};
-    static int per_sm[64] = {};
-    const int di = h->device & 63;
-    if (!attr_dev[di]) {
-        CK(cudaFuncSetAttribute(pfb_fm1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes));
+    typedef void (*fm1_fn)(const CUtensorMap, const PfbParams, const int);
+    static const fm1_fn kerns[4] = {pfb_fm1_kernel<0>, pfb_fm1_kernel<1>, pfb_fm1_kernel<2>, pfb_fm1_kernel<3>};
+    static bool attr_dev[64][4] = {};
+    static int per_sm[64][4] = {};
+    const int di = h->device & 63, fi = s.in_fmt & 3;
+    fm1_fn kern = kerns[fi];
+    if (!attr_dev[di][fi]) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes));
         int nb = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pfb_fm1_kernel, G::THREADS, G::smem_bytes));
-        per_sm[di] = std::max(nb, 1);
-        attr_dev[di] = true;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, G::THREADS, G::smem_bytes));
+        per_sm[di][fi] = std::max(nb, 1);
+        attr_dev[di][fi] = true;
     }
     PfbParams q = p0;
     q.twiddle = s.d_tw_tma;
     q.work_counter = s.d_counter;
     const int NI = (int)((frames + G::FPI - 1) / G::FPI);
-    const int grid = std::max(1, std::min(NI, per_sm[di] * h->sm_count));
+    const int grid = std::max(1, std::min(NI, per_sm[di][fi] * h->sm_count));
     CK(cudaMemsetAsync(s.d_counter, 0, sizeof(int), h->stream));
-    pfb_fm1_kernel<<<grid, G::THREADS, G::smem_bytes, h->stream>>>(tm_out, q, out_rank);
+    kern<<<grid, G::THREADS, G::smem_bytes, h->stream>>>(tm_out, q, out_rank);
     CKL(h);
     return RCB_OK;
 }
@@ -513,6 +522,16 @@ void pfb_free(rcb_t* h) {
     cudaFree(s.d_tw_gen);
     s.d_taps_gen = nullptr;
     s.d_tw_gen = nullptr;
+    cudaFree(s.d_hist_raw[0]);
+    cudaFree(s.d_hist_raw[1]);
+    s.d_hist_raw[0] = s.d_hist_raw[1] = nullptr;
+    cudaFree(s.d_conv);
+    s.d_conv = nullptr;
+    s.conv_cap = 0;
+    s.in_fmt = 0;
+    s.in_off = 0.f;
+    s.in_scale = 1.f;
+    s.hist_valid = 0;
     s.use_cl = false;
 
     cudaFree(s.d_hist[0]);
@@ -533,11 +552,17 @@ void pfb_free(rcb_t* h) {
 }
 
 // one launch over device-resident input; advances the streaming history
-int pfb_run_device(rcb_t* h, const float2* d_x, size_t frames, float2* d_iq, float* d_fm, size_t ostride) {
+size_t pfb_in_bytes_per_sample(int fmt) { return fmt == 0 ? 8 : (fmt == RCB_FMT_S16 ? 4 : 2); }
+
+// one launch over device-resident input (complex64, or raw integer I/Q when an input format is set); advances the
+// streaming history
+int pfb_run_device(rcb_t* h, const void* d_in, size_t frames, float2* d_iq, float* d_fm, size_t ostride) {
     auto& s = h->pfb;
     if (frames == 0) return RCB_OK;
+    const bool raw = (s.in_fmt != 0);
+    const size_t nsamp = frames * (size_t)s.N;
     PfbParams p{};
-    p.x = d_x;
+    p.x = (const float2*)d_in;
     p.hist = s.d_hist[s.hist_cur];
     p.taps = s.d_taps;
     p.twiddle = s.d_tw;
@@ -550,15 +575,43 @@ int pfb_run_device(rcb_t* h, const float2* d_x, size_t frames, float2* d_iq, flo
     p.P = s.P;
     p.N = s.N;
     p.gain = s.gain;
+    p.in_fmt = s.in_fmt;
+    p.in_off = s.in_off;
+    p.in_scale = s.in_scale;
+    p.hist_raw = s.d_hist_raw[s.hist_cur];
+    p.hist_valid = s.hist_valid;
     int cl_rc = 1;
-    // 1024 channels, one tap per arm: the TMA-store variant of the round-1 headline kernel (2 CTAs / SM, 16 FFT warps);
-    // everything else with FM-only output on N = 256 / 1024: the cluster / register-window kernel
-    // (experiment builds: RCB_PFB_VARIANT=21 runs the cluster kernel for one tap per arm too)
+    // 1024 channels, FM only: one tap per arm -> the TMA-store variant of the round-1 headline kernel (2 CTAs / SM, 16
+    // FFT warps; reads raw integer I/Q directly); 2..8 taps per arm -> the cluster / register-window kernel; 16 taps per
+    // arm -> the round-1 warp-specialised kernel (measured, scripts/exp/sweep_pfb.py).
+    // (experiment builds: RCB_PFB_VARIANT=21 runs the cluster kernel for every tap count)
     if (s.use_cl && s.R == 32 && s.PT == 1 && s.variant != 21) {
         cl_rc = pfb_launch_fm1(h, p, frames, d_fm, ostride);
         if (cl_rc != RCB_OK && cl_rc != 1) return cl_rc;
     }
-    if (cl_rc == 1 && s.use_cl) {
+    const float2* d_x = (const float2*)d_in;
+    if (cl_rc == 1 && raw) {
+        // every other kernel takes complex64: convert this block once (K5) and go on as usual
+        if (s.conv_cap < nsamp) {
+            cudaFree(s.d_conv);
+            s.d_conv = nullptr;
+            s.conv_cap = 0;
+            CK(cudaMalloc(&s.d_conv, nsamp * sizeof(float2)));
+            s.conv_cap = nsamp;
+        }
+        const unsigned grid = (unsigned)((nsamp + 1023) / 1024);
+        if (s.in_fmt == RCB_FMT_U8)
+            convert_iq_kernel<uint8_t><<<grid, 256, 0, h->stream>>>((const uint8_t*)d_in, s.d_conv, (long long)nsamp, s.in_off, s.in_scale);
+        else if (s.in_fmt == RCB_FMT_S8)
+            convert_iq_kernel<int8_t><<<grid, 256, 0, h->stream>>>((const int8_t*)d_in, s.d_conv, (long long)nsamp, s.in_off, s.in_scale);
+        else
+            convert_iq_kernel<int16_t><<<grid, 256, 0, h->stream>>>((const int16_t*)d_in, s.d_conv, (long long)nsamp, s.in_off, s.in_scale);
+        CKL(h);
+        d_x = s.d_conv;
+        p.x = d_x;
+        p.in_fmt = 0;
+    }
+    if (cl_rc == 1 && s.use_cl && (s.PT <= 8 || s.variant == 21)) {
         cl_rc = pfb_launch_cl(h, d_x, s.d_hist[s.hist_cur], frames, d_fm, ostride);
         if (cl_rc != RCB_OK && cl_rc != 1) return cl_rc;
     }
@@ -592,12 +645,25 @@ int pfb_run_device(rcb_t* h, const float2* d_x, size_t frames, float2* d_iq, flo
                                                            p.ostride, p.T, p.gain, p.oblock_log2, p.N);
         CKL(h);
     }
-    // hist <- last P rows of (hist ++ x)
+    // hist <- last P rows of (hist ++ x): complex64 always (every kernel but the fused-ingest one reads it), plus the raw
+    // copy when an input format is set
     const long long cap = (long long)s.P * s.N;
     const int nxt = s.hist_cur ^ 1;
-    hist_update_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, h->stream>>>(s.d_hist[s.hist_cur], d_x,
-                                                                          (long long)frames * s.N, s.d_hist[nxt], cap);
-    CKL(h);
+    if (raw) {
+        hist_update_convert_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, h->stream>>>(
+            s.d_hist[s.hist_cur], d_in, s.in_fmt, s.in_off, s.in_scale, (long long)nsamp, s.d_hist[nxt], cap);
+        CKL(h);
+        const long long u = (long long)(pfb_in_bytes_per_sample(s.in_fmt) / 2);  // 16-bit units per sample
+        hist_update_raw_kernel<<<(unsigned)((cap * u + 255) / 256), 256, 0, h->stream>>>(
+            (const unsigned short*)s.d_hist_raw[s.hist_cur], (const unsigned short*)d_in, (long long)nsamp * u,
+            (unsigned short*)s.d_hist_raw[nxt], cap * u);
+        CKL(h);
+        s.hist_valid = (int)std::min<long long>((long long)s.P, (long long)s.hist_valid + (long long)frames);
+    } else {
+        hist_update_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, h->stream>>>(s.d_hist[s.hist_cur], d_x,
+                                                                              (long long)nsamp, s.d_hist[nxt], cap);
+        CKL(h);
+    }
     s.hist_cur = nxt;
     h->stats.samples_in += frames * (uint64_t)s.N;
     h->stats.channel_samples += frames * (uint64_t)s.N;
@@ -614,7 +680,7 @@ int pfb_ensure_stages(rcb_t* h) {
         cf = std::max(blk, cf / blk * blk);
     }
     for (auto& st : s.st) {
-        CK(cudaMalloc(&st.d_in, cf * s.N * sizeof(float2)));
+        CK(cudaMalloc(&st.d_in, cf * s.N * pfb_in_bytes_per_sample(s.in_fmt)));
         if (s.mode & RCB_OUT_FM) CK(cudaMalloc(&st.d_fm, cf * s.N * sizeof(float)));
         if (s.mode & RCB_OUT_IQ) CK(cudaMalloc(&st.d_iq, cf * s.N * sizeof(float2)));
         CK(cudaEventCreateWithFlags(&st.ev_in, cudaEventDisableTiming));
@@ -964,7 +1030,7 @@ extern "C" int rcb_pfb_config(rcb_t* h, int nchans, const float* taps, int ntaps
             CK(cudaMemcpy(s.d_taps_kc, kc.data(), kc.size() * sizeof(float), cudaMemcpyHostToDevice));
         }
         // FM only, N = 256 / 1024: cluster / register-window kernel (RCB_PFB_VARIANT=20 in experiment builds: round-1 kernels)
-        s.use_cl = (s.use_tma && (R == 16 || R == 32) && s.mode == RCB_OUT_FM && s.variant != 20);
+        s.use_cl = (s.use_tma && R == 32 && s.mode == RCB_OUT_FM && s.variant != 20);  // (N = 256: the round-1 kernels are faster)
         if (s.use_cl) {
             if (!s.d_taps_kc) {  // one tap per arm: the [PT][N] column-major table is just the reversed prototype
                 std::vector<float> kc((size_t)N, 0.f);
@@ -1066,6 +1132,27 @@ extern "C" int rcb_pfb_reset(rcb_t* h) {
     if (!s.configured) return RCB_ESTATE;
     CK(cudaSetDevice(h->device));
     for (int b = 0; b < 2; ++b) CK(cudaMemsetAsync(s.d_hist[b], 0, (size_t)s.P * s.N * sizeof(float2), h->stream));
+    s.hist_valid = 0;
+    CK(cudaStreamSynchronize(h->stream));
+    return RCB_OK;
+}
+
+extern "C" int rcb_pfb_set_input_format(rcb_t* h, int fmt, float offset, float scale) {
+    if (!h) return RCB_EINVAL;
+    auto& s = h->pfb;
+    if (!s.configured) return RCB_ESTATE;
+    if (fmt != 0 && fmt != RCB_FMT_U8 && fmt != RCB_FMT_S8 && fmt != RCB_FMT_S16) return RCB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    pfb_free_stages(h);  // the staging buffers are sized for the wire format
+    s.in_fmt = fmt;
+    s.in_off = fmt ? offset : 0.f;
+    s.in_scale = fmt ? scale : 1.f;
+    s.hist_valid = 0;
+    for (int b = 0; b < 2; ++b) {
+        CK(cudaMemsetAsync(s.d_hist[b], 0, (size_t)s.P * s.N * sizeof(float2), h->stream));
+        if (fmt && !s.d_hist_raw[b]) CK(cudaMalloc(&s.d_hist_raw[b], (size_t)s.P * s.N * 4));
+        if (s.d_hist_raw[b]) CK(cudaMemsetAsync(s.d_hist_raw[b], 0, (size_t)s.P * s.N * 4, h->stream));
+    }
     CK(cudaStreamSynchronize(h->stream));
     return RCB_OK;
 }
@@ -1087,8 +1174,10 @@ extern "C" int rcb_pfb_process(rcb_t* h, const void* iq, size_t nsamples, int in
     CK(cudaSetDevice(h->device));
     if (frames == 0) return RCB_OK;
 
+    const size_t bps = pfb_in_bytes_per_sample(s.in_fmt);  // complex64, or the wire format set by rcb_pfb_set_input_format
+    if (in_mem == RCB_MEM_DEVICE && ((uintptr_t)iq & 15)) return RCB_EINVAL;
     if (in_mem == RCB_MEM_DEVICE && out_mem == RCB_MEM_DEVICE) {
-        int rc = pfb_run_device(h, (const float2*)iq, frames, (float2*)out_iq, (float*)out_fm, out_stride);
+        int rc = pfb_run_device(h, iq, frames, (float2*)out_iq, (float*)out_fm, out_stride);
         if (rc) return rc;
         if (nout) *nout = frames;
         return RCB_OK;
@@ -1108,17 +1197,16 @@ extern "C" int rcb_pfb_process(rcb_t* h, const void* iq, size_t nsamples, int in
     while (done < frames) {
         const size_t f = std::min(cf, frames - done);
         Stage& st = s.st[si];
-        const float2* d_x;
+        const void* d_x;
         if (in_mem == RCB_MEM_HOST) {
             if (st.used) CK(cudaStreamWaitEvent(h->s_in, st.ev_k, 0));  // previous kernel finished reading d_in
-            CK(cudaMemcpyAsync(st.d_in, (const float2*)iq + done * s.N, f * s.N * sizeof(float2),
-                               cudaMemcpyHostToDevice, h->s_in));
-            h->stats.h2d_bytes += f * s.N * sizeof(float2);
+            CK(cudaMemcpyAsync(st.d_in, (const char*)iq + done * s.N * bps, f * s.N * bps, cudaMemcpyHostToDevice, h->s_in));
+            h->stats.h2d_bytes += f * s.N * bps;
             CK(cudaEventRecord(st.ev_in, h->s_in));
             CK(cudaStreamWaitEvent(h->stream, st.ev_in, 0));
             d_x = st.d_in;
         } else {
-            d_x = (const float2*)iq + done * s.N;
+            d_x = (const char*)iq + done * s.N * bps;
         }
         float2* d_iq;
         float* d_fm;

@@ -228,4 +228,44 @@ __global__ void hist_update_kernel(const float2* __restrict__ old_hist, const fl
     new_hist[i] = (src >= 0) ? x[src] : ((src >= -cap) ? old_hist[cap + src] : make_float2(0.f, 0.f));
 }
 
+// same for raw integer I/Q kept as 16-bit units (u8 / s8: one unit per complex sample, s16: two): byte-exact copy
+__global__ void hist_update_raw_kernel(const unsigned short* __restrict__ old_hist, const unsigned short* __restrict__ x,
+                                       long long n, unsigned short* __restrict__ new_hist, long long cap) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap) return;
+    const long long src = i + n - cap;
+    new_hist[i] = (src >= 0) ? x[src] : ((src >= -cap) ? old_hist[cap + src] : (unsigned short)0);
+}
+
+// complex64 history from raw integer input: new_hist = last `cap` samples of (old_hist ++ convert(x[0..n)))
+// fmt: 1 u8, 2 s8, 3 s16 (include/b200chan.h RCB_FMT_*); out = (v + offset) * scale like convert_iq_kernel
+__global__ void hist_update_convert_kernel(const float2* __restrict__ old_hist, const void* __restrict__ x, int fmt,
+                                           float offset, float scale, long long n, float2* __restrict__ new_hist,
+                                           long long cap) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap) return;
+    const long long src = i + n - cap;
+    float2 v = make_float2(0.f, 0.f);
+    if (src >= 0) {
+        float a, b;
+        if (fmt == 3) {
+            const short* q = reinterpret_cast<const short*>(x) + 2 * src;
+            a = (float)q[0];
+            b = (float)q[1];
+        } else if (fmt == 2) {
+            const signed char* q = reinterpret_cast<const signed char*>(x) + 2 * src;
+            a = (float)q[0];
+            b = (float)q[1];
+        } else {
+            const unsigned char* q = reinterpret_cast<const unsigned char*>(x) + 2 * src;
+            a = (float)q[0];
+            b = (float)q[1];
+        }
+        v = make_float2((a + offset) * scale, (b + offset) * scale);
+    } else if (src >= -cap) {
+        v = old_hist[cap + src];
+    }
+    new_hist[i] = v;
+}
+
 }  // namespace rcb

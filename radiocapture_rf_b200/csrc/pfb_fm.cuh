@@ -49,6 +49,12 @@ struct PfbParams {
     int oblock_log2;        // > 0: channel-major inside time blocks of 2^k frames: (m, t) at
                             //   ((t >> k) * N + m) << k | (t & (2^k - 1)); keeps the 1024 rows a CTA writes
                             //   per iteration within a few MB (TLB / DRAM-page locality, +15 % on cfg3)
+    // fused integer ingest (pfb_fm1_kernel<FMT != 0>, pfb_cl_kernel): x / hist_raw hold raw interleaved integer I/Q
+    // (RCB_FMT_U8 / S8 / S16), sample value = (v + in_off) * in_scale; rows before -hist_valid are zero samples
+    const void* hist_raw;   // P rows of raw samples preceding x
+    int in_fmt;             // 0 = complex64
+    int hist_valid;         // rows of hist_raw that hold real samples (0 at stream start)
+    float in_off, in_scale;
     int T;                  // frames in this launch
     int P;                  // taps per arm
     int N;                  // channels

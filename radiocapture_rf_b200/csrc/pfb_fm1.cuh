@@ -36,10 +36,32 @@ struct PfbFm1Geom {
     static constexpr size_t smem_bytes = off_bar + 128 + 1024;
 };
 
+// Fused ingest: FMT = RCB_FMT_U8 / S8 / S16 reads the SDR's wire format directly - the TMA row copy
+// moves 2 / 2 / 4 bytes per sample instead of 8 (HBM read traffic and, on the host path, PCIe bytes drop 4x / 4x / 2x),
+// the first radix pass converts while it loads ((v + offset), the scale is folded into the taps), nothing else
+// changes.  configs/config_denver_usrp.py:20 (otw_format sc8), every rtlsdr config (u8), logging_receiver.py:107-109.
+template <int FMT>
+__device__ __forceinline__ float2 fm1_load_sample(const float2* wf, int idx, float off) {
+    if constexpr (FMT == 0) {
+        return wf[idx];
+    } else if constexpr (FMT == 3) {  // s16 pairs
+        const int v = reinterpret_cast<const int*>(wf)[idx];
+        return make_float2((float)(short)(v & 0xffff) + off, (float)(short)(v >> 16) + off);
+    } else if constexpr (FMT == 2) {  // s8 pairs
+        const unsigned short v = reinterpret_cast<const unsigned short*>(wf)[idx];
+        return make_float2((float)(signed char)(v & 0xff) + off, (float)(signed char)(v >> 8) + off);
+    } else {                          // u8 pairs
+        const unsigned short v = reinterpret_cast<const unsigned short*>(wf)[idx];
+        return make_float2((float)(v & 0xff) + off, (float)(v >> 8) + off);
+    }
+}
+
 // p.twiddle / p.taps layouts as for pfb_fm_tma_kernel (dense swizzled table, float4 tap groups).
 // out_rank: 2 = plain [N][ostride] (tensor (t, m)), 3 = time blocks of 2^k >= 8 frames (tensor (t_lo, m, t_hi)).
+template <int FMT = 0>
 __global__ void __launch_bounds__(256, 2) pfb_fm1_kernel(const __grid_constant__ CUtensorMap tm_out, const PfbParams p,
                                                          const int out_rank) {
+    constexpr uint32_t ROWB = 1024u * (FMT == 0 ? 8u : (FMT == 3 ? 4u : 2u));  // bytes of one input row
     using G = PfbFm1Geom;
     constexpr int R = 32, N = 1024, W = 8, FPI = 8, THREADS = 256;
     extern __shared__ unsigned char smem_fm1_raw[];
@@ -62,7 +84,7 @@ __global__ void __launch_bounds__(256, 2) pfb_fm1_kernel(const __grid_constant__
 
     for (int i = tid; i < N; i += THREADS) {
         tws[i] = p.twiddle[i];
-        taps_s[i] = p.taps[i];
+        taps_s[i] = (FMT == 0) ? p.taps[i] : p.taps[i] * p.in_scale;
     }
     if (tid < W) mbar_init(bars + tid, 1);
     if (tid == W) mbar_init(tile_done, THREADS);
@@ -95,11 +117,21 @@ __global__ void __launch_bounds__(256, 2) pfb_fm1_kernel(const __grid_constant__
     int nxt0 = NI, nxt1 = NI;
 
     long long frame0 = (long long)(cur0 - 1) * FPI + warp;
+    auto row_src = [&](long long f) -> const void* {
+        if constexpr (FMT == 0) {
+            return pfb_row_ptr<R>(p, f);
+        } else {  // raw rows; rows that do not exist (zero samples) are flagged by the caller, any valid row is loaded
+            if (f >= p.T) f = p.T - 1;
+            if (f >= 0) return reinterpret_cast<const char*>(p.x) + (size_t)f * ROWB;
+            if (f >= -(long long)p.hist_valid) return reinterpret_cast<const char*>(p.hist_raw) + (size_t)(f + p.P) * ROWB;
+            return reinterpret_cast<const char*>(p.x);
+        }
+    };
     auto issue_rows = [&](long long f0) {
         if (lane == 0) {
             fence_proxy_async();
-            mbar_expect_tx(row_bar, (uint32_t)(N * 8));
-            tma_bulk_g2s(work, pfb_row_ptr<R>(p, f0), (uint32_t)(N * 8), row_bar);
+            mbar_expect_tx(row_bar, ROWB);
+            tma_bulk_g2s(work, row_src(f0), ROWB, row_bar);
         }
     };
     issue_rows(frame0);
@@ -136,7 +168,8 @@ __global__ void __launch_bounds__(256, 2) pfb_fm1_kernel(const __grid_constant__
                     const float4 h = tap4[jq * R + ll];
                     hreg[4 * jq + 0] = h.x; hreg[4 * jq + 1] = h.y; hreg[4 * jq + 2] = h.z; hreg[4 * jq + 3] = h.w;
                 }
-                auto get = [&](auto j) { return wf[(R - 1 - decltype(j)::value) * R + ll]; };
+                const float off = p.in_off;
+                auto get = [&](auto j) { return fm1_load_sample<FMT>(wf, (R - 1 - decltype(j)::value) * R + ll, off); };
                 auto tap = [&](auto j) { return hreg[R - 1 - decltype(j)::value]; };
                 fft_packed<R, +1, true>(pr, pi, get, tap);
             }
@@ -170,6 +203,15 @@ __global__ void __launch_bounds__(256, 2) pfb_fm1_kernel(const __grid_constant__
                 const float2 a = atan2_nan_p2(pi[q], pr[q]);
                 ph[2 * q] = a.x;
                 ph[2 * q + 1] = a.y;
+            }
+            if constexpr (FMT != 0) {
+                // a frame before the first real sample is all zeros: its angle is the (0,0) sentinel.  (Frames past the
+                // end of the block are never stored.)  The raw zero row cannot be represented for u8 (offset 127.4).
+                const long long fcur = (long long)it * FPI + warp;
+                if (fcur < -(long long)p.hist_valid) {
+#pragma unroll
+                    for (int m2 = 0; m2 < R; ++m2) ph[m2] = __int_as_float(0x7fc00000);
+                }
             }
         }
         if (!first_ever) {  // the previous iteration's tile has been read by its TMA stores

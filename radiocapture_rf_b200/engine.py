@@ -198,6 +198,15 @@ class PfbChannelizer(object):
         check(self.e.lib.rcb_pfb_set_out_block(self.e.h, int(frames)), "rcb_pfb_set_out_block", self.e.h)
         self.out_block = int(frames)
 
+    _RAW_DTYPES = {_lib.FMT_U8: np.uint8, _lib.FMT_S8: np.int8, _lib.FMT_S16: np.int16}
+
+    def set_input_format(self, fmt, offset=0.0, scale=1.0):
+        """Fused ingest: process() / process_device() then take interleaved integer I/Q (FMT_U8 / FMT_S8 / FMT_S16),
+        sample = (v + offset) * scale; fmt 0 = complex64 again.  Resets the streaming state."""
+        check(self.e.lib.rcb_pfb_set_input_format(self.e.h, int(fmt), float(offset), float(scale)),
+              "rcb_pfb_set_input_format", self.e.h)
+        self.in_fmt = int(fmt)
+
     @staticmethod
     def unblock(arr, nchans, frames, block):
         """[nblocks][nchans][block] device layout (flat) -> [nchans][frames]."""
@@ -209,10 +218,16 @@ class PfbChannelizer(object):
         """iq: complex64 host array, len multiple of nchans.  Returns (iq_out, fm_out) (None where not produced):
         [N][T] arrays, or - after set_out_block(b) - [ceil(T / b)][N][b] arrays (each channel as contiguous b-sample
         messages; `unblock` gives the [N][T] view back)."""
-        iq = np.ascontiguousarray(iq, dtype=np.complex64)
-        if len(iq) % self.nchans:
+        fmt = getattr(self, "in_fmt", 0)
+        if fmt:
+            iq = np.ascontiguousarray(iq, dtype=self._RAW_DTYPES[fmt]).reshape(-1)
+            nsamp = len(iq) // 2
+        else:
+            iq = np.ascontiguousarray(iq, dtype=np.complex64)
+            nsamp = len(iq)
+        if nsamp % self.nchans:
             raise ValueError("nsamples must be a multiple of nchans")
-        t = len(iq) // self.nchans
+        t = nsamp // self.nchans
         b = getattr(self, "out_block", 0)
         shape = (-(-t // b), self.nchans, b) if b else (self.nchans, t)
         if (self.out_mask & OUT_IQ) and out_iq is None:
@@ -221,7 +236,7 @@ class PfbChannelizer(object):
             out_fm = np.empty(shape, dtype=np.float32)
         nout = C.c_size_t(0)
         check(self.e.lib.rcb_pfb_process(
-            self.e.h, iq.ctypes.data, len(iq), MEM_HOST,
+            self.e.h, iq.ctypes.data, nsamp, MEM_HOST,
             out_iq.ctypes.data if out_iq is not None else None,
             out_fm.ctypes.data if out_fm is not None else None,
             max(t, 1), MEM_HOST, C.byref(nout)), "rcb_pfb_process", self.e.h)

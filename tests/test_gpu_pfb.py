@@ -154,6 +154,16 @@ def test_copy_ceiling_reports_both_directions(engine):
     assert h2d > 1.0 and d2h > 1.0 and wall > 0
 
 
+@pytest.mark.parametrize("n,tpa,frames,mode", [(64, 20, 300, OUT_IQ | OUT_FM), (256, 40, 100, OUT_FM), (1024, 24, 64, OUT_FM),
+                                               (1024, 256, 300, OUT_FM)])
+def test_pfb_more_than_16_taps_per_arm(engine, n, tpa, frames, mode):
+    """P > 16 runs the register-prefetch kernel (pfb_fm_kernel, taps streamed from global memory): the third reading
+    of BASELINE's "256-tap / 1024-channel" (256 taps PER ARM, bench.py also.tap_readings) included."""
+    taps = fd.pfb_prototype(n, tpa)
+    assert -(-len(taps) // n) == tpa
+    _check(engine, n, taps, frames, seed=3000 + tpa, mode=mode, active_every=8 if n == 1024 else 2)
+
+
 def test_pfb_cfg3_literal_256_taps_1024_channels(engine):
     """BASELINE config 3, literal reading: 256-tap prototype, 1024 channels -> 1 tap/arm, 768 zero arms."""
     taps = fd.pfb_prototype(4, 64)  # any 256-tap low-pass
