@@ -602,12 +602,10 @@ def run_e2e_ddc(device, wl, steps, dist, local, log2n=24):
     chk = 0.0
     for _ in range(steps):
         ctx.bank.process(hin)
-        d2h = 0
-        for cid in ctx.ids:
-            y = ctx.bank.pull(cid, OUT_IQ)
-            f = ctx.bank.pull(cid, OUT_FM)
-            d2h += y.nbytes + f.nbytes
-            chk += float(f[-1])
+        ys = ctx.bank.pull_all(OUT_IQ)     # one transfer per output kind for all channels
+        fs = ctx.bank.pull_all(OUT_FM)
+        d2h = sum(v.nbytes for v in ys.values()) + sum(v.nbytes for v in fs.values())
+        chk += float(sum(v[-1] for v in fs.values() if len(v)))
     dt = time.perf_counter() - t0
     barrier(dist, local)
     ctx.close()
@@ -736,7 +734,7 @@ def run_b200(args):
         api = "rcb_fft_process(host pinned in, host out)"
     elif is_ddc:
         e2e_v, h2d, d2h, chk = run_e2e_ddc(device, wl, args.e2e_steps, dist, local)
-        api = "rcb_ddc_process(host pinned in) + rcb_ddc_pull(host out) per channel"
+        api = "rcb_ddc_process(host pinned in) + rcb_ddc_pull_all(host out) for IQ and FM"
     else:
         e2e_v, h2d, d2h, chk = run_e2e(device, wl, args.e2e_steps, 1, dist, local, out_block=out_block)
     e2e_v = e2e_v * world if dist is None else allreduce_sum_min(dist, local, e2e_v, world)

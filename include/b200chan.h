@@ -123,6 +123,11 @@ int rcb_ddc_close(rcb_t* h, int chan_id);
 int rcb_ddc_process(rcb_t* h, const void* iq, size_t nsamples, int in_mem);
 int rcb_ddc_pull(rcb_t* h, int chan_id, int which, void* dst, size_t cap_items, int dst_mem,
                  size_t* nitems);
+/* Every open channel's outputs of the last rcb_ddc_process call in ONE transfer (the per-channel pulls of a source
+ * with many channels cost more than the kernels): row r of dst (row_stride_items apart) receives counts[r] items of
+ * channel ids[r] (ascending chan_id; ids may be NULL).  *nrows = channels; cap_rows < *nrows -> RCB_ERANGE. */
+int rcb_ddc_pull_all(rcb_t* h, int which, void* dst, size_t row_stride_items, int dst_mem, int* ids, size_t* counts,
+                     size_t cap_rows, size_t* nrows);
 
 /* ---- K4: stand-alone quadrature demod / AFC probe on narrowband rows ---------------------------
  * out[r][n] = gain * atan2(Im p, Re p), p = x[r][n] conj(x[r][n-1]); prev (rows complex64, may be

@@ -97,6 +97,7 @@ _PROTOTYPES = {
     "rcb_ddc_close": (C.c_int, [_vp, C.c_int]),
     "rcb_ddc_process": (C.c_int, [_vp, _vp, _sz, C.c_int]),
     "rcb_ddc_pull": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _sz, C.c_int, C.POINTER(_sz)]),
+    "rcb_ddc_pull_all": (C.c_int, [_vp, C.c_int, _vp, _sz, C.c_int, _vp, _vp, _sz, C.POINTER(_sz)]),
     "rcb_quad_demod": (C.c_int, [_vp, _vp, _sz, _sz, _sz, C.c_float, _vp, _vp, _sz, C.c_int]),
     "rcb_probe_mean": (C.c_int, [_vp, _vp, _sz, _sz, _sz, _sz, C.c_float, _vp, C.c_int]),
     "rcb_convert_iq": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_float, _sz, C.c_int, _vp, C.c_int]),

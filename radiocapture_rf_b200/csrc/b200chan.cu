@@ -18,6 +18,7 @@
 #include "ddc_bank.cuh"
 #include "demod.cuh"
 #include "fft_logpow.cuh"
+#include "fft_scan.cuh"
 #include "pfb_fm.cuh"
 #include "pfb_fm_tma.cuh"
 #include "pfb_fm_ws.cuh"
@@ -44,7 +45,8 @@ struct DdcChan {
     float4* d_ctaps4_rev = nullptr;
     float2* d_out_iq = nullptr;
     float* d_out_fm = nullptr;
-    float2* d_prev = nullptr;
+    float2* d_prev = nullptr;  // [2]: FM carry, double buffered
+    int prev_cur = 0;
     size_t out_cap = 0;
     size_t nout_last = 0;
     uint64_t start_sample = 0;  // stream position of the newest sample of output 0
@@ -121,12 +123,22 @@ struct rcb_ctx {
         uint64_t n_consumed = 0;
         float2* d_in = nullptr;
         size_t in_cap = 0;
-        DdcChanDev* d_chans = nullptr;
-        DdcChanDev* h_chans = nullptr;  // pinned
+        DdcChanDev* d_chans = nullptr;      // current slot of the rings below
+        DdcChanDev* h_chans = nullptr;
+        DdcChanDev* d_chans_ring = nullptr;
+        DdcChanDev* h_chans_ring = nullptr;  // pinned
         size_t chans_cap = 0;
         DdcGroupDev* d_groups = nullptr;
-        DdcGroupDev* h_groups = nullptr;  // pinned
+        DdcGroupDev* h_groups = nullptr;
+        DdcGroupDev* d_groups_ring = nullptr;
+        DdcGroupDev* h_groups_ring = nullptr;  // pinned
         size_t groups_cap = 0;
+        unsigned long long slot_no = 0;
+        cudaEvent_t ev_slot[4] = {nullptr, nullptr, nullptr, nullptr};
+        float2* d_in2[2] = {nullptr, nullptr};   // host-input staging (chunked)
+        size_t in_cap2[2] = {0, 0};
+        cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+        bool in_used[2] = {false, false};
     } ddc;
 
     // ---- FFT ----
@@ -768,10 +780,17 @@ extern "C" int rcb_close(rcb_t* h) {
     cudaFree(h->ddc.d_hist[0]);
     cudaFree(h->ddc.d_hist[1]);
     cudaFree(h->ddc.d_in);
-    cudaFree(h->ddc.d_chans);
-    if (h->ddc.h_chans) cudaFreeHost(h->ddc.h_chans);
-    cudaFree(h->ddc.d_groups);
-    if (h->ddc.h_groups) cudaFreeHost(h->ddc.h_groups);
+    cudaFree(h->ddc.d_chans_ring);
+    if (h->ddc.h_chans_ring) cudaFreeHost(h->ddc.h_chans_ring);
+    cudaFree(h->ddc.d_groups_ring);
+    if (h->ddc.h_groups_ring) cudaFreeHost(h->ddc.h_groups_ring);
+    for (int i = 0; i < 4; ++i)
+        if (h->ddc.ev_slot[i]) cudaEventDestroy(h->ddc.ev_slot[i]);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(h->ddc.d_in2[i]);
+        if (h->ddc.ev_in[i]) cudaEventDestroy(h->ddc.ev_in[i]);
+        if (h->ddc.ev_done[i]) cudaEventDestroy(h->ddc.ev_done[i]);
+    }
     fft_free(h->fft);
     cudaFree(h->d_tmp[0]);
     cudaFree(h->d_tmp[1]);
@@ -1331,8 +1350,8 @@ extern "C" int rcb_ddc_open(rcb_t* h, int decim, const float* taps, int ntaps, d
     c.start_sample = ((h->ddc.n_consumed + (uint64_t)decim - 1) / (uint64_t)decim) * (uint64_t)decim;
     rc = ddc_upload_taps(h, c);
     if (rc) return rc;
-    CK(cudaMalloc(&c.d_prev, sizeof(float2)));
-    CK(cudaMemsetAsync(c.d_prev, 0, sizeof(float2), h->stream));
+    CK(cudaMalloc(&c.d_prev, 2 * sizeof(float2)));
+    CK(cudaMemsetAsync(c.d_prev, 0, 2 * sizeof(float2), h->stream));
     h->ddc.chans[c.id] = c;
     *chan_id = c.id;
     return RCB_OK;
@@ -1378,47 +1397,36 @@ extern "C" int rcb_ddc_close(rcb_t* h, int chan_id) {
     return RCB_OK;
 }
 
-extern "C" int rcb_ddc_process(rcb_t* h, const void* iq, size_t nsamples, int in_mem) {
-    if (!h || (!iq && nsamples)) return RCB_EINVAL;
-    if (in_mem != RCB_MEM_HOST && in_mem != RCB_MEM_DEVICE) return RCB_EINVAL;
-    if (nsamples > ((size_t)1 << 31)) return RCB_ERANGE;
-    CK(cudaSetDevice(h->device));
+namespace {
+
+constexpr int kDdcSlots = 4;            // pinned parameter blocks in flight (one per chunk)
+constexpr size_t kDdcChunk = 1u << 22;  // host input is staged in chunks of this many samples (H2D overlaps compute)
+
+// one device-resident piece of the wideband stream through every open channel; outputs are APPENDED to what this
+// rcb_ddc_process call has produced so far (c.nout_last)
+int ddc_process_chunk(rcb_t* h, const float2* d_x, size_t nsamples) {
     auto& d = h->ddc;
-    int rc = ddc_ensure_hist(h);
-    if (rc) return rc;
-    if (nsamples == 0) {
-        for (auto& kv : d.chans) kv.second.nout_last = 0;
-        return RCB_OK;
-    }
-    const float2* d_x;
-    if (in_mem == RCB_MEM_HOST) {
-        if (d.in_cap < nsamples) {
-            cudaFree(d.d_in);
-            d.d_in = nullptr;
-            d.in_cap = 0;
-            CK(cudaMalloc(&d.d_in, nsamples * sizeof(float2)));
-            d.in_cap = nsamples;
-        }
-        CK(cudaMemcpyAsync(d.d_in, iq, nsamples * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
-        h->stats.h2d_bytes += nsamples * sizeof(float2);
-        d_x = d.d_in;
-    } else {
-        d_x = (const float2*)iq;
-    }
     const size_t M = d.chans.size();
     if (M) {
         if (d.chans_cap < M) {
-            cudaFree(d.d_chans);
-            if (d.h_chans) cudaFreeHost(d.h_chans);
-            d.d_chans = nullptr;
-            d.h_chans = nullptr;
+            CK(cudaStreamSynchronize(h->stream));
+            cudaFree(d.d_chans_ring);
+            if (d.h_chans_ring) cudaFreeHost(d.h_chans_ring);
+            d.d_chans_ring = nullptr;
+            d.h_chans_ring = nullptr;
             d.chans_cap = 0;
             const size_t cap = std::max<size_t>(16, M * 2);
-            CK(cudaMalloc(&d.d_chans, cap * sizeof(DdcChanDev)));
-            CK(cudaHostAlloc(&d.h_chans, cap * sizeof(DdcChanDev), cudaHostAllocDefault));
+            CK(cudaMalloc(&d.d_chans_ring, kDdcSlots * cap * sizeof(DdcChanDev)));
+            CK(cudaHostAlloc(&d.h_chans_ring, kDdcSlots * cap * sizeof(DdcChanDev), cudaHostAllocDefault));
             d.chans_cap = cap;
         }
-        CK(cudaStreamSynchronize(h->stream));  // h_chans reuse + previous outputs consumed
+        // parameter blocks live in a ring of pinned slots: no stream synchronisation per block, a slot is reused only
+        // after the upload that read it has completed
+        const int slot = (int)(d.slot_no++ % kDdcSlots);
+        if (!d.ev_slot[slot]) CK(cudaEventCreateWithFlags(&d.ev_slot[slot], cudaEventDisableTiming));
+        else CK(cudaEventSynchronize(d.ev_slot[slot]));
+        d.h_chans = d.h_chans_ring + (size_t)slot * d.chans_cap;
+        d.d_chans = d.d_chans_ring + (size_t)slot * d.chans_cap;
         const uint64_t n0 = d.n_consumed, n1 = d.n_consumed + nsamples;
         size_t max_nout = 0;
         size_t ci = 0;
@@ -1429,23 +1437,16 @@ extern "C" int rcb_ddc_process(rcb_t* h, const void* iq, size_t nsamples, int in
             const uint64_t s_next = c.start_sample + c.i_next * (uint64_t)c.decim;
             size_t nout = 0;
             if (s_next < n1) nout = (size_t)((n1 - 1 - s_next) / (uint64_t)c.decim) + 1;
-            if (c.out_cap < nout) {
-                cudaFree(c.d_out_iq);
-                cudaFree(c.d_out_fm);
-                c.d_out_iq = nullptr;
-                c.d_out_fm = nullptr;
-                c.out_cap = 0;
-                const size_t cap = nout + nout / 4 + 16;
-                CK(cudaMalloc(&c.d_out_iq, cap * sizeof(float2)));
-                CK(cudaMalloc(&c.d_out_fm, cap * sizeof(float)));
-                c.out_cap = cap;
-            }
+            const size_t base = c.nout_last;  // appended after the earlier chunks of this call
+            if (c.out_cap < base + nout) return RCB_ERANGE;  // (capacity is reserved by rcb_ddc_process)
             DdcChanDev& dv = d.h_chans[ci++];
             dv.ctaps_rev = c.d_ctaps_rev;
             dv.ctaps4_rev = c.d_ctaps4_rev;
-            dv.out_iq = c.d_out_iq;
-            dv.out_fm = (c.out_mask & RCB_OUT_FM) ? c.d_out_fm : nullptr;
-            dv.prev = c.d_prev;
+            dv.out_iq = c.d_out_iq + base;
+            dv.out_fm = (c.out_mask & RCB_OUT_FM) ? c.d_out_fm + base : nullptr;
+            dv.prev = c.d_prev + (c.prev_cur & 1);          // FM carry in
+            dv.prev_out = c.d_prev + ((c.prev_cur ^ 1) & 1);  // carry out (double buffered: ddc_post_kernel reads and
+            if (nout > 0) c.prev_cur ^= 1;                    // writes it in the same launch)
             dv.cyc = c.cyc;
             dv.phase0 = ddc_phase_at(c, c.i_next);
             dv.s_first = (long long)s_next - (long long)n0;
@@ -1457,7 +1458,7 @@ extern "C" int rcb_ddc_process(rcb_t* h, const void* iq, size_t nsamples, int in
             // fast path needs every window sample of this block to lie at / after the channel's first sample
             dv.fast = (nout > 0 && dv.s_open <= dv.s_first - (long long)(c.ntaps - 1) &&
                        (size_t)(7 * c.decim + c.ntaps) * sizeof(float2) <= 160 * 1024) ? 1 : 0;
-            c.nout_last = nout;
+            c.nout_last = base + nout;
             c.i_next += nout;
             max_nout = std::max(max_nout, nout);
             any_fm |= (dv.out_fm != nullptr);
@@ -1476,16 +1477,19 @@ extern "C" int rcb_ddc_process(rcb_t* h, const void* iq, size_t nsamples, int in
         size_t ngroups = 0;
         for (auto& b : buckets) ngroups += (b.second.size() + 15) / 16;
         if (ngroups > d.groups_cap) {
-            cudaFree(d.d_groups);
-            if (d.h_groups) cudaFreeHost(d.h_groups);
-            d.d_groups = nullptr;
-            d.h_groups = nullptr;
+            CK(cudaStreamSynchronize(h->stream));
+            cudaFree(d.d_groups_ring);
+            if (d.h_groups_ring) cudaFreeHost(d.h_groups_ring);
+            d.d_groups_ring = nullptr;
+            d.h_groups_ring = nullptr;
             d.groups_cap = 0;
             const size_t cap = std::max<size_t>(8, ngroups * 2);
-            CK(cudaMalloc(&d.d_groups, cap * sizeof(DdcGroupDev)));
-            CK(cudaHostAlloc(&d.h_groups, cap * sizeof(DdcGroupDev), cudaHostAllocDefault));
+            CK(cudaMalloc(&d.d_groups_ring, kDdcSlots * cap * sizeof(DdcGroupDev)));
+            CK(cudaHostAlloc(&d.h_groups_ring, kDdcSlots * cap * sizeof(DdcGroupDev), cudaHostAllocDefault));
             d.groups_cap = cap;
         }
+        d.h_groups = d.h_groups_ring + (size_t)slot * d.groups_cap;
+        d.d_groups = d.d_groups_ring + (size_t)slot * d.groups_cap;
         CK(cudaMemcpyAsync(d.d_chans, d.h_chans, M * sizeof(DdcChanDev), cudaMemcpyHostToDevice, h->stream));
         if (max_nout) {
             size_t gi = 0;
@@ -1553,22 +1557,148 @@ extern "C" int rcb_ddc_process(rcb_t* h, const void* iq, size_t nsamples, int in
                                                             kDdcHistCap);
                 CKL(h);
             }
-            if (any_fm) {
-                dim3 g2((unsigned)((max_nout + 255) / 256), (unsigned)M);
-                ddc_fm_kernel<<<g2, 256, 0, h->stream>>>(d.d_chans);
-                CKL(h);
-            }
-            ddc_carry_kernel<<<(unsigned)((M + 127) / 128), 128, 0, h->stream>>>(d.d_chans, (int)M);
-            CKL(h);
         }
+        CK(cudaEventRecord(d.ev_slot[slot], h->stream));  // both parameter uploads of this slot are behind this point
+        // FM demod of this chunk's outputs + FM carry + wideband history update: ONE launch (ddc_post_kernel)
+        {
+            const unsigned gx = (unsigned)std::max<size_t>((max_nout + 255) / 256, (kDdcHistCap + 255) / 256);
+            dim3 g2(gx, (unsigned)M + 1);
+            const int nxt = d.hist_cur ^ 1;
+            ddc_post_kernel<<<g2, 256, 0, h->stream>>>(d.d_chans, (int)M, d.d_hist[d.hist_cur], d_x, (long long)nsamples,
+                                                     d.d_hist[nxt], kDdcHistCap);
+            CKL(h);
+            d.hist_cur = nxt;
+        }
+        (void)any_fm;
+    } else {
+        const int nxt = d.hist_cur ^ 1;
+        hist_update_kernel<<<(kDdcHistCap + 255) / 256, 256, 0, h->stream>>>(d.d_hist[d.hist_cur], d_x, (long long)nsamples,
+                                                                            d.d_hist[nxt], kDdcHistCap);
+        CKL(h);
+        d.hist_cur = nxt;
     }
-    const int nxt = d.hist_cur ^ 1;
-    hist_update_kernel<<<(kDdcHistCap + 255) / 256, 256, 0, h->stream>>>(d.d_hist[d.hist_cur], d_x, (long long)nsamples,
-                                                                        d.d_hist[nxt], kDdcHistCap);
-    CKL(h);
-    d.hist_cur = nxt;
     d.n_consumed += nsamples;
     h->stats.samples_in += nsamples;
+    return RCB_OK;
+}
+
+}  // namespace
+
+extern "C" int rcb_ddc_process(rcb_t* h, const void* iq, size_t nsamples, int in_mem) {
+    if (!h || (!iq && nsamples)) return RCB_EINVAL;
+    if (in_mem != RCB_MEM_HOST && in_mem != RCB_MEM_DEVICE) return RCB_EINVAL;
+    if (nsamples > ((size_t)1 << 31)) return RCB_ERANGE;
+    CK(cudaSetDevice(h->device));
+    auto& d = h->ddc;
+    int rc = ddc_ensure_hist(h);
+    if (rc) return rc;
+    for (auto& kv : d.chans) kv.second.nout_last = 0;
+    if (nsamples == 0) return RCB_OK;
+    // reserve every channel's output capacity for the whole call (chunks append)
+    {
+        const uint64_t n1 = d.n_consumed + nsamples;
+        bool synced = false;
+        for (auto& kv : d.chans) {
+            DdcChan& c = kv.second;
+            const uint64_t s_next = c.start_sample + c.i_next * (uint64_t)c.decim;
+            size_t nout = 0;
+            if (s_next < n1) nout = (size_t)((n1 - 1 - s_next) / (uint64_t)c.decim) + 1;
+            if (c.out_cap < nout) {
+                if (!synced) {
+                    CK(cudaStreamSynchronize(h->stream));
+                    synced = true;
+                }
+                cudaFree(c.d_out_iq);
+                cudaFree(c.d_out_fm);
+                c.d_out_iq = nullptr;
+                c.d_out_fm = nullptr;
+                c.out_cap = 0;
+                const size_t cap = nout + nout / 4 + 16;
+                CK(cudaMalloc(&c.d_out_iq, cap * sizeof(float2)));
+                CK(cudaMalloc(&c.d_out_fm, cap * sizeof(float)));
+                c.out_cap = cap;
+            }
+        }
+    }
+    if (in_mem == RCB_MEM_DEVICE) return ddc_process_chunk(h, (const float2*)iq, nsamples);
+    // host input: chunks through two staging buffers, the H2D of chunk k + 1 (copy stream) overlaps the kernels of chunk k
+    const size_t csz = std::min(nsamples, kDdcChunk);
+    for (int i = 0; i < 2; ++i) {
+        if (d.in_cap2[i] < csz) {
+            CK(cudaStreamSynchronize(h->stream));
+            cudaFree(d.d_in2[i]);
+            d.d_in2[i] = nullptr;
+            d.in_cap2[i] = 0;
+            CK(cudaMalloc(&d.d_in2[i], csz * sizeof(float2)));
+            d.in_cap2[i] = csz;
+        }
+        if (!d.ev_in[i]) CK(cudaEventCreateWithFlags(&d.ev_in[i], cudaEventDisableTiming));
+        if (!d.ev_done[i]) CK(cudaEventCreateWithFlags(&d.ev_done[i], cudaEventDisableTiming));
+    }
+    size_t done = 0;
+    int k = 0;
+    while (done < nsamples) {
+        const int sl = k & 1;
+        const size_t n = std::min(csz, nsamples - done);
+        if (d.in_used[sl]) CK(cudaStreamWaitEvent(h->s_in, d.ev_done[sl], 0));  // the kernels that read this buffer are done
+        CK(cudaMemcpyAsync(d.d_in2[sl], (const float2*)iq + done, n * sizeof(float2), cudaMemcpyHostToDevice, h->s_in));
+        h->stats.h2d_bytes += n * sizeof(float2);
+        CK(cudaEventRecord(d.ev_in[sl], h->s_in));
+        CK(cudaStreamWaitEvent(h->stream, d.ev_in[sl], 0));
+        rc = ddc_process_chunk(h, d.d_in2[sl], n);
+        if (rc) return rc;
+        CK(cudaEventRecord(d.ev_done[sl], h->stream));
+        d.in_used[sl] = true;
+        done += n;
+        ++k;
+    }
+    return RCB_OK;
+}
+
+// every channel's outputs of the last rcb_ddc_process call in ONE transfer: row c (channels in ascending id order) of
+// dst holds counts[c] items (`which` = RCB_OUT_IQ: complex64, RCB_OUT_FM: float32; channels without FM give 0).
+extern "C" int rcb_ddc_pull_all(rcb_t* h, int which, void* dst, size_t row_stride_items, int dst_mem, int* ids,
+                                size_t* counts, size_t cap_rows, size_t* nrows) {
+    if (!h || !nrows) return RCB_EINVAL;
+    if (which != RCB_OUT_IQ && which != RCB_OUT_FM) return RCB_EINVAL;
+    auto& d = h->ddc;
+    const size_t M = d.chans.size();
+    *nrows = M;
+    if (M == 0) return RCB_OK;
+    if (!dst || !counts || cap_rows < M) return RCB_ERANGE;
+    CK(cudaSetDevice(h->device));
+    const size_t isz = (which == RCB_OUT_IQ) ? sizeof(float2) : sizeof(float);
+    size_t mx = 0, r = 0;
+    std::vector<const void*> src(M);
+    std::vector<int> cnt(M);
+    for (auto& kv : d.chans) {
+        DdcChan& c = kv.second;
+        const bool has = (which == RCB_OUT_IQ) || (c.out_mask & RCB_OUT_FM);
+        const size_t n = has ? c.nout_last : 0;
+        if (ids) ids[r] = c.id;
+        counts[r] = n;
+        cnt[r] = (int)n;
+        src[r] = (which == RCB_OUT_IQ) ? (const void*)c.d_out_iq : (const void*)c.d_out_fm;
+        mx = std::max(mx, n);
+        ++r;
+    }
+    if (mx == 0) return RCB_OK;
+    if (mx > row_stride_items) return RCB_ERANGE;
+    // gather into one dense [M][mx] block, then one copy
+    int rc = ensure_tmp(h, 0, M * mx * isz + M * (sizeof(void*) + sizeof(int)) + 64);
+    if (rc) return rc;
+    char* base = (char*)h->d_tmp[0];
+    const void** d_src = (const void**)(base + ((M * mx * isz + 15) / 16) * 16);
+    int* d_cnt = (int*)(d_src + M);
+    CK(cudaMemcpyAsync(d_src, src.data(), M * sizeof(void*), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_cnt, cnt.data(), M * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    dim3 grid((unsigned)((mx * (isz / 4) + 255) / 256), (unsigned)M);
+    ddc_gather_kernel<<<grid, 256, 0, h->stream>>>(d_src, d_cnt, (int)(isz / 4), (unsigned*)base, (long long)(mx * (isz / 4)));
+    CKL(h);
+    CK(cudaMemcpy2DAsync(dst, row_stride_items * isz, base, mx * isz, mx * isz, M,
+                         dst_mem == RCB_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // src / cnt are stack vectors
+    if (dst_mem == RCB_MEM_HOST) h->stats.d2h_bytes += M * mx * isz;
     return RCB_OK;
 }
 
@@ -1737,7 +1867,14 @@ extern "C" int rcb_fft_process(rcb_t* h, const void* iq, size_t nsamples, int in
     if (nsamples % (size_t)h->fft.L) return RCB_EINVAL;
     CK(cudaSetDevice(h->device));
     uint64_t launches = 0, h2d = 0, d2h = 0;
-    int rc = fft_process(h->fft, (const float2*)iq, nsamples, in_mem, (float*)out_sums, cap_vectors, out_mem, nvec,
+    // one persistent launch per call (fft_scan.cuh); the round-1 three-kernel pipeline remains as the fallback for inputs
+    // a TMA descriptor cannot address
+    int rc = 1;
+    if (h->fft.use_scan)
+        rc = fft_process_scan(h->fft, (const float2*)iq, nsamples, in_mem, (float*)out_sums, cap_vectors, out_mem, nvec,
+                              h->stream, &launches, &h2d, &d2h, h->sm_count);
+    if (rc == 1)
+        rc = fft_process(h->fft, (const float2*)iq, nsamples, in_mem, (float*)out_sums, cap_vectors, out_mem, nvec,
                          h->stream, &launches, &h2d, &d2h, h->sm_count);
     h->stats.kernel_launches += launches;
     h->stats.h2d_bytes += h2d;

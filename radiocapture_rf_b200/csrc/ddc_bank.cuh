@@ -26,7 +26,8 @@ struct DdcChanDev {
                               //          packed complex MAC  acc += x.re * (t.re, t.im) + x.im * (-t.im, t.re)
     float2* out_iq;           // [nout] this block's outputs
     float* out_fm;            // [nout] or null
-    float2* prev;             // device scalar: last output of the previous block (FM carry)
+    float2* prev;             // device scalar: last output of the previous block (FM carry in)
+    float2* prev_out;         // where this block's last output goes (the other half of the double buffer)
     double cyc;               // frac(f0 * D / fs)  (cycles per output, reduced mod 1)
     double phase0;            // frac(cyc * i_first)
     long long s_first;        // block-relative index of the newest input sample of output 0 (may be < 0)
@@ -217,6 +218,39 @@ __global__ void ddc_carry_kernel(const DdcChanDev* __restrict__ chans, int M) {
     if (c >= M) return;
     const DdcChanDev ch = chans[c];
     if (ch.nout > 0) *ch.prev = ch.out_iq[ch.nout - 1];
+}
+
+// FM demod of every channel's block + FM carry + wideband history update in ONE launch (was three).
+// grid (max(ceil(max_nout / 256), ceil(cap / 256)), M + 1): rows 0..M-1 = channels, row M = history copy.
+__global__ void __launch_bounds__(256) ddc_post_kernel(const DdcChanDev* __restrict__ chans, int M,
+                                                       const float2* __restrict__ old_hist, const float2* __restrict__ x,
+                                                       long long n, float2* __restrict__ new_hist, long long cap) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((int)blockIdx.y == M) {
+        if (i >= cap) return;
+        const long long src = i + n - cap;  // index into x; negative -> old hist
+        new_hist[i] = (src >= 0) ? x[src] : ((src >= -cap) ? old_hist[cap + src] : make_float2(0.f, 0.f));
+        return;
+    }
+    const DdcChanDev ch = chans[blockIdx.y];
+    if (i >= ch.nout) return;
+    const int o = (int)i;
+    const float2 c = ch.out_iq[o];
+    if (ch.out_fm) {
+        const float2 pv = (o == 0) ? *ch.prev : ch.out_iq[o - 1];
+        const float2 pr = cmul_conj(c, pv);
+        ch.out_fm[o] = ch.gain * atan2_fast(pr.y, pr.x);
+    }
+    if (o == ch.nout - 1) *ch.prev_out = c;
+}
+
+// rows of 32-bit words from M separately allocated channel buffers into one dense [M][stride] block (rcb_ddc_pull_all)
+__global__ void __launch_bounds__(256) ddc_gather_kernel(const void* const* __restrict__ src, const int* __restrict__ cnt,
+                                                         int words_per_item, unsigned* __restrict__ dst, long long stride) {
+    const int r = blockIdx.y;
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= (long long)cnt[r] * words_per_item) return;
+    dst[(long long)r * stride + w] = reinterpret_cast<const unsigned*>(src[r])[w];
 }
 
 // new_hist (cap samples) = last `cap` samples of (old_hist ++ x[0..n))

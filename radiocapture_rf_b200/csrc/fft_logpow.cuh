@@ -365,6 +365,13 @@ struct FftState {
     size_t emit_cap = 0;
     float2* d_in = nullptr;   // staging for host input
     size_t in_cap = 0;
+    // persistent scan kernel (fft_scan.cuh)
+    bool use_scan = true;
+    float2* d_ring = nullptr;     // scratch ring, `ring` frames
+    int ring = 0, la = 0, scan_grid = 0;
+    unsigned* d_ctl = nullptr;    // [1 task counter | ring cols_done | ring rows_done | row tiles tile_seq]
+    size_t ctl_words = 0;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
 };
 
 inline void fft_free(FftState& s) {
@@ -390,6 +397,12 @@ inline void fft_free(FftState& s) {
     cudaFree(s.d_acc);
     cudaFree(s.d_emit);
     cudaFree(s.d_in);
+    cudaFree(s.d_ring);
+    cudaFree(s.d_ctl);
+    for (int i = 0; i < 2; ++i) {
+        if (s.ev_copy[i]) cudaEventDestroy(s.ev_copy[i]);
+        if (s.ev_used[i]) cudaEventDestroy(s.ev_used[i]);
+    }
     s = FftState{};
 }
 
@@ -435,12 +448,16 @@ inline int fft_config(FftState& s, int L, const float* window, int avg, cudaStre
     s.L1 = r1 * r1;
     s.L2 = r2 * r2;
     s.avg = avg;
+    // the persistent scan kernel (fft_scan.cuh) pays off where a frame is many tiles (its per-tile dependency counters
+    // and in-order accumulation serialise short frames): 2^18 / 2^20 points; the three-kernel pipeline runs the rest
+    s.use_scan = (L >= (1 << 18));
     // sub-batch: keep scratch (8 B) + vals (4 B) per sample under ~48 MB so they stay in L2
     size_t budget_mb = 48;
 #ifdef RCB_EXPERIMENTS  // tuning builds only (radiocapture_rf_b200.build.build_experiments): never in the shipped library
     if (const char* e = getenv("RCB_FFT_VARIANT")) {
         s.cols_tma = (atoi(e) != 1);
         s.rows_k1 = (atoi(e) == 3);
+        s.use_scan = (atoi(e) == 4) || (atoi(e) == 0 && s.use_scan);   // 4: scan kernel for every length; 1-3: never
     }
     if (const char* e = getenv("RCB_FFT_SCRATCH_MB")) budget_mb = (size_t)std::max(1, atoi(e));
 #endif

@@ -310,6 +310,33 @@ class DdcBank(object):
               "rcb_ddc_pull", self.e.h)
         return n.value
 
+    def pull_all(self, which=OUT_IQ, max_items=None):
+        """Every open channel's outputs of the last process() call in ONE device-to-host transfer.
+        Returns {chan_id: array}."""
+        n = C.c_size_t(0)
+        st = self.e.lib.rcb_ddc_pull_all(self.e.h, int(which), None, 0, MEM_HOST, None, None, 0, C.byref(n))
+        if st not in (0, _lib.RCB_ERANGE):
+            check(st, "rcb_ddc_pull_all", self.e.h)
+        m = n.value
+        if m == 0:
+            return {}
+        if max_items is None:
+            max_items = getattr(self, "_last_max", 4096)
+        dt = np.complex64 if which == OUT_IQ else np.float32
+        ids = (C.c_int * m)()
+        counts = (C.c_size_t * m)()
+        while True:
+            out = np.empty((m, max_items), dtype=dt)
+            st = self.e.lib.rcb_ddc_pull_all(self.e.h, int(which), out.ctypes.data, max_items, MEM_HOST, ids, counts, m,
+                                             C.byref(n))
+            if st == _lib.RCB_ERANGE and max(counts) > max_items:   # rows longer than guessed: counts are valid, retry
+                max_items = int(max(counts))
+                continue
+            check(st, "rcb_ddc_pull_all", self.e.h)
+            break
+        self._last_max = max(int(max(counts)), 1)
+        return {int(ids[r]): out[r, :counts[r]].copy() for r in range(m)}
+
     def pull(self, chan, which=OUT_IQ):
         n = C.c_size_t(0)
         # first ask for the size (dst NULL is only legal when there is nothing to fetch)

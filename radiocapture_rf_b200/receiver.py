@@ -86,8 +86,13 @@ class SourceStream(object):
         with self.lock:
             self.bank.process(iq)
             self.samples_in += len(iq)
-            for cid, ch in list(self.channels.items()):
-                ch.deliver(self.bank.pull(cid, OUT_IQ))
+            if hasattr(self.bank, "pull_all") and len(self.channels) > 1:
+                outs = self.bank.pull_all(OUT_IQ)     # one device-to-host transfer for every channel of the source
+                for cid, ch in list(self.channels.items()):
+                    ch.deliver(outs.get(cid, np.zeros(0, np.complex64)))
+            else:
+                for cid, ch in list(self.channels.items()):
+                    ch.deliver(self.bank.pull(cid, OUT_IQ))
             for hook in self.post_push:
                 hook()
 

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 400 python -m pytest tests/test_gpu_fft.py tests/test_gpu_ddc.py tests/test_gpu_frontend.py -q -m gpu --tb=short 2>&1 | tail -12
+timeout 200 python -m pytest tests/test_gpu_fullsize.py -q -m gpu --tb=short -x -k "fft or scan" 2>&1 | tail -3
+for w in cfg4 cfg4_16k cfg1 ddc64; do
+  timeout 200 python bench.py --workload $w --steps 10 --warmup 3 --no-cpu --no-also --e2e-steps 3 2>gpurun_out/bench_$w.err | tee gpurun_out/bench_$w.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['config']['workload'][:40], round(d['value']), round(d['roofline']['frac'],3), d['gpu_launches'], round(d['e2e']['value']), d['e2e'].get('pcie_ceiling',{}).get('frac'))"
+done

@@ -241,3 +241,62 @@ def test_ingest_conversion_bit_exact(engine, fmt, dt, off, sc):
     assert engine.convert_iq(raw, "u8", out_device=d) == 96 * 200
     x = engine.to_host(d, (96 * 200,), np.complex64)
     assert np.array_equal(x, ((raw.astype(np.float32) - np.float32(127.4)) * np.float32(1 / 128.0)).view(np.complex64))
+
+
+def test_pull_all_matches_per_channel_pulls_and_chunked_host_input(engine):
+    """rcb_ddc_pull_all = every channel's block in one transfer; host input longer than one staging chunk (2^22 samples)
+    is pipelined in chunks whose outputs are appended - same samples as per-channel pulls / one device-resident call."""
+    fs = 2.4e6
+    n = (1 << 22) + (1 << 20) + 12345
+    rng = np.random.default_rng(7)
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64) * np.float32(0.1)
+    decim, taps = fd.channel_taps(fs, 12500)
+    bank = DdcBank(engine)
+    ids = [bank.open(decim, taps, f, fs, OUT_IQ | OUT_FM, 5.0) for f in (-62500.0, 12500.0, 437500.0)]
+    ids.append(bank.open(decim * 2, taps, 100000.0, fs, OUT_IQ, 1.0))     # another decimation grid, no FM
+    bank.process(x)
+    iq_all, fm_all = bank.pull_all(OUT_IQ), bank.pull_all(OUT_FM)
+    assert sorted(iq_all) == sorted(ids)
+    for c in ids:
+        assert np.array_equal(iq_all[c], bank.pull(c, OUT_IQ))
+    for c in ids[:3]:
+        assert np.array_equal(fm_all[c], bank.pull(c, OUT_FM))
+    assert len(fm_all[ids[3]]) == 0
+    # reference: the same stream from device memory in one piece on a fresh bank
+    bank2 = DdcBank(engine)
+    ids2 = [bank2.open(decim, taps, f, fs, OUT_IQ | OUT_FM, 5.0) for f in (-62500.0, 12500.0, 437500.0)]
+    d_x = engine.to_device(x)
+    bank2.process_device(d_x, n)
+    for a, b in zip(ids[:3], ids2):
+        assert np.array_equal(iq_all[a], bank2.pull(b, OUT_IQ))
+        assert np.array_equal(fm_all[a], bank2.pull(b, OUT_FM))
+    y = iq_all[ids[0]]
+    ref = gb.freq_xlating_fir(x[:96 * 4000], taps, decim, -62500.0, fs)
+    assert gb.rel_l2(y[:len(ref)], ref) <= 1e-5
+
+
+def test_two_engines_on_one_device_keep_their_shared_memory_opt_in(built_lib):
+    """cudaFuncSetAttribute is per function and per device - a second handle with a smaller tile must not
+    lower the limit the first handle's launches rely on (lone 12.5 kHz channel: 100 KB tile; group of 3: 26 KB)."""
+    from radiocapture_rf_b200.engine import Engine
+    fs = 2.4e6
+    decim, taps = fd.channel_taps(fs, 12500)
+    a, b = Engine(0), Engine(0)
+    try:
+        rng = np.random.default_rng(3)
+        x = (rng.standard_normal(96 * 500) + 1j * rng.standard_normal(96 * 500)).astype(np.complex64)
+        ba, bb = DdcBank(a), DdcBank(b)
+        ca = ba.open(decim, taps, -62500.0, fs)
+        cbs = [bb.open(decim, taps, f, fs) for f in (1e4, 2e4, 3e4)]
+        outs = []
+        for _ in range(3):     # alternate: A (large tile), B (small tile), A again ...
+            ba.process(x)
+            outs.append(ba.pull(ca))
+            bb.process(x)
+            bb.pull(cbs[0])
+        ref = gb.freq_xlating_fir(x, taps, decim, -62500.0, fs)
+        assert gb.rel_l2(outs[0][:len(ref)], ref[:len(outs[0])]) <= 1e-5
+        assert len(outs[2]) > 0
+    finally:
+        a.close()
+        b.close()
