@@ -475,10 +475,20 @@ class DdcCtx(object):
         self.e.close()
 
 
-def timed_loop(ctxs, steps, warmup, dist, local):
-    for _ in range(warmup):
+def step_all(ctxs):
+    """One step of every stream of this rank: multi-stream PFB workloads (BASELINE config 5) go through ONE
+    rcb_pfb_process_multi call (one batched kernel launch, blockIdx.y = stream)."""
+    if len(ctxs) > 1 and all(isinstance(c, StreamCtx) for c in ctxs):
+        from radiocapture_rf_b200.engine import pfb_process_multi
+        pfb_process_multi([c.ch for c in ctxs], [c.d_in for c in ctxs], ctxs[0].n, [c.d_fm for c in ctxs], ctxs[0].frames)
+    else:
         for c in ctxs:
             c.step()
+
+
+def timed_loop(ctxs, steps, warmup, dist, local):
+    for _ in range(warmup):
+        step_all(ctxs)
     for c in ctxs:
         c.e.sync()
     barrier(dist, local)
@@ -487,8 +497,7 @@ def timed_loop(ctxs, steps, warmup, dist, local):
         c.e.timer_start()
     t0 = time.time()
     for _ in range(steps):
-        for c in ctxs:
-            c.step()
+        step_all(ctxs)
     ms = max(c.e.timer_stop() for c in ctxs)   # events on each stream's own CUDA stream; streams run concurrently
     t1 = time.time()
     for c in ctxs:
@@ -500,16 +509,18 @@ def timed_loop(ctxs, steps, warmup, dist, local):
 
 def side_run(device, wl, world, dist, local, peak, steps, out_block, log2n=None, in_fmt=None, bytes_per_sample=None):
     """One extra device-resident measurement of a PFB workload for the `also` object."""
+    from radiocapture_rf_b200 import sharding
     cfg = WORKLOADS[wl]
-    ctxs = [StreamCtx(device, wl, seed=3 + i, log2n=log2n, out_block=out_block, in_fmt=in_fmt)
-            for i in range(cfg["streams"])]
+    w_, r_, _ = sharding.world_from_env()
+    ctxs = [StreamCtx(device, wl, seed=3 + sid, log2n=log2n, out_block=out_block, in_fmt=in_fmt)
+            for sid in sharding.assign_streams(cfg["streams"] * world, world, r_ if world > 1 else 0)]
     ms, _, _, _ = timed_loop(ctxs, steps, 3, dist, local)
-    ms = allreduce_max(dist, local, ms)
     tot = sum(c.n for c in ctxs) * steps
+    rate, ms = sharding.whole_job_rate(tot, ms, sharding.Reducer(dist, "cuda:%d" % local if dist is not None else None))
     bps = bytes_per_sample or ctxs[0].bytes_per_sample
     for c in ctxs:
         c.close()
-    return {"workload": cfg["desc"], "kernel": kernel_name(wl), "unit": "Msps", "value": tot * world / (ms * 1e-3) / 1e6,
+    return {"workload": cfg["desc"], "kernel": kernel_name(wl), "unit": "Msps", "value": rate / 1e6,
             "algorithmic_bytes_per_sample": bps, "roofline_frac": tot * bps / (ms * 1e-3) / 1e9 / peak}
 
 
@@ -595,7 +606,10 @@ def run_e2e_ddc(device, wl, steps, dist, local, log2n=24):
     n = ctx.n
     hin = ctx.e.pinned((n,), np.complex64)
     hin[:] = synth_block(n, 64, 5)
-    ctx.bank.process(hin)
+    for _ in range(2):   # warm-up incl. the pulls (staging buffers, row-length guess)
+        ctx.bank.process(hin)
+        ctx.bank.pull_all(OUT_IQ)
+        ctx.bank.pull_all(OUT_FM)
     barrier(dist, local)
     t0 = time.perf_counter()
     d2h = 0
@@ -658,8 +672,10 @@ def run_b200(args):
     is_pfb = not (is_fft or is_ddc)
     out_block = args.out_block if is_pfb else 0
     Ctx = FftCtx if is_fft else (DdcCtx if is_ddc else StreamCtx)
-    ctxs = [Ctx(device, wl, seed=3 + 100 * rank + i, log2n=args.log2n, out_block=out_block)
-            for i in range(cfg["streams"])]
+    # stream s of the job runs on rank s mod world (sharding.assign_streams): streams_per_gpu x world streams in total
+    from radiocapture_rf_b200 import sharding
+    my_streams = sharding.assign_streams(cfg["streams"] * world, world, rank)
+    ctxs = [Ctx(device, wl, seed=3 + sid, log2n=args.log2n, out_block=out_block) for sid in my_streams]
     sampler = ClockSampler(device)
     sampler.start()
     time.sleep(0.3)

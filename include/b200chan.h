@@ -106,6 +106,15 @@ int rcb_pfb_set_out_block(rcb_t* h, int frames);
 int rcb_pfb_set_input_format(rcb_t* h, int fmt, float offset, float scale);
 int rcb_pfb_process(rcb_t* h, const void* iq, size_t nsamples, int in_mem,
                     void* out_iq, void* out_fm, size_t out_stride, int out_mem, size_t* nout);
+/* Several independent wideband streams of ONE shape on one GPU in one call (one stream per SDR source,
+ * rc_frontend/receiver.py:67-70; systemd/radiocapture-channelizer@.service:11 runs one frontend per source): handle
+ * hs[i] carries stream i's configuration and streaming state exactly as for rcb_pfb_process, iq[i] / out_fm[i] are its
+ * device-resident input block (nsamples complex64) and FM output.  256-channel FM-only configurations with <= 16 taps
+ * per arm run as ONE kernel launch (blockIdx.y = stream) plus one history update; any other shape is processed stream
+ * after stream.  All handles must live on the same device and share nchans, ntaps, out_mask and output layout.
+ * Asynchronous; ordered after everything queued on every handle's stream, and every handle's later calls after it. */
+int rcb_pfb_process_multi(rcb_t* const* hs, int nstreams, const void* const* iq, size_t nsamples,
+                          void* const* out_fm, size_t out_stride);
 
 /* ---- K2: bank of arbitrary-offset DDC channels (+ optional FM demod) ----------------------------
  * One channel = filter.freq_xlating_fir_filter_ccc(decim, taps, center_freq, samp_rate)
@@ -197,6 +206,11 @@ int rcb_fft_config(rcb_t* h, int length, const float* window, int avg_frames);
 int rcb_fft_reset(rcb_t* h);
 int rcb_fft_process(rcb_t* h, const void* iq, size_t nsamples, int in_mem, void* out_sums,
                     size_t cap_vectors, int out_mem, size_t* nvec);
+/* Which kernels run rcb_fft_process: 0 (default) = column pass / row pass / fold per L2-resident sub-batch on two
+ * streams; 1 = ONE persistent launch per call (task queue over column and row tiles of all frames, scratch ring kept in
+ * L2, block sums accumulated in frame order by the row tiles).  Same results bit for bit; the persistent kernel needs
+ * frames of many tiles (2^18, 2^20 points) to be competitive. */
+int rcb_fft_set_pipeline(rcb_t* h, int persistent);
 
 #ifdef __cplusplus
 }

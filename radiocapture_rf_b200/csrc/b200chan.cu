@@ -106,6 +106,14 @@ struct rcb_ctx {
         int hist_valid = 0;
         float2* d_conv = nullptr;      // complex64 staging for kernels without the fused conversion
         size_t conv_cap = 0;
+        // multi-stream launches (rcb_pfb_process_multi): parameter blocks of all streams, owned by the leader handle
+        unsigned char* d_multi = nullptr;
+        unsigned char* h_multi = nullptr;   // pinned, kMultiSlots slots
+        size_t multi_cap = 0;               // streams
+        unsigned long long multi_no = 0;
+        cudaEvent_t ev_mslot[4] = {nullptr, nullptr, nullptr, nullptr};
+        cudaEvent_t ev_multi = nullptr;     // per handle: "my stream has reached this point"
+        int* d_mcounters = nullptr;
         float* d_taps_gen = nullptr;   // generic-kernel tables, also built for the fast shapes (fallback for
         float2* d_tw_gen = nullptr;    // output buffers the sector-store / TMA kernels cannot address)
         bool use_cl = false;      // FM only, N in {256, 1024}, <= 16 taps per arm: cluster / register-window kernel
@@ -534,6 +542,22 @@ void pfb_free(rcb_t* h) {
     cudaFree(s.d_tw_gen);
     s.d_taps_gen = nullptr;
     s.d_tw_gen = nullptr;
+    cudaFree(s.d_multi);
+    if (s.h_multi) cudaFreeHost(s.h_multi);
+    cudaFree(s.d_mcounters);
+    s.d_multi = nullptr;
+    s.h_multi = nullptr;
+    s.d_mcounters = nullptr;
+    s.multi_cap = 0;
+    for (int i = 0; i < 4; ++i)
+        if (s.ev_mslot[i]) {
+            cudaEventDestroy(s.ev_mslot[i]);
+            s.ev_mslot[i] = nullptr;
+        }
+    if (s.ev_multi) {
+        cudaEventDestroy(s.ev_multi);
+        s.ev_multi = nullptr;
+    }
     cudaFree(s.d_hist_raw[0]);
     cudaFree(s.d_hist_raw[1]);
     s.d_hist_raw[0] = s.d_hist_raw[1] = nullptr;
@@ -1283,6 +1307,156 @@ extern "C" int rcb_pfb_process(rcb_t* h, const void* iq, size_t nsamples, int in
     return RCB_OK;
 }
 
+// ---- several independent streams of one shape in ONE launch --------------------------------------------------------
+namespace {
+template <int R, int PT>
+int pfb_launch_multi_t(rcb_t* lead, const PfbParams* d_ps, int nstreams, int frames) {
+    using G = PfbTmaGeom<R, 8, PFB_OUT_FM>;
+    auto kern = pfb_fm_tma_multi_kernel<R, 8, true, PT, PFB_OUT_FM>;
+    rcb_t* h = lead;
+    static bool attr_dev[64] = {};
+    static int per_sm[64] = {};
+    const int di = h->device & 63;
+    if (!attr_dev[di]) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes));
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, G::THREADS, G::smem_bytes));
+        per_sm[di] = std::max(nb, 1);
+        attr_dev[di] = true;
+    }
+    const int NI = (frames + G::FPI - 1) / G::FPI;
+    const int per_stream = std::max(1, std::min(NI, per_sm[di] * h->sm_count / nstreams));
+    dim3 grid((unsigned)per_stream, (unsigned)nstreams);
+    kern<<<grid, G::THREADS, G::smem_bytes, h->stream>>>(d_ps);
+    CKL(h);
+    return RCB_OK;
+}
+template <int R>
+int pfb_launch_multi_r(rcb_t* lead, const PfbParams* d_ps, int nstreams, int frames) {
+    switch (lead->pfb.PT) {
+        case 1: return pfb_launch_multi_t<R, 1>(lead, d_ps, nstreams, frames);
+        case 2: return pfb_launch_multi_t<R, 2>(lead, d_ps, nstreams, frames);
+        case 4: return pfb_launch_multi_t<R, 4>(lead, d_ps, nstreams, frames);
+        case 8: return pfb_launch_multi_t<R, 8>(lead, d_ps, nstreams, frames);
+        case 16: return pfb_launch_multi_t<R, 16>(lead, d_ps, nstreams, frames);
+    }
+    return RCB_EUNSUPPORTED;
+}
+constexpr int kMultiSlots = 4;
+}  // namespace
+
+extern "C" int rcb_pfb_process_multi(rcb_t* const* hs, int nstreams, const void* const* iq, size_t nsamples,
+                                     void* const* out_fm, size_t out_stride) {
+    if (!hs || nstreams < 1 || !iq || !out_fm) return RCB_EINVAL;
+    rcb_t* h = hs[0];
+    if (!h) return RCB_EINVAL;
+    auto& s0 = h->pfb;
+    if (!s0.configured) return RCB_ESTATE;
+    if (nsamples % (size_t)s0.N) return RCB_EINVAL;
+    const size_t frames = nsamples / (size_t)s0.N;
+    if (frames > 0x7fffff00u) return RCB_ERANGE;
+    bool batched = (s0.R == 16 && s0.mode == RCB_OUT_FM && s0.use_tma && s0.PT <= 16 && s0.in_fmt == 0 && nstreams <= 1024);
+    for (int i = 0; i < nstreams; ++i) {
+        rcb_t* g = hs[i];
+        if (!g || !iq[i] || !out_fm[i]) return RCB_EINVAL;
+        auto& s = g->pfb;
+        if (!s.configured) return RCB_ESTATE;
+        if (g->device != h->device || s.N != s0.N || s.L != s0.L || s.mode != s0.mode || s.oblock_log2 != s0.oblock_log2 ||
+            s.in_fmt != s0.in_fmt)
+            return RCB_EINVAL;   // one shape, one device per batch
+        if (out_stride < frames && !s.oblock_log2) return RCB_EINVAL;
+        const bool aligned32 = (s.oblock_log2 > 0 || (out_stride % 8) == 0) && (((uintptr_t)out_fm[i] & 31) == 0) &&
+                               (((uintptr_t)iq[i] & 15) == 0);
+        batched = batched && aligned32;
+    }
+    CK(cudaSetDevice(h->device));
+    if (frames == 0) return RCB_OK;
+    if (!batched) {  // any other shape: the streams one after the other (same results, nstreams launches)
+        for (int i = 0; i < nstreams; ++i) {
+            int rc = rcb_pfb_process(hs[i], iq[i], nsamples, RCB_MEM_DEVICE, nullptr, out_fm[i], out_stride, RCB_MEM_DEVICE,
+                                     nullptr);
+            if (rc) return rc;
+        }
+        return RCB_OK;
+    }
+    // parameter blocks of all streams -> one pinned slot -> device
+    const size_t per = sizeof(PfbParams) + sizeof(PfbHistJob);
+    if (s0.multi_cap < (size_t)nstreams) {
+        CK(cudaStreamSynchronize(h->stream));
+        cudaFree(s0.d_multi);
+        if (s0.h_multi) cudaFreeHost(s0.h_multi);
+        cudaFree(s0.d_mcounters);
+        s0.d_multi = nullptr;
+        s0.h_multi = nullptr;
+        s0.d_mcounters = nullptr;
+        s0.multi_cap = 0;
+        const size_t cap = (size_t)nstreams;
+        CK(cudaMalloc(&s0.d_multi, kMultiSlots * cap * per));
+        CK(cudaHostAlloc(&s0.h_multi, kMultiSlots * cap * per, cudaHostAllocDefault));
+        CK(cudaMalloc(&s0.d_mcounters, cap * sizeof(int)));
+        s0.multi_cap = cap;
+    }
+    const int slot = (int)(s0.multi_no++ % kMultiSlots);
+    if (!s0.ev_mslot[slot]) CK(cudaEventCreateWithFlags(&s0.ev_mslot[slot], cudaEventDisableTiming));
+    else CK(cudaEventSynchronize(s0.ev_mslot[slot]));
+    unsigned char* hb = s0.h_multi + (size_t)slot * s0.multi_cap * per;
+    unsigned char* db = s0.d_multi + (size_t)slot * s0.multi_cap * per;
+    PfbParams* hp = reinterpret_cast<PfbParams*>(hb);
+    PfbHistJob* hj = reinterpret_cast<PfbHistJob*>(hb + (size_t)nstreams * sizeof(PfbParams));
+    const PfbParams* dp = reinterpret_cast<const PfbParams*>(db);
+    const PfbHistJob* dj = reinterpret_cast<const PfbHistJob*>(db + (size_t)nstreams * sizeof(PfbParams));
+    for (int i = 0; i < nstreams; ++i) {
+        rcb_t* g = hs[i];
+        auto& s = g->pfb;
+        // whatever is queued on the stream of handle i (its previous block, the producer of its input) comes first
+        if (i > 0) {
+            if (!s.ev_multi) CK(cudaEventCreateWithFlags(&s.ev_multi, cudaEventDisableTiming));
+            CK(cudaEventRecord(s.ev_multi, g->stream));
+            CK(cudaStreamWaitEvent(h->stream, s.ev_multi, 0));
+        }
+        PfbParams p{};
+        p.x = (const float2*)iq[i];
+        p.hist = s.d_hist[s.hist_cur];
+        p.taps = s.d_taps;
+        p.twiddle = s.d_tw_tma;
+        p.taps_kc = s.d_taps_kc;
+        p.zeros = s.d_zeros;
+        p.work_counter = s0.d_mcounters + i;
+        p.out_fm = (float*)out_fm[i];
+        p.out_iq = nullptr;
+        p.ostride = (long long)out_stride;
+        p.oblock_log2 = s.oblock_log2;
+        p.T = (int)frames;
+        p.P = s.P;
+        p.N = s.N;
+        p.gain = s.gain;
+        hp[i] = p;
+        hj[i].old_hist = s.d_hist[s.hist_cur];
+        hj[i].x = (const float2*)iq[i];
+        hj[i].new_hist = s.d_hist[s.hist_cur ^ 1];
+    }
+    CK(cudaMemcpyAsync(db, hb, (size_t)nstreams * per, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(s0.ev_mslot[slot], h->stream));
+    CK(cudaMemsetAsync(s0.d_mcounters, 0, (size_t)nstreams * sizeof(int), h->stream));
+    int rc = pfb_launch_multi_r<16>(h, dp, nstreams, (int)frames);
+    if (rc) return rc;
+    const long long cap = (long long)s0.P * s0.N;
+    dim3 hg((unsigned)((cap + 255) / 256), (unsigned)nstreams);
+    pfb_hist_multi_kernel<<<hg, 256, 0, h->stream>>>(dj, (long long)nsamples, cap);
+    CKL(h);
+    // the other handles' streams continue after the batch
+    if (!s0.ev_multi) CK(cudaEventCreateWithFlags(&s0.ev_multi, cudaEventDisableTiming));
+    CK(cudaEventRecord(s0.ev_multi, h->stream));
+    for (int i = 0; i < nstreams; ++i) {
+        rcb_t* g = hs[i];
+        if (i > 0) CK(cudaStreamWaitEvent(g->stream, s0.ev_multi, 0));
+        g->pfb.hist_cur ^= 1;
+        g->stats.samples_in += frames * (uint64_t)s0.N;
+        g->stats.channel_samples += frames * (uint64_t)s0.N;
+    }
+    return RCB_OK;
+}
+
 // =================================================================================================
 // K2  DDC bank
 // =================================================================================================
@@ -1859,6 +2033,14 @@ extern "C" int rcb_fft_reset(rcb_t* h) {
     int rc = fft_reset(h->fft, h->stream);
     if (rc == RCB_ECUDA) return fail_cuda(h, cudaGetLastError(), "fft_reset");
     return rc;
+}
+extern "C" int rcb_fft_set_pipeline(rcb_t* h, int persistent) {
+    if (!h) return RCB_EINVAL;
+    if (!h->fft.configured) return RCB_ESTATE;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    h->fft.use_scan = (persistent != 0);
+    return RCB_OK;
 }
 extern "C" int rcb_fft_process(rcb_t* h, const void* iq, size_t nsamples, int in_mem, void* out_sums, size_t cap_vectors,
                                int out_mem, size_t* nvec) {

@@ -366,7 +366,7 @@ struct FftState {
     float2* d_in = nullptr;   // staging for host input
     size_t in_cap = 0;
     // persistent scan kernel (fft_scan.cuh)
-    bool use_scan = true;
+    bool use_scan = false;
     float2* d_ring = nullptr;     // scratch ring, `ring` frames
     int ring = 0, la = 0, scan_grid = 0;
     unsigned* d_ctl = nullptr;    // [1 task counter | ring cols_done | ring rows_done | row tiles tile_seq]
@@ -448,16 +448,18 @@ inline int fft_config(FftState& s, int L, const float* window, int avg, cudaStre
     s.L1 = r1 * r1;
     s.L2 = r2 * r2;
     s.avg = avg;
-    // the persistent scan kernel (fft_scan.cuh) pays off where a frame is many tiles (its per-tile dependency counters
-    // and in-order accumulation serialise short frames): 2^18 / 2^20 points; the three-kernel pipeline runs the rest
-    s.use_scan = (L >= (1 << 18));
+    // default: the three-kernel pipeline.  The persistent scan kernel (fft_scan.cuh, rcb_fft_set_pipeline) is parity-green
+    // but measured slower (2^20 points: 91 vs 116 Gsps; its per-task barriers and in-order accumulation expose the
+    // latencies the hardware CTA scheduler hides, profiles/r02_fft_scan_v2_summary.txt; short frames serialise on
+    // the per-tile counters), so it is opt-in
+    s.use_scan = false;
     // sub-batch: keep scratch (8 B) + vals (4 B) per sample under ~48 MB so they stay in L2
     size_t budget_mb = 48;
 #ifdef RCB_EXPERIMENTS  // tuning builds only (radiocapture_rf_b200.build.build_experiments): never in the shipped library
     if (const char* e = getenv("RCB_FFT_VARIANT")) {
         s.cols_tma = (atoi(e) != 1);
         s.rows_k1 = (atoi(e) == 3);
-        s.use_scan = (atoi(e) == 4) || (atoi(e) == 0 && s.use_scan);   // 4: scan kernel for every length; 1-3: never
+        s.use_scan = (atoi(e) == 4);   // 4: persistent scan kernel
     }
     if (const char* e = getenv("RCB_FFT_SCRATCH_MB")) budget_mb = (size_t)std::max(1, atoi(e));
 #endif

@@ -163,7 +163,7 @@ __device__ __forceinline__ void pfb_demod_from_y(const PfbParams& p, const float
 //             lane + 32 q, so a store instruction covers 1 KB of contiguous memory (8 full lines instead of 32
 //             scattered sectors: a quarter of the LSU wavefronts of the store path).
 template <int R, int W = 8, bool PK = false, int PT = 1, int MODE = PFB_OUT_FM, bool OB8 = false>
-__global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pfb_fm_tma_kernel(const PfbParams p) {
+__device__ __forceinline__ void pfb_fm_tma_body(const PfbParams& p) {
     static_assert(!OB8 || (R == 32 && W == 8 && MODE == PFB_OUT_FM), "OB8 is an FM-only 1024-channel layout variant");
     using G = PfbTmaGeom<R, W, MODE>;
     static_assert(PK || MODE == PFB_OUT_FM, "IQ outputs are implemented on the packed path only");
@@ -530,6 +530,35 @@ __global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pf
             it = cur0 - 1 - WARM;  // ++it -> warm-up iteration of the new range
         }
     }
+}
+
+template <int R, int W = 8, bool PK = false, int PT = 1, int MODE = PFB_OUT_FM, bool OB8 = false>
+__global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS)) pfb_fm_tma_kernel(const PfbParams p) {
+    pfb_fm_tma_body<R, W, PK, PT, MODE, OB8>(p);
+}
+
+// Several independent streams of the same shape in ONE launch (one stream per SDR source,
+// rc_frontend/receiver.py:67-70; BASELINE config 5 = 8 x 256-channel streams per GPU): blockIdx.y = stream, each with
+// its own parameter block (input, history, outputs, work counter) and gridDim.x persistent CTAs.
+template <int R, int W = 8, bool PK = false, int PT = 1, int MODE = PFB_OUT_FM>
+__global__ void __launch_bounds__(32 * W, (PfbTmaGeom<R, W, MODE>::MIN_CTAS))
+    pfb_fm_tma_multi_kernel(const PfbParams* __restrict__ ps) {
+    const PfbParams p = ps[blockIdx.y];
+    pfb_fm_tma_body<R, W, PK, PT, MODE, false>(p);
+}
+
+// history update of every stream of a multi-stream launch: new_hist = last cap samples of (old_hist ++ x)
+struct PfbHistJob {
+    const float2* old_hist;
+    const float2* x;
+    float2* new_hist;
+};
+__global__ void pfb_hist_multi_kernel(const PfbHistJob* __restrict__ jobs, long long n, long long cap) {
+    const PfbHistJob j = jobs[blockIdx.y];
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap) return;
+    const long long src = i + n - cap;
+    j.new_hist[i] = (src >= 0) ? j.x[src] : ((src >= -cap) ? j.old_hist[cap + src] : make_float2(0.f, 0.f));
 }
 
 }  // namespace rcb

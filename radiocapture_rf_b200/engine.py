@@ -169,6 +169,21 @@ class Engine(object):
         return out[0] if x.ndim == 1 else out
 
 
+def pfb_process_multi(channelizers, d_ins, nsamples, d_fms, out_stride):
+    """One call (one kernel launch where the shape allows) over several independent streams of one shape on one GPU:
+    channelizers[i] (its own Engine handle = its own streaming state), device input d_ins[i], device FM output d_fms[i]."""
+    n = len(channelizers)
+    assert n == len(d_ins) == len(d_fms) and n >= 1
+
+    def _p(x):
+        return x.ptr if isinstance(x, DeviceBuffer) else int(x)
+    hs = (C.c_void_p * n)(*[c.e.h for c in channelizers])
+    ins = (C.c_void_p * n)(*[_p(x) for x in d_ins])
+    outs = (C.c_void_p * n)(*[_p(x) for x in d_fms])
+    lead = channelizers[0].e
+    check(lead.lib.rcb_pfb_process_multi(hs, n, ins, int(nsamples), outs, int(out_stride)), "rcb_pfb_process_multi", lead.h)
+
+
 def copy_ceiling(engine, h2d_bytes, d2h_bytes, iters=4):
     """Bare pinned host <-> device copy rate of the engine's GPU (both directions concurrently, no kernels):
     returns (h2d GB/s, d2h GB/s, wall seconds)."""
@@ -464,6 +479,10 @@ class FftScanner(object):
 
     def reset(self):
         check(self.e.lib.rcb_fft_reset(self.e.h), "rcb_fft_reset", self.e.h)
+
+    def set_pipeline(self, persistent):
+        """False (default): three kernels per L2-resident sub-batch; True: one persistent fused launch per call."""
+        check(self.e.lib.rcb_fft_set_pipeline(self.e.h, int(bool(persistent))), "rcb_fft_set_pipeline", self.e.h)
 
     def process(self, iq):
         """Returns float32 [nvec][L]: one vector per completed block of avg frames."""

@@ -23,6 +23,39 @@ def test_fft_logpow_parity(engine, length, avg, nblocks):
     _check_logsum(out, ref, avg)
 
 
+@pytest.mark.parametrize("length,avg,nblocks,frames_extra", [(4096, 10, 3, 4), (16384, 7, 2, 0), (262144, 3, 2, 1),
+                                                              (1048576, 2, 2, 1)])
+def test_fft_persistent_pipeline_matches_oracle_and_default(engine, length, avg, nblocks, frames_extra):
+    """rcb_fft_set_pipeline(1): ONE persistent launch per call (task queue over column / row tiles, L2-resident scratch
+    ring, block sums accumulated in frame order).  Same parity bar as the three-kernel pipeline, the same samples as it
+    bit for bit, and split invariance (the running block sum is carried across calls)."""
+    n = length * (avg * nblocks + frames_extra)
+    x, _ = synth.scan_stream(n, 2.4e6, length, seed=14, ncarriers=5)
+    w = fd.blackmanharris(length)
+    sc = FftScanner(engine, length, w, avg)
+    base = sc.process(x)
+    sc.reset()
+    sc.set_pipeline(True)
+    out = sc.process(x)
+    assert out.shape == (nblocks, length)
+    _check_logsum(out, gb.logpower_block_sums(x[:length * avg * nblocks], length, w, avg), avg)
+    np.testing.assert_allclose(out, base, atol=2e-5 * avg)
+    sc.reset()
+    parts, pos = [], 0
+    for nfr in [1, avg - 1, 2, avg * nblocks + frames_extra - avg - 2]:
+        parts.append(sc.process(x[pos * length:(pos + nfr) * length]))
+        pos += nfr
+    split = np.concatenate([p for p in parts if len(p)], axis=0)
+    assert np.array_equal(split, out)       # frame-ordered accumulation: any split gives the same bits
+    # device-resident input and output
+    sc.reset()
+    d_in = engine.to_device(x)
+    d_out = engine.dev_alloc(nblocks * length * 4)
+    assert sc.process_device(d_in, n, d_out, nblocks) == nblocks
+    engine.sync()
+    assert np.array_equal(engine.to_host(d_out, (nblocks, length), np.float32), out)
+
+
 def _check_logsum(out, ref, avg):
     """float32 FFT rounding is relative to the STRONGEST bins of a frame (~5e-7 of their amplitude), so
     bins 100+ dB down (Blackman-Harris leaves >110 dB of dynamic range on synthetic data) carry large

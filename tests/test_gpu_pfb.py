@@ -164,6 +164,46 @@ def test_pfb_more_than_16_taps_per_arm(engine, n, tpa, frames, mode):
     _check(engine, n, taps, frames, seed=3000 + tpa, mode=mode, active_every=8 if n == 1024 else 2)
 
 
+@pytest.mark.parametrize("n,tpa,streams,block", [(256, 16, 8, 0), (256, 4, 3, 64), (1024, 2, 2, 0)])
+def test_pfb_multi_stream_launch_equals_per_stream_calls(built_lib, n, tpa, streams, block):
+    """BASELINE config 5 shape: several independent 256-channel streams on one GPU through rcb_pfb_process_multi (one
+    launch, blockIdx.y = stream) give bit for bit what per-stream calls give, block after block (streaming state per
+    handle); other shapes take the stream-after-stream path of the same call."""
+    from radiocapture_rf_b200.engine import Engine, pfb_process_multi
+    taps = fd.pfb_prototype(n, tpa)
+    frames = [200, 57]
+    engines = [Engine(0) for _ in range(streams)]
+    try:
+        xs = [synth.pfb_stream(n * sum(frames), 1.0e6 * n / 4.0, n, 50 + i)[0] for i in range(streams)]
+        refs = []
+        for i, e in enumerate(engines):
+            ch = PfbChannelizer(e, n, taps, OUT_FM, 5.0)
+            refs.append(ch.process(xs[i])[1])
+        chs = [PfbChannelizer(e, n, taps, OUT_FM, 5.0) for e in engines]     # reconfigure: fresh streaming state
+        if block:
+            for c in chs:
+                c.set_out_block(block)
+        pos = 0
+        got = [[] for _ in range(streams)]
+        for f in frames:
+            d_ins = [e.to_device(xs[i][pos * n:(pos + f) * n]) for i, e in enumerate(engines)]
+            nb = -(-f // block) if block else 0
+            d_fms = [e.dev_alloc((nb * n * block if block else n * f) * 4) for e in engines]
+            pfb_process_multi(chs, d_ins, n * f, d_fms, f)
+            for i, e in enumerate(engines):
+                e.sync()
+                if block:
+                    got[i].append(PfbChannelizer.unblock(e.to_host(d_fms[i], (nb * n * block,), np.float32), n, f, block))
+                else:
+                    got[i].append(e.to_host(d_fms[i], (n, f), np.float32))
+            pos += f
+        for i in range(streams):
+            assert np.array_equal(np.concatenate(got[i], axis=1), refs[i]), i
+    finally:
+        for e in engines:
+            e.close()
+
+
 def test_pfb_cfg3_literal_256_taps_1024_channels(engine):
     """BASELINE config 3, literal reading: 256-tap prototype, 1024 channels -> 1 tap/arm, 768 zero arms."""
     taps = fd.pfb_prototype(4, 64)  # any 256-tap low-pass

@@ -256,3 +256,130 @@ def test_golden_vectors():
     idx, freqs = gb.peak_detect(g["scan_vec"], 2.4e6, 855.05e6)
     assert idx.tolist() == man["scan_peaks_idx"]
     assert freqs.tolist() == man["scan_peaks_hz"]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# More of GNU Radio's own QA restated against the oracle (the upstream tests compute their expectations with small Python
+# reference loops rather than golden numbers; the same loops are written out here and must agree with the oracle).
+# ---------------------------------------------------------------------------------------------------------------------
+def _qa_fir_filter(x, taps, decim):
+    """gr-filter/python/filter/qa_freq_xlating_fir_filter.py `fir_filter`: zero history, newest tap first."""
+    y = []
+    x2 = (len(taps) - 1) * [0, ] + list(x)
+    for i in range(0, len(x), decim):
+        yi = 0
+        for j in range(len(taps)):
+            yi += taps[len(taps) - 1 - j] * x2[i + j]
+        y.append(yi)
+    return np.array(y)
+
+
+def _qa_sig_source_c(samp_rate, freq, amp, n):
+    t = np.arange(n) / float(samp_rate)
+    return amp * np.exp(2j * np.pi * freq * t)
+
+
+def _qa_mix(lo, data):
+    return np.asarray(lo) * np.asarray(data)
+
+
+@pytest.mark.parametrize("decim", [1, 4])
+def test_freq_xlating_matches_gnuradio_qa_construction(decim):
+    """qa_freq_xlating_fir_filter.py test_fir_filter_ccf_00x / ccc_00x: the block equals "mix down with a rotator at
+    -f0, then FIR-decimate" computed by the QA file's Python loops (fs 1.0, f0 0.2 / -0.2 there, real low-pass taps
+    (ccf) and the same taps made complex-bandpass (ccc))."""
+    fs, f0 = 1.0, 0.2
+    bw = 0.1
+    taps = fd.low_pass(1, fs, bw, bw / 4.0).astype(np.float64)
+    src = _qa_sig_source_c(fs, -0.2, 1, 600) + _qa_sig_source_c(fs, 0.21, 0.5, 600)
+    despun = _qa_mix(_qa_sig_source_c(fs, -f0, 1, len(src)), src)       # rotator(-2 pi f0 / fs), phase 0 at n = 0
+    expected = _qa_fir_filter(despun, list(taps), decim)
+    got = gb.freq_xlating_fir(src.astype(np.complex64), taps, decim, f0, fs)
+    assert gb.rel_l2(got, expected[:len(got)]) < 2e-7                     # input rounded to complex64 only
+    # ccc variant: complex band-pass taps t[k] e^{j w k} centred on f0, then the same construction
+    ctaps = taps * np.exp(2j * np.pi * f0 * np.arange(len(taps)))
+    expected_c = _qa_fir_filter(despun, list(ctaps * np.exp(-2j * np.pi * f0 * np.arange(len(taps)))), decim)
+    assert gb.rel_l2(got, expected_c[:len(got)]) < 2e-7
+
+
+def test_rotator_matches_gnuradio_qa_definition():
+    """gr-blocks/python/blocks/qa_rotator.py: ones through rotator_cc(phase_inc) give e^{j n phase_inc}, the first
+    output unrotated - the phase convention the xlating filter's derotation inherits (oracle: exact phase)."""
+    n, f, fs = 1000, 0.0125, 1.0
+    inc = 2 * np.pi * f / fs
+    expected = np.exp(1j * inc * np.arange(n))
+    # unit taps, decimation 1, centre frequency -f: y[i] = x[i] e^{+j inc i}
+    got = gb.freq_xlating_fir(np.ones(n, np.complex64), np.array([1.0]), 1, -f, fs)
+    assert np.abs(got - expected).max() < 1e-12
+
+
+def test_moving_average_matches_gnuradio_qa_construction():
+    """gr-blocks/python/blocks/qa_moving_average.py test_01 / test_02: N samples through moving_average(length, scale)
+    = scale * running sum of the last `length` inputs (zero history)."""
+    rng = np.random.default_rng(0)
+    for length, scale in ((100, 1.0 / 100), (10000, 1e-4), (7, 3.0)):
+        x = rng.standard_normal(2500)
+        pad = np.concatenate([np.zeros(length - 1), x])
+        expected = scale * np.array([pad[i:i + length].sum() for i in range(len(x))])
+        assert np.abs(gb.moving_average(x, length, scale) - expected).max() < 1e-9
+
+
+def test_pfb_channelizer_matches_gnuradio_qa_construction():
+    """gr-filter/python/filter/qa_pfb_channelizer.py test_0000: M = 5 channels of fs = 5000, one tone per channel at
+    freqs = [-230, 121, 110, -513, 203] Hz around the channel centres, low_pass_2(1, M fs, fs/2, fs/10, 80,
+    BLACKMAN_hARRIS) prototype; every output port carries its tone, delayed by the filter: expected = e^{j 2 pi f t}
+    with t starting (tpf - 1) / 2 samples early - compared after the filter has filled."""
+    M, fs, N = 5, 5000.0, 1000
+    ifs = M * fs
+    taps = fd.low_pass_2(1, ifs, fs / 2, fs / 10, 80.0, fd.WIN_BLACKMAN_HARRIS).astype(np.float64)
+    freqs = [-230.0, 121.0, 110.0, -513.0, 203.0]
+    t = np.arange(N * M) / ifs
+    x = np.zeros(N * M, complex)
+    for i, f in enumerate(freqs):
+        # channel i sits at i * fs (bins above M/2 are the negative frequencies, rc_frontend/receiver.py:373-375)
+        centre = i * fs if i <= M // 2 else (i - M) * fs
+        x += np.exp(2j * np.pi * (centre + f) * t)
+    y = gb.pfb_channelizer(x.astype(np.complex64), taps, M)
+    tpf = int(np.ceil(len(taps) / float(M)))
+    L = y.shape[1]
+    for i, f in enumerate(freqs):
+        # group delay of the prototype = (len(taps) - 1) / 2 input samples; the commutator advances the input by M - 1
+        tt = (np.arange(L) * M + (M - 1) - (len(taps) - 1) / 2.0) / ifs
+        centre = i * fs if i <= M // 2 else (i - M) * fs
+        # output n of bin i = the tone at the (delayed) time of frame n with the bin centre mixed out at frame rate:
+        # e^{j 2 pi (centre + f) tt} e^{-j 2 pi centre n M / ifs}
+        expected = np.exp(2j * np.pi * f * tt) * np.exp(2j * np.pi * centre * ((M - 1) - (len(taps) - 1) / 2.0) / ifs)
+        got = y[i]
+        err = np.abs(got[2 * tpf:] - expected[2 * tpf:]).max()
+        assert err < 2e-3, (i, err)       # QA: assertComplexTuplesAlmostEqual(..., 3); stop-band leakage of the others
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# post-demod stages (SURVEY 8(f) row 3): the restatements against independent library implementations
+# ---------------------------------------------------------------------------------------------------------------------
+def test_post_demod_restatements_match_scipy():
+    from scipy.signal import lfilter, upfirdn
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal(3000)
+    hp = fd.high_pass(1, 25000, 300, 30, fd.WIN_HAMMING, 6.76)
+    assert len(hp) == 2007 and abs(hp.astype(np.float64).sum()) < 1e-3          # DC removed
+    assert np.abs(gb.fir_filter_fff(x, hp) - lfilter(hp.astype(np.float64), 1, x)).max() < 1e-12
+    assert np.abs(gb.fir_filter_fff(x, hp, decim=3) - lfilter(hp.astype(np.float64), 1, x)[::3]).max() < 1e-12
+    i, d, rt = fd.rational_resampler_taps(8000, 25000)
+    assert (i, d, len(rt)) == (8, 25, 821)
+    y = gb.rational_resampler_fff(x, i, d, rt)
+    assert len(y) == (len(x) * 8 + 24) // 25
+    assert np.abs(y - upfirdn(rt.astype(np.float64), x, i, d)[:len(y)]).max() < 1e-12
+    b, a = fd.fm_deemph_taps(25000.0, 75e-6)
+    assert np.abs(gb.iir_filter_ffd(x, b, a) - lfilter(b, a, x)).max() < 1e-12
+    # de-emphasis: unity gain at DC, -3 dB near 1 / (2 pi tau) = 2122 Hz
+    w = 2 * np.pi * 2122.0 / 25000.0
+    hz = (b[0] + b[1] * np.exp(-1j * w)) / (1 + a[1] * np.exp(-1j * w))
+    assert abs((b[0] + b[1]) / (1 + a[1]) - 1.0) < 1e-12 and abs(20 * np.log10(abs(hz)) + 3.0) < 0.1
+    # symbol filter (p25_control_demod.py:130-133) and the squelch state machine
+    assert np.allclose(gb.fir_filter_fff(np.ones(10), np.full(5, 0.2)), [0.2, 0.4, 0.6, 0.8, 1, 1, 1, 1, 1, 1])
+    z = np.concatenate([np.zeros(50), 0.1 * np.ones(500), np.zeros(3000)]).astype(complex)
+    out, keep = gb.pwr_squelch_cc(z, -40.0, 0.01, 0, True)
+    assert not keep[:50].any() and keep[60:550].all() and not keep[-1000:].any() and len(out) == keep.sum()
+    # Kaiser tap count of the resampler prototype: firdes.compute_ntaps with max_attenuation = beta / 0.1102 + 8.7
+    assert fd.compute_ntaps(8.0, 0.032, fd.WIN_KAISER, 7.0) == 821
