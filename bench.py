@@ -93,7 +93,7 @@ def kernel_name(wl):
             return "pfb_cl_kernel<32,%d>" % pt
         if pt == 16:
             return "pfb_fm_ws_kernel<32,16>"
-        return "pfb_fm_kernel<32>"
+        return "pfb_arm_fir_kernel+pfb_fm1_kernel"
     if n == 1024 and pt >= 8:
         return "pfb_fm_ws_kernel<32,%d,IQ>" % pt
     r = {64: 8, 256: 16, 1024: 32}[n]
@@ -477,7 +477,7 @@ class DdcCtx(object):
 
 def step_all(ctxs):
     """One step of every stream of this rank: multi-stream PFB workloads (BASELINE config 5) go through ONE
-    rcb_pfb_process_multi call (one batched kernel launch, blockIdx.y = stream)."""
+    rcb_pfb_process_multi call (one persistent kernel launch that walks the streams)."""
     if len(ctxs) > 1 and all(isinstance(c, StreamCtx) for c in ctxs):
         from radiocapture_rf_b200.engine import pfb_process_multi
         pfb_process_multi([c.ch for c in ctxs], [c.d_in for c in ctxs], ctxs[0].n, [c.d_fm for c in ctxs], ctxs[0].frames)

@@ -110,7 +110,7 @@ int rcb_pfb_process(rcb_t* h, const void* iq, size_t nsamples, int in_mem,
  * rc_frontend/receiver.py:67-70; systemd/radiocapture-channelizer@.service:11 runs one frontend per source): handle
  * hs[i] carries stream i's configuration and streaming state exactly as for rcb_pfb_process, iq[i] / out_fm[i] are its
  * device-resident input block (nsamples complex64) and FM output.  256-channel FM-only configurations with <= 16 taps
- * per arm run as ONE kernel launch (blockIdx.y = stream) plus one history update; any other shape is processed stream
+ * per arm run as ONE persistent kernel launch (the grid walks the streams) plus one history update; any other shape is processed stream
  * after stream.  All handles must live on the same device and share nchans, ntaps, out_mask and output layout.
  * Asynchronous; ordered after everything queued on every handle's stream, and every handle's later calls after it. */
 int rcb_pfb_process_multi(rcb_t* const* hs, int nstreams, const void* const* iq, size_t nsamples,

@@ -114,6 +114,12 @@ struct rcb_ctx {
         cudaEvent_t ev_mslot[4] = {nullptr, nullptr, nullptr, nullptr};
         cudaEvent_t ev_multi = nullptr;     // per handle: "my stream has reached this point"
         int* d_mcounters = nullptr;
+        // > 16 taps per arm, FM only, 1024 channels: time-blocked arm FIR (pfb_arm_fir_kernel) + the one-tap kernel
+        bool use_bigp = false;
+        float* d_taps_unit = nullptr;  // all-ones taps of the second pass
+        float2* d_u = nullptr;         // filtered frames of one chunk
+        size_t u_cap = 0;
+        float2* d_u_prev = nullptr;    // filtered frame before the block (FM carry of the second pass)
         float* d_taps_gen = nullptr;   // generic-kernel tables, also built for the fast shapes (fallback for
         float2* d_tw_gen = nullptr;    // output buffers the sector-store / TMA kernels cannot address)
         bool use_cl = false;      // FM only, N in {256, 1024}, <= 16 taps per arm: cluster / register-window kernel
@@ -430,7 +436,7 @@ int pfb_launch_fm1(rcb_t* h, const PfbParams& p0, size_t frames, float* d_fm, si
     static const fm1_fn kerns[4] = {pfb_fm1_kernel<0>, pfb_fm1_kernel<1>, pfb_fm1_kernel<2>, pfb_fm1_kernel<3>};
     static bool attr_dev[64][4] = {};
     static int per_sm[64][4] = {};
-    const int di = h->device & 63, fi = s.in_fmt & 3;
+    const int di = h->device & 63, fi = p0.in_fmt & 3;  // (the format of THIS launch's input: a converted block is complex64)
     fm1_fn kern = kerns[fi];
     if (!attr_dev[di][fi]) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes));
@@ -558,6 +564,14 @@ void pfb_free(rcb_t* h) {
         cudaEventDestroy(s.ev_multi);
         s.ev_multi = nullptr;
     }
+    cudaFree(s.d_taps_unit);
+    cudaFree(s.d_u);
+    cudaFree(s.d_u_prev);
+    s.d_taps_unit = nullptr;
+    s.d_u = nullptr;
+    s.d_u_prev = nullptr;
+    s.u_cap = 0;
+    s.use_bigp = false;
     cudaFree(s.d_hist_raw[0]);
     cudaFree(s.d_hist_raw[1]);
     s.d_hist_raw[0] = s.d_hist_raw[1] = nullptr;
@@ -650,6 +664,53 @@ int pfb_run_device(rcb_t* h, const void* d_in, size_t frames, float2* d_iq, floa
     if (cl_rc == 1 && s.use_cl && (s.PT <= 8 || s.variant == 21)) {
         cl_rc = pfb_launch_cl(h, d_x, s.d_hist[s.hist_cur], frames, d_fm, ostride);
         if (cl_rc != RCB_OK && cl_rc != 1) return cl_rc;
+    }
+    if (cl_rc == 1 && s.use_bigp) {
+        // > 16 taps per arm: u = arm FIR of the block (time-blocked, shared-memory tiles), then FFT + FM demod of u as a
+        // one-tap channelizer with unit taps; chunks of 2^26 samples bound the temporary
+        const size_t chunk = std::max<size_t>(128, ((size_t)1 << 26) / (size_t)s.N);
+        const size_t ucap = std::min(frames, chunk) * (size_t)s.N;
+        if (s.u_cap < ucap) {
+            cudaFree(s.d_u);
+            s.d_u = nullptr;
+            s.u_cap = 0;
+            CK(cudaMalloc(&s.d_u, ucap * sizeof(float2)));
+            s.u_cap = ucap;
+        }
+        const size_t smem = (size_t)(128 + s.P - 1) * 16 * sizeof(float2) + (size_t)s.P * 16 * sizeof(float);
+        static size_t fir_attr[64] = {};
+        size_t& cur = fir_attr[h->device & 63];
+        if (smem > cur) {
+            CK(cudaFuncSetAttribute(pfb_arm_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cur = smem;
+        }
+        const size_t blk = s.oblock_log2 ? ((size_t)1 << s.oblock_log2) : 0;
+        bool ok = true;
+        for (size_t t0 = 0; t0 < frames && ok; t0 += chunk) {
+            const size_t cnt = std::min(chunk, frames - t0);
+            dim3 grid((unsigned)(s.N / 16), (unsigned)((cnt + 127) / 128));
+            pfb_arm_fir_kernel<<<grid, 256, smem, h->stream>>>(d_x, s.d_hist[s.hist_cur], s.d_taps_kc, s.d_u, s.N, s.P,
+                                                             (long long)frames, (long long)t0, (long long)cnt);
+            CKL(h);
+            PfbParams q = p;
+            q.x = s.d_u;
+            q.hist = s.d_u_prev;
+            q.taps = s.d_taps_unit;
+            q.P = 1;
+            q.T = (int)cnt;
+            q.in_fmt = 0;
+            float* o = blk ? d_fm + (t0 / blk) * (size_t)s.N * blk : d_fm + t0;
+            q.out_fm = o;
+            const int rc = pfb_launch_fm1(h, q, cnt, o, ostride);
+            if (rc == 1 && t0 == 0) {
+                ok = false;   // output not addressable by a tensor map: the round-1 kernel runs the whole call
+                break;
+            }
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(s.d_u_prev, s.d_u + (cnt - 1) * (size_t)s.N, (size_t)s.N * sizeof(float2), cudaMemcpyDeviceToDevice,
+                               h->stream));
+        }
+        if (ok) cl_rc = RCB_OK;
     }
     // the round-1 fast kernels emit 32-byte sector stores (st.global.v8 / two of them per complex row piece): they need
     // 32-byte aligned output rows; anything else takes the generic path
@@ -1095,7 +1156,23 @@ extern "C" int rcb_pfb_config(rcb_t* h, int nchans, const float* taps, int ntaps
             CK(cudaMalloc(&s.d_tw4, t4.size() * sizeof(float4)));
             CK(cudaMemcpy(s.d_tw4, t4.data(), t4.size() * sizeof(float4), cudaMemcpyHostToDevice));
         }
-        if (s.use_tma) {
+        // many taps per arm (FM only, 1024 channels): arm FIR kernel + the one-tap kernel with unit taps
+        s.use_bigp = (R == 32 && P > 16 && P <= 1024 && s.mode == RCB_OUT_FM && s.variant != 20);
+        if (s.use_bigp) {
+            std::vector<float> kc((size_t)P * N, 0.f);
+            for (int k = 0; k < P; ++k)
+                for (int c = 0; c < N; ++c) kc[(size_t)k * N + c] = hp[(size_t)(N - 1 - c) + (size_t)k * N];
+            cudaFree(s.d_taps_kc);
+            s.d_taps_kc = nullptr;
+            CK(cudaMalloc(&s.d_taps_kc, kc.size() * sizeof(float)));
+            CK(cudaMemcpy(s.d_taps_kc, kc.data(), kc.size() * sizeof(float), cudaMemcpyHostToDevice));
+            std::vector<float> ones((size_t)N, 1.f);
+            CK(cudaMalloc(&s.d_taps_unit, ones.size() * sizeof(float)));
+            CK(cudaMemcpy(s.d_taps_unit, ones.data(), ones.size() * sizeof(float), cudaMemcpyHostToDevice));
+            CK(cudaMalloc(&s.d_u_prev, (size_t)N * sizeof(float2)));
+            CK(cudaMemset(s.d_u_prev, 0, (size_t)N * sizeof(float2)));
+        }
+        if (s.use_tma || s.use_bigp) {
             std::vector<float2> tt((size_t)N);
             for (int ll = 0; ll < R; ++ll) {
                 const int sw = (R == 8) ? ((ll >> 1) & 3) : (ll & (R / 2 - 1));
@@ -1176,6 +1253,7 @@ extern "C" int rcb_pfb_reset(rcb_t* h) {
     CK(cudaSetDevice(h->device));
     for (int b = 0; b < 2; ++b) CK(cudaMemsetAsync(s.d_hist[b], 0, (size_t)s.P * s.N * sizeof(float2), h->stream));
     s.hist_valid = 0;
+    if (s.d_u_prev) CK(cudaMemsetAsync(s.d_u_prev, 0, (size_t)s.N * sizeof(float2), h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return RCB_OK;
 }
@@ -1325,9 +1403,8 @@ int pfb_launch_multi_t(rcb_t* lead, const PfbParams* d_ps, int nstreams, int fra
         attr_dev[di] = true;
     }
     const int NI = (frames + G::FPI - 1) / G::FPI;
-    const int per_stream = std::max(1, std::min(NI, per_sm[di] * h->sm_count / nstreams));
-    dim3 grid((unsigned)per_stream, (unsigned)nstreams);
-    kern<<<grid, G::THREADS, G::smem_bytes, h->stream>>>(d_ps);
+    const int grid = std::max(1, std::min(NI, per_sm[di] * h->sm_count));
+    kern<<<grid, G::THREADS, G::smem_bytes, h->stream>>>(d_ps, nstreams);
     CKL(h);
     return RCB_OK;
 }

@@ -29,6 +29,7 @@
 #pragma once
 #include "common.cuh"
 #include "fft_inreg.cuh"
+#include "fft_packed.cuh"
 
 namespace rcb {
 
@@ -403,6 +404,73 @@ __global__ void pfb_generic_kernel(const PfbParams p, float2* __restrict__ y_out
             }
             y_out[(long long)m * ystride + col] = acc;
         }
+    }
+}
+
+}  // namespace rcb
+
+namespace rcb {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Arm FIR for MANY taps per arm (P > 16): u[t][c] = sum_k h_c[k] x[t - k][c], the polyphase filter alone.  The FFT + FM
+// demod of u then run as a one-tap channelizer with unit taps (pfb_fm1_kernel / pfb_fm_tma_kernel), so the third reading of
+// BASELINE's "256-tap / 1024-channel" (256 taps PER ARM, compute bound: 512 fp32 lane-operations per sample) runs at
+// FP32-pipe speed instead of re-reading 256 rows per frame through L2 as pfb_fm_kernel does.
+// CTA = 16 columns x 128 frames: the (128 + P - 1) x 16 input tile and the P x 16 taps are staged in shared memory once
+// (L2 read amplification (127 + P) / 128), a thread owns one column for 8 consecutive frames and slides an 8-sample
+// register window over the taps (unrolled by 8 so the ring is statically indexed): per tap one LDS.64 (new sample), one
+// LDS.32 (tap, broadcast across the half-warps) and 8 packed FFMA2.
+// grid (N / 16, ceil(count / 128)), 256 threads, dynamic smem ((128 + P - 1) * 16 * 8 + P * 16 * 4) bytes.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pfb_arm_fir_kernel(const float2* __restrict__ x, const float2* __restrict__ hist,
+                                                          const float* __restrict__ taps_kc, float2* __restrict__ u,
+                                                          int N, int P, long long T, long long t_begin, long long count) {
+    constexpr int CB = 16, TB = 128, OPT = 8;
+    extern __shared__ __align__(16) unsigned char fir_smem[];
+    const int rows = TB + P - 1;
+    float2* xt = reinterpret_cast<float2*>(fir_smem);              // [rows][CB]: row i <-> frame t0 - (P - 1) + i
+    float* ht = reinterpret_cast<float*>(xt + (size_t)rows * CB);  // [P][CB]
+    const int tid = threadIdx.x, c = tid & 15, g = tid >> 4;
+    const int c0 = blockIdx.x * CB;
+    const long long t0 = t_begin + (long long)blockIdx.y * TB;
+    for (int i = tid; i < rows * CB; i += 256) {
+        const int r = i / CB, cc = i % CB;
+        const long long f = t0 - (P - 1) + r;
+        float2 v = make_float2(0.f, 0.f);
+        if (f >= 0) {
+            if (f < T) v = __ldg(x + f * N + c0 + cc);
+        } else if (f >= -(long long)P) {
+            v = __ldg(hist + (f + P) * N + c0 + cc);
+        }
+        xt[i] = v;
+    }
+    for (int i = tid; i < P * CB; i += 256) ht[i] = __ldg(taps_kc + (size_t)(i / CB) * N + c0 + (i % CB));
+    __syncthreads();
+    // outputs t0 + 8 g + j, j = 0..7; ring[p & 7] = x[p] for the 8 samples the current tap needs
+    const int rb = (P - 1) + OPT * g;      // tile row of frame t0 + 8 g
+    float2 ring[OPT], acc[OPT];
+#pragma unroll
+    for (int j = 0; j < OPT; ++j) {
+        ring[j] = xt[(rb + j) * CB + c];
+        acc[j] = make_float2(0.f, 0.f);
+    }
+    for (int k0 = 0; k0 < P; k0 += OPT) {
+#pragma unroll
+        for (int kk = 0; kk < OPT; ++kk) {
+            const int k = k0 + kk;
+            if (k < P) {
+                const float h = ht[k * CB + c];
+#pragma unroll
+                for (int j = 0; j < OPT; ++j) acc[j] = p2fmas(ring[(j - kk + 8 * OPT) % OPT], h, acc[j]);
+                // next tap needs x[t - k - 1]: it replaces the newest sample of the window (same residue mod 8)
+                if (k + 1 < P) ring[(OPT - 1 - kk) % OPT] = xt[(rb - k - 1) * CB + c];
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < OPT; ++j) {
+        const long long t = t0 + OPT * g + j;
+        if (t < t_begin + count && t < T) u[(t - t_begin) * N + c0 + c] = acc[j];
     }
 }
 

@@ -167,11 +167,11 @@ def test_pfb_more_than_16_taps_per_arm(engine, n, tpa, frames, mode):
 @pytest.mark.parametrize("n,tpa,streams,block", [(256, 16, 8, 0), (256, 4, 3, 64), (1024, 2, 2, 0)])
 def test_pfb_multi_stream_launch_equals_per_stream_calls(built_lib, n, tpa, streams, block):
     """BASELINE config 5 shape: several independent 256-channel streams on one GPU through rcb_pfb_process_multi (one
-    launch, blockIdx.y = stream) give bit for bit what per-stream calls give, block after block (streaming state per
+    persistent launch that walks the streams) give bit for bit what per-stream calls give, block after block (streaming state per
     handle); other shapes take the stream-after-stream path of the same call."""
     from radiocapture_rf_b200.engine import Engine, pfb_process_multi
     taps = fd.pfb_prototype(n, tpa)
-    frames = [200, 57]
+    frames = [200, 56]      # (multiples of 8: a plain-layout row stride the sector-store / TMA kernels can address)
     engines = [Engine(0) for _ in range(streams)]
     try:
         xs = [synth.pfb_stream(n * sum(frames), 1.0e6 * n / 4.0, n, 50 + i)[0] for i in range(streams)]
