@@ -475,10 +475,14 @@ class DdcCtx(object):
         self.e.close()
 
 
+USE_MULTI = False  # --multi: one rcb_pfb_process_multi call per step instead of one rcb_pfb_process call per stream
+                   # (measured on cfg5: 202 vs 218 Gsps - the per-stream launches on their own CUDA streams overlap better)
+
+
 def step_all(ctxs):
     """One step of every stream of this rank: multi-stream PFB workloads (BASELINE config 5) go through ONE
     rcb_pfb_process_multi call (one persistent kernel launch that walks the streams)."""
-    if len(ctxs) > 1 and all(isinstance(c, StreamCtx) for c in ctxs):
+    if len(ctxs) > 1 and USE_MULTI and all(isinstance(c, StreamCtx) for c in ctxs):
         from radiocapture_rf_b200.engine import pfb_process_multi
         pfb_process_multi([c.ch for c in ctxs], [c.d_in for c in ctxs], ctxs[0].n, [c.d_fm for c in ctxs], ctxs[0].frames)
     else:
@@ -741,8 +745,17 @@ def run_b200(args):
             r["e2e"] = {"value": ev, "unit": "Msps", "h2d_bytes_per_step": h2d_i, "d2h_bytes_per_step": d2h_i}
             also["ingest_" + name] = r
         # ---- BASELINE config 5: 8 independent 256-channel streams per GPU (64 over 8 GPUs) ----
+        global USE_MULTI
+        keep = USE_MULTI
+        USE_MULTI = False
         also["cfg5"] = side_run(device, "cfg5", world, dist, local, peak, half, out_block)
         also["cfg5"]["streams_total"] = WORKLOADS["cfg5"]["streams"] * world
+        also["cfg5"]["launch"] = "one rcb_pfb_process call per stream, each on its handle's own CUDA stream"
+        USE_MULTI = True
+        m = side_run(device, "cfg5", world, dist, local, peak, half, out_block)
+        also["cfg5"]["single_launch"] = {"value": m["value"], "unit": "Msps", "roofline_frac": m["roofline_frac"],
+                                         "launch": "one rcb_pfb_process_multi call per step (one persistent launch walks the 8 streams)"}
+        USE_MULTI = keep
 
     api = "rcb_pfb_process(host pinned in, host pinned out)"
     if is_fft:
@@ -831,10 +844,13 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--out-block", type=int, default=1024,
                     help="device output layout: channel-major in blocks of this many frames (0 = plain [N][T])")
+    ap.add_argument("--multi", action="store_true", help="multi-stream workloads: ONE rcb_pfb_process_multi launch per step instead of one call per stream")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ceiling", action="store_true", help="skip the bare-copy ceiling measurement of the e2e path")
     ap.add_argument("--no-also", action="store_true")
     args = ap.parse_args()
+    global USE_MULTI
+    USE_MULTI = bool(args.multi)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference(args)

@@ -92,6 +92,8 @@ struct rcb_ctx {
         int hist_cur = 0;
         float2* d_zeros = nullptr;  // one all-zero row
         int* d_counter = nullptr;   // dynamic work counter of the TMA kernel
+        int* d_counter2 = nullptr;  // pfb_fm1_kernel: ping-pong pair (each launch zeroes the other one)
+        unsigned fm1_launches = 0;
         float2* d_ys = nullptr;  // generic path scratch [N][T+1]
         size_t ys_cap = 0;
         int blocks_per_sm = 0;
@@ -447,10 +449,12 @@ int pfb_launch_fm1(rcb_t* h, const PfbParams& p0, size_t frames, float* d_fm, si
     }
     PfbParams q = p0;
     q.twiddle = s.d_tw_tma;
-    q.work_counter = s.d_counter;
+    // ping-pong work counters: this launch uses one and zeroes the other for the next launch (stream order)
+    q.work_counter = s.d_counter2 + (s.fm1_launches & 1);
+    q.next_counter = s.d_counter2 + ((s.fm1_launches + 1) & 1);
+    ++s.fm1_launches;
     const int NI = (int)((frames + G::FPI - 1) / G::FPI);
     const int grid = std::max(1, std::min(NI, per_sm[di][fi] * h->sm_count));
-    CK(cudaMemsetAsync(s.d_counter, 0, sizeof(int), h->stream));
     kern<<<grid, G::THREADS, G::smem_bytes, h->stream>>>(tm_out, q, out_rank);
     CKL(h);
     return RCB_OK;
@@ -591,6 +595,9 @@ void pfb_free(rcb_t* h) {
     s.d_zeros = nullptr;
     cudaFree(s.d_counter);
     s.d_counter = nullptr;
+    cudaFree(s.d_counter2);
+    s.d_counter2 = nullptr;
+    s.fm1_launches = 0;
     pfb_free_stages(h);
     s.d_taps = nullptr;
     s.d_tw = nullptr;
@@ -635,9 +642,13 @@ int pfb_run_device(rcb_t* h, const void* d_in, size_t frames, float2* d_iq, floa
     // FFT warps; reads raw integer I/Q directly); 2..8 taps per arm -> the cluster / register-window kernel; 16 taps per
     // arm -> the round-1 warp-specialised kernel (measured, scripts/exp/sweep_pfb.py).
     // (experiment builds: RCB_PFB_VARIANT=21 runs the cluster kernel for every tap count)
+    bool hist_in_kernel = false;
     if (s.use_cl && s.R == 32 && s.PT == 1 && s.variant != 21) {
-        cl_rc = pfb_launch_fm1(h, p, frames, d_fm, ostride);
+        PfbParams q1 = p;
+        if (!raw) q1.hist_out = s.d_hist[s.hist_cur ^ 1];   // P = 1: the kernel saves the block's last row itself
+        cl_rc = pfb_launch_fm1(h, q1, frames, d_fm, ostride);
         if (cl_rc != RCB_OK && cl_rc != 1) return cl_rc;
+        hist_in_kernel = (cl_rc == RCB_OK && !raw);
     }
     const float2* d_x = (const float2*)d_in;
     if (cl_rc == 1 && raw) {
@@ -756,7 +767,7 @@ int pfb_run_device(rcb_t* h, const void* d_in, size_t frames, float2* d_iq, floa
             (unsigned short*)s.d_hist_raw[nxt], cap * u);
         CKL(h);
         s.hist_valid = (int)std::min<long long>((long long)s.P, (long long)s.hist_valid + (long long)frames);
-    } else {
+    } else if (!hist_in_kernel) {
         hist_update_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, h->stream>>>(s.d_hist[s.hist_cur], d_x,
                                                                               (long long)nsamp, s.d_hist[nxt], cap);
         CKL(h);
@@ -1215,6 +1226,8 @@ extern "C" int rcb_pfb_config(rcb_t* h, int nchans, const float* taps, int ntaps
     }
     s.hist_cur = 0;
     CK(cudaMalloc(&s.d_counter, sizeof(int)));
+    CK(cudaMalloc(&s.d_counter2, 2 * sizeof(int)));
+    CK(cudaMemsetAsync(s.d_counter2, 0, 2 * sizeof(int), h->stream));
     CK(cudaMalloc(&s.d_zeros, (size_t)N * sizeof(float2)));
     CK(cudaMemsetAsync(s.d_zeros, 0, (size_t)N * sizeof(float2), h->stream));
     CK(cudaStreamSynchronize(h->stream));

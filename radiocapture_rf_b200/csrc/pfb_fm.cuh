@@ -43,6 +43,8 @@ struct PfbParams {
     const float* taps_kc;   // [P][N]: taps_kc[k*N + c] = h[(N-1-c) + k*N] (tap of column c; pfb_fm_tma_kernel, P > 1)
     const float2* zeros;    // N complex zeros (rows outside the stream)
     int* work_counter;      // zeroed before each launch: dynamic tail-chunk counter (pfb_fm_tma_kernel)
+    int* next_counter;      // pfb_fm1_kernel: the counter of the NEXT launch, zeroed by this one (no memset per launch)
+    float2* hist_out;       // pfb_fm1_kernel<0>: receives the last input row of this block (no history kernel per launch)
     const float2* twiddle;  // fast: [R][R+2]: tw[ll*(R+2) + m1] = W_N^{+(R-1-ll) m1};  generic: [N] W_N^{+q}
     float* out_fm;          // [N][ostride] floats (or null)
     float2* out_iq;         // [N][ostride] complex (or null)

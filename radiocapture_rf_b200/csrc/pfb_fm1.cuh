@@ -93,6 +93,18 @@ __global__ void __launch_bounds__(256, 2) pfb_fm1_kernel(const __grid_constant__
     if (tid == 0) prefetch_tmap(&tm_out);
     __syncthreads();
     const float4* tap4 = reinterpret_cast<const float4*>(taps_s);
+    // housekeeping that used to be two more stream operations per block: the last CTA zeroes the work counter of the NEXT
+    // launch (ping-pong pair) and, for complex64 input, saves the block's last row as the next block's "frame -1"
+    if (blockIdx.x == gridDim.x - 1) {
+        if (tid == 0 && p.next_counter) *p.next_counter = 0;
+        if constexpr (FMT == 0) {
+            if (p.hist_out && p.T >= 1) {
+                const float4* src = reinterpret_cast<const float4*>(p.x + (size_t)(p.T - 1) * N);
+                float4* dst = reinterpret_cast<float4*>(p.hist_out);
+                for (int i = tid; i < N / 2; i += THREADS) dst[i] = __ldg(src + i);
+            }
+        }
+    }
 
     // work distribution as in pfb_fm_tma_kernel: static run (7/8 of the even share) + dynamic tail chunks, each range
     // preceded by a warm-up iteration (recomputes the 8 frames before it: the carried angles are rebuilt, nothing
@@ -134,7 +146,11 @@ __global__ void __launch_bounds__(256, 2) pfb_fm1_kernel(const __grid_constant__
             tma_bulk_g2s(work, row_src(f0), ROWB, row_bar);
         }
     };
-    issue_rows(frame0);
+    // A warm-up iteration exists only to rebuild the angles of the frame before the range: the warp that owns the LAST
+    // frame of the iteration does its normal work, the other seven skip theirs (their issue slots go to the second
+    // CTA of the SM) and just start the copy of their first real frame.
+    const bool warm_owner = (warp == W - 1);
+    if (warm_owner) issue_rows(frame0);
 
     uint32_t row_par = 0, done_par = 0, free_par = 0;
     bool first_ever = true;
@@ -146,20 +162,27 @@ __global__ void __launch_bounds__(256, 2) pfb_fm1_kernel(const __grid_constant__
             const int c = atomicAdd(p.work_counter, 1);
             s_next = tail0 + c * kTailChunk;
         }
-        mbar_wait(row_bar, row_par);
-        row_par ^= 1u;
+        const bool works = !range_first || warm_owner;
+        if (works) {
+            mbar_wait(row_bar, row_par);
+            row_par ^= 1u;
+        }
         const bool range_last = (it + 1 == cur1);
         auto issue_next = [&]() {
             if (!range_last) {
                 frame0 += FPI;
                 issue_rows(frame0);
-            } else if (nxt0 < NI) {
+            } else if (nxt0 < NI) {  // warm-up frames of the next range
                 frame0 = (long long)(nxt0 - 1) * FPI + warp;
-                issue_rows(frame0);
+                if (warm_owner) issue_rows(frame0);
             }
         };
         float ph[R];
-        {
+        if (!works) {
+            issue_next();
+#pragma unroll
+            for (int m2 = 0; m2 < R; ++m2) ph[m2] = 0.f;
+        } else {
             float2 pr[R / 2], pi[R / 2];
             {
                 float hreg[R];
@@ -234,7 +257,7 @@ __global__ void __launch_bounds__(256, 2) pfb_fm1_kernel(const __grid_constant__
             nxt1 = min(nxt0 + kTailChunk, NI);
             if (range_last && nxt0 < NI) {
                 frame0 = (long long)(nxt0 - 1) * FPI + warp;
-                issue_rows(frame0);
+                if (warm_owner) issue_rows(frame0);
             }
         }
         // ---- demod: thread t owns channels t + 256 q ----

@@ -82,6 +82,73 @@ def test_cfg3_full_size_1024ch_256taps_fm(engine):
     _periodic_pfb_case(engine, 1024, 0.25, 28, OUT_FM, seed=3)
 
 
+def test_cfg3_full_size_blocked_layout_as_benchmarked(engine):
+    """The exact launch bench.py times by default: 2^28 samples, 1024 channels, 256-tap prototype, FM, output channel-major
+    inside time blocks of 1024 frames (rcb_pfb_set_out_block(1024), TMA tile stores through the 3-D tensor map).  Every
+    checked channel's stream must equal the plain-layout result of the first period and repeat it bit for bit."""
+    nch, per_frames, gain = 1024, 256, 5.0
+    n = 1 << 28
+    frames = n // nch
+    block = 1024
+    taps = fd.pfb_prototype(nch, 0.25)
+    base, _ = synth.pfb_stream(nch * per_frames, 1.0e6 * nch / 4.0, nch, 3, active_every=8)
+    d_in = _resident_periodic(engine, base, n)
+    ch = PfbChannelizer(engine, nch, taps, OUT_FM, gain)
+    ch.set_out_block(block)
+    d_fm = engine.dev_alloc(n * 4)
+    assert ch.process_device(d_in, n, None, d_fm, 0) == frames
+    engine.sync()
+    x2 = np.concatenate([base, base])
+    fref = gb.quadrature_demod(gb.pfb_channelizer(x2, np.asarray(taps, np.float64), nch), gain)
+    nb = frames // block
+    worst = 0.0
+    for m in [1, 9, 513, 1017, 0, 2, 1023]:
+        # channel m = the m-th 4 KB piece of every 4 MB block
+        pieces = [engine.to_host(d_fm.ptr + ((b * nch + m) * block) * 4, (block,), np.float32) for b in (0, 1, 2, nb // 2, nb - 1)]
+        if m % 8 == 1:
+            worst = max(worst, _fm_err(pieces[0][:2 * per_frames], fref[m], gain))
+        # period 256 divides the block: from block 1 on every block of the channel is identical, block 0 differs only in
+        # the start-up frames
+        assert np.array_equal(pieces[1], pieces[2]) and np.array_equal(pieces[1], pieces[3]) and np.array_equal(pieces[1], pieces[4])
+        assert np.array_equal(pieces[0][per_frames:], pieces[1][per_frames:])
+    assert worst <= 1e-5, worst
+    d_in.free()
+    d_fm.free()
+
+
+def test_cfg3_full_size_fused_sc16_ingest(engine):
+    """2^28 samples in the sc16 wire format (1 GiB instead of 2) through the fused-ingest kernel: equals the complex64
+    path on the same (converted) stream for the first period, then repeats bit for bit."""
+    from radiocapture_rf_b200 import _lib
+    nch, per_frames, gain = 1024, 256, 5.0
+    n = 1 << 28
+    frames = n // nch
+    taps = fd.pfb_prototype(nch, 0.25)
+    base, _ = synth.pfb_stream(nch * per_frames, 1.0e6 * nch / 4.0, nch, 7, active_every=8)
+    scale = 1.0 / 32768.0
+    raw = np.clip(np.round(base.view(np.float32) / (np.abs(base.view(np.float32)).max() * 1.01) * 32767.0), -32768, 32767).astype(np.int16)
+    xf = (raw.astype(np.float32) * np.float32(scale)).view(np.complex64)
+    ch = PfbChannelizer(engine, nch, taps, OUT_FM, gain)
+    _, ref = ch.process(np.concatenate([xf, xf]))
+    ch.set_input_format(_lib.FMT_S16, 0.0, scale)
+    d_in = engine.dev_alloc(n * 4)
+    check(engine.lib.rcb_memcpy(engine.h, d_in.ptr, raw.ctypes.data, raw.nbytes, COPY_H2D), "h2d", engine.h)
+    filled = raw.nbytes
+    while filled < n * 4:
+        c = min(filled, n * 4 - filled)
+        engine.copy_d2d(d_in.ptr + filled, d_in.ptr, c)
+        filled += c
+    d_fm = engine.dev_alloc(n * 4)
+    assert ch.process_device(d_in, n, None, d_fm, frames) == frames
+    engine.sync()
+    for m in [1, 9, 513, 1017, 0, 1023]:
+        row = engine.to_host(d_fm.ptr + m * frames * 4, (frames,), np.float32)
+        assert np.array_equal(row[:2 * per_frames], ref[m])
+        assert np.array_equal(row[2:frames - per_frames], row[2 + per_frames:])
+    d_in.free()
+    d_fm.free()
+
+
 def test_cfg3_full_size_16_taps_per_arm_fm(engine):
     """Same stream with a 16384-tap prototype (warp-specialised producer / consumer kernel)."""
     _periodic_pfb_case(engine, 1024, 16, 28, OUT_FM, seed=31)
