@@ -458,6 +458,8 @@ class DdcCtx(object):
         self.n = 1 << (log2n or cfg["log2n"])
         self.e = Engine(device)
         self.bank = DdcBank(self.e)
+        if not DDC_TENSOR_CORES:
+            self.bank.set_tensor_cores(False)
         fs, rate = cfg["fs"], cfg["rate"]
         decim = firdes.channel_decimation(fs, rate)
         taps = firdes.low_pass_2(1.0, fs, rate / 2, rate / 2, 20.0, firdes.WIN_HAMMING)
@@ -475,6 +477,7 @@ class DdcCtx(object):
         self.e.close()
 
 
+DDC_TENSOR_CORES = True  # --no-tensor-cores: keep every DDC bucket on the CUDA-core ddc_tile_kernel
 USE_MULTI = False  # --multi: one rcb_pfb_process_multi call per step instead of one rcb_pfb_process call per stream
                    # (measured on cfg5: 202 vs 218 Gsps - the per-stream launches on their own CUDA streams overlap better)
 
@@ -845,12 +848,14 @@ def main():
     ap.add_argument("--out-block", type=int, default=1024,
                     help="device output layout: channel-major in blocks of this many frames (0 = plain [N][T])")
     ap.add_argument("--multi", action="store_true", help="multi-stream workloads: ONE rcb_pfb_process_multi launch per step instead of one call per stream")
+    ap.add_argument("--no-tensor-cores", action="store_true", help="DDC workloads: CUDA-core kernel for every bucket")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ceiling", action="store_true", help="skip the bare-copy ceiling measurement of the e2e path")
     ap.add_argument("--no-also", action="store_true")
     args = ap.parse_args()
-    global USE_MULTI
+    global USE_MULTI, DDC_TENSOR_CORES
     USE_MULTI = bool(args.multi)
+    DDC_TENSOR_CORES = not args.no_tensor_cores
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference(args)

@@ -132,6 +132,15 @@ int rcb_ddc_close(rcb_t* h, int chan_id);
 int rcb_ddc_process(rcb_t* h, const void* iq, size_t nsamples, int in_mem);
 int rcb_ddc_pull(rcb_t* h, int chan_id, int which, void* dst, size_t cap_items, int dst_mem,
                  size_t* nitems);
+/* Buckets of >= 12 channels that share (decim, ntaps) with an even decim run on the tensor cores (ddc_mma_kernel:
+ * tcgen05 kind::tf32, every operand split hi + lo -> 3 MMAs, fp32 accumulate in TMEM; same 1e-5 parity bar as the CUDA-core
+ * kernel).  enable = 0 forces the CUDA-core ddc_tile_kernel for every bucket (what gr::filter::freq_xlating_fir_filter_ccc
+ * instances do one by one, rc_frontend/channel.py:35).  nseg in 1..3 = K segments of the main accumulation that get their own
+ * TMEM accumulator (0 = keep; default 3). */
+int rcb_ddc_set_tensor_cores(rcb_t* h, int enable, int nseg);
+/* ddc_mma_kernel launches on this handle so far (which path a block took is otherwise invisible to the caller) */
+int rcb_ddc_tensor_core_launches(rcb_t* h, uint64_t* launches);
+
 /* Every open channel's outputs of the last rcb_ddc_process call in ONE transfer (the per-channel pulls of a source
  * with many channels cost more than the kernels): row r of dst (row_stride_items apart) receives counts[r] items of
  * channel ids[r] (ascending chan_id; ids may be NULL).  *nrows = channels; cap_rows < *nrows -> RCB_ERANGE. */

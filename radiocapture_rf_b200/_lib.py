@@ -98,6 +98,8 @@ _PROTOTYPES = {
     "rcb_ddc_close": (C.c_int, [_vp, C.c_int]),
     "rcb_ddc_process": (C.c_int, [_vp, _vp, _sz, C.c_int]),
     "rcb_ddc_pull": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _sz, C.c_int, C.POINTER(_sz)]),
+    "rcb_ddc_set_tensor_cores": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "rcb_ddc_tensor_core_launches": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "rcb_ddc_pull_all": (C.c_int, [_vp, C.c_int, _vp, _sz, C.c_int, _vp, _vp, _sz, C.POINTER(_sz)]),
     "rcb_quad_demod": (C.c_int, [_vp, _vp, _sz, _sz, _sz, C.c_float, _vp, _vp, _sz, C.c_int]),
     "rcb_probe_mean": (C.c_int, [_vp, _vp, _sz, _sz, _sz, _sz, C.c_float, _vp, C.c_int]),

@@ -16,6 +16,7 @@
 
 #include "common.cuh"
 #include "ddc_bank.cuh"
+#include "ddc_mma.cuh"
 #include "demod.cuh"
 #include "fft_logpow.cuh"
 #include "fft_scan.cuh"
@@ -155,6 +156,15 @@ struct rcb_ctx {
         size_t in_cap2[2] = {0, 0};
         cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
         bool in_used[2] = {false, false};
+        // tensor-core path (ddc_mma_kernel): group descriptors (pinned ring like the two above) and the packed B operand
+        bool use_mma = true;      // rcb_ddc_set_tensor_cores
+        int mma_nseg = 3;
+        DdcMmaGroupDev* d_mgroups_ring = nullptr;
+        DdcMmaGroupDev* h_mgroups_ring = nullptr;  // pinned
+        size_t mgroups_cap = 0;
+        float* d_mma_b = nullptr;
+        size_t mma_b_cap = 0;     // floats
+        uint64_t mma_launches = 0;
     } ddc;
 
     // ---- FFT ----
@@ -880,6 +890,9 @@ extern "C" int rcb_close(rcb_t* h) {
     if (h->ddc.h_chans_ring) cudaFreeHost(h->ddc.h_chans_ring);
     cudaFree(h->ddc.d_groups_ring);
     if (h->ddc.h_groups_ring) cudaFreeHost(h->ddc.h_groups_ring);
+    cudaFree(h->ddc.d_mgroups_ring);
+    if (h->ddc.h_mgroups_ring) cudaFreeHost(h->ddc.h_mgroups_ring);
+    cudaFree(h->ddc.d_mma_b);
     for (int i = 0; i < 4; ++i)
         if (h->ddc.ev_slot[i]) cudaEventDestroy(h->ddc.ev_slot[i]);
     for (int i = 0; i < 2; ++i) {
@@ -1646,6 +1659,21 @@ extern "C" int rcb_ddc_set_taps(rcb_t* h, int chan_id, const float* taps, int nt
     return ddc_upload_taps(h, c);
 }
 
+extern "C" int rcb_ddc_set_tensor_cores(rcb_t* h, int enable, int nseg) {
+    if (!h || nseg < 0 || nseg > 3) return RCB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    h->ddc.use_mma = (enable != 0);
+    if (nseg) h->ddc.mma_nseg = nseg;
+    return RCB_OK;
+}
+
+extern "C" int rcb_ddc_tensor_core_launches(rcb_t* h, uint64_t* launches) {
+    if (!h || !launches) return RCB_EINVAL;
+    *launches = h->ddc.mma_launches;
+    return RCB_OK;
+}
+
 extern "C" int rcb_ddc_close(rcb_t* h, int chan_id) {
     if (!h) return RCB_EINVAL;
     auto it = h->ddc.chans.find(chan_id);
@@ -1740,6 +1768,59 @@ int ddc_process_chunk(rcb_t* h, const float2* d_x, size_t nsamples) {
         }
         size_t ngroups = 0;
         for (auto& b : buckets) ngroups += (b.second.size() + 15) / 16;
+        // buckets that go to the tensor cores: outputs [o_head, nout) by ddc_mma_kernel, the head (windows reaching into
+        // the history buffer) stays on ddc_tile_kernel
+        struct MmaPlan {
+            int o_head, lead, kchunks, ng;
+            size_t b_off;  // floats into d_mma_b
+            const float2* base;
+        };
+        std::map<std::vector<long long>, MmaPlan> mma_plans;
+        size_t mma_groups = 0, mma_b_floats = 0;
+        if (d.use_mma && tmap_encoder()) {
+            for (auto& b : buckets) {
+                const long long decim = b.first[0], ntaps = b.first[1], s_first = b.first[2], nout = b.first[3];
+                if ((int)b.second.size() < kDdcMmaMinChans || (decim & 1)) continue;
+                const long long need = std::max<long long>(0, ntaps - s_first);   // window start >= 1
+                const long long o_head = (need + decim - 1) / decim;
+                if (nout - o_head < 64) continue;
+                MmaPlan pl;
+                pl.o_head = (int)o_head;
+                const long long w0 = s_first + o_head * decim - (ntaps - 1);
+                const float2* base = d_x + w0;
+                pl.lead = (reinterpret_cast<uintptr_t>(base) & 15) ? 1 : 0;
+                pl.base = base - pl.lead;
+                if (reinterpret_cast<uintptr_t>(pl.base) & 15) continue;  // input not even 8-byte aligned
+                pl.kchunks = (int)((2 * (ntaps + pl.lead) + 31) / 32);
+                pl.ng = (int)((b.second.size() + 63) / 64);
+                pl.b_off = mma_b_floats;
+                mma_b_floats += (size_t)2 * pl.ng * 128 * pl.kchunks * 32;
+                mma_groups += pl.ng;
+                mma_plans[b.first] = pl;
+            }
+        }
+        if (mma_groups > d.mgroups_cap) {
+            CK(cudaStreamSynchronize(h->stream));
+            cudaFree(d.d_mgroups_ring);
+            if (d.h_mgroups_ring) cudaFreeHost(d.h_mgroups_ring);
+            d.d_mgroups_ring = nullptr;
+            d.h_mgroups_ring = nullptr;
+            d.mgroups_cap = 0;
+            const size_t cap = std::max<size_t>(4, mma_groups * 2);
+            CK(cudaMalloc(&d.d_mgroups_ring, kDdcSlots * cap * sizeof(DdcMmaGroupDev)));
+            CK(cudaHostAlloc(&d.h_mgroups_ring, kDdcSlots * cap * sizeof(DdcMmaGroupDev), cudaHostAllocDefault));
+            d.mgroups_cap = cap;
+        }
+        if (mma_b_floats > d.mma_b_cap) {
+            CK(cudaStreamSynchronize(h->stream));
+            cudaFree(d.d_mma_b);
+            d.d_mma_b = nullptr;
+            d.mma_b_cap = 0;
+            CK(cudaMalloc(&d.d_mma_b, mma_b_floats * sizeof(float)));
+            d.mma_b_cap = mma_b_floats;
+        }
+        DdcMmaGroupDev* h_mgroups = d.h_mgroups_ring ? d.h_mgroups_ring + (size_t)slot * d.mgroups_cap : nullptr;
+        DdcMmaGroupDev* d_mgroups = d.d_mgroups_ring ? d.d_mgroups_ring + (size_t)slot * d.mgroups_cap : nullptr;
         if (ngroups > d.groups_cap) {
             CK(cudaStreamSynchronize(h->stream));
             cudaFree(d.d_groups_ring);
@@ -1767,15 +1848,84 @@ int ddc_process_chunk(rcb_t* h, const float2* d_x, size_t nsamples) {
                     g.ntaps = (int)b.first[1];
                     g.s_first = b.first[2];
                     g.nout = (int)b.first[3];
+                    auto mp = mma_plans.find(b.first);
+                    if (mp != mma_plans.end()) g.nout = mp->second.o_head;  // the head only
                 }
                 (void)first_group;
+            }
+            if (mma_groups) {
+                size_t mg = 0;
+                for (auto& b : buckets) {
+                    auto mp = mma_plans.find(b.first);
+                    if (mp == mma_plans.end()) continue;
+                    const MmaPlan& pl = mp->second;
+                    for (int q = 0; q < pl.ng; ++q) {
+                        DdcMmaGroupDev& g = h_mgroups[mg++];
+                        g.nch = (int)std::min<size_t>(64, b.second.size() - (size_t)q * 64);
+                        for (int u = 0; u < 64; ++u) g.ch[u] = (u < g.nch) ? b.second[(size_t)q * 64 + u] : -1;
+                        g.ncols = ((2 * g.nch + 15) / 16) * 16;
+                        g.ntaps = (int)b.first[1];
+                        g.decim = (int)b.first[0];
+                        g.lead = pl.lead;
+                        g.kchunks = pl.kchunks;
+                        g.o_head = pl.o_head;
+                        g.nout = (int)b.first[3];
+                        g.ldb = pl.kchunks * 32;
+                        g.nseg = std::max(1, std::min(std::min(3, d.mma_nseg), pl.kchunks));
+                    }
+                }
+                CK(cudaMemcpyAsync(d_mgroups, h_mgroups, mma_groups * sizeof(DdcMmaGroupDev), cudaMemcpyHostToDevice, h->stream));
+                static bool mma_attr_dev[64] = {};
+                if (!mma_attr_dev[h->device & 63]) {
+                    CK(cudaFuncSetAttribute(ddc_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDdcMmaSmem));
+                    mma_attr_dev[h->device & 63] = true;
+                }
+                mg = 0;
+                for (auto& b : buckets) {
+                    auto mp = mma_plans.find(b.first);
+                    if (mp == mma_plans.end()) continue;
+                    const MmaPlan& pl = mp->second;
+                    const int decim = (int)b.first[0], ntaps = (int)b.first[1], nout = (int)b.first[3];
+                    const uint64_t ldb = (uint64_t)pl.kchunks * 32;
+                    float* bptr = d.d_mma_b + pl.b_off;
+                    CUtensorMap tm_a, tm_b;
+                    const uint64_t nrows = (uint64_t)(nout - pl.o_head);
+                    const uint64_t ad[2] = {(uint64_t)2 * (uint64_t)(ntaps + pl.lead), nrows};
+                    const uint64_t as[1] = {(uint64_t)decim * 8};
+                    const uint64_t bd[2] = {ldb, (uint64_t)2 * pl.ng * 128};
+                    const uint64_t bs[1] = {ldb * 4};
+                    const uint32_t box[2] = {32, 128};
+                    if (!tmap_encode_f32(&tm_a, 2, pl.base, ad, as, box, CU_TENSOR_MAP_SWIZZLE_128B) ||
+                        !tmap_encode_f32(&tm_b, 2, bptr, bd, bs, box, CU_TENSOR_MAP_SWIZZLE_128B))
+                        {
+                        snprintf(h->err, sizeof(h->err), "ddc: tensor map encode failed");
+                        return RCB_ECUDA;
+                    }
+                    dim3 pg((unsigned)((ldb + 255) / 256), 128, (unsigned)pl.ng);
+                    ddc_mma_pack_kernel<<<pg, 256, 0, h->stream>>>(d.d_chans, d_mgroups + mg, pl.ng, bptr);
+                    CKL(h);
+                    dim3 grid((unsigned)((nrows + 127) / 128), (unsigned)pl.ng);
+                    ddc_mma_kernel<<<grid, kDdcMmaThreads, kDdcMmaSmem, h->stream>>>(tm_a, tm_b, d.d_chans, d_mgroups + mg, pl.ng);
+                    CKL(h);
+                    d.mma_launches++;
+                    mg += pl.ng;
+                }
             }
             if (ngroups) {
                 CK(cudaMemcpyAsync(d.d_groups, d.h_groups, ngroups * sizeof(DdcGroupDev), cudaMemcpyHostToDevice, h->stream));
                 gi = 0;
                 for (auto& b : buckets) {
                     const size_t ng = (b.second.size() + 15) / 16;
-                    const int decim = (int)b.first[0], ntaps = (int)b.first[1], nout = (int)b.first[3];
+                    const int decim = (int)b.first[0], ntaps = (int)b.first[1];
+                    int nout = (int)b.first[3];
+                    {
+                        auto mp = mma_plans.find(b.first);
+                        if (mp != mma_plans.end()) nout = mp->second.o_head;
+                    }
+                    if (nout == 0) {
+                        gi += ng;
+                        continue;
+                    }
                     // output quads per CTA: as many as the group's channel count leaves warps for and smem allows
                     const size_t per_group = std::min<size_t>(16, b.second.size());
                     int oq = per_group <= 4 ? 8 : (per_group <= 8 ? 4 : 2);

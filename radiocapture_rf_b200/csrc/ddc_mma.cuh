@@ -1,0 +1,288 @@
+// K2 many-channel path on the tensor cores:  ddc_mma_kernel  (tcgen05.mma kind::tf32, accumulators in TMEM).
+//
+// When many `rc_frontend/channel.py:35` channels (freq_xlating_fir_filter_ccc) of one source share (decim, ntaps) -
+// the reference's normal case: every P25/analog voice channel of a wideband source is 12.5 kHz wide - the bank is a
+// contraction
+//
+//     Y[o][2c + {re,im}]  =  sum_kk  A[o][kk] * B[kk][2c + {re,im}]
+//
+//     A[o][kk] = the input block read as interleaved floats starting at the window of output o
+//                (row o begins D complex samples after row o-1: the rows OVERLAP in memory, a 2-D tensor map with
+//                 row stride D*8 bytes is the im2col - nothing is materialised)
+//     B[2r][2c] = t.re   B[2r+1][2c] = -t.im   B[2r][2c+1] = t.im   B[2r+1][2c+1] = t.re     t = ct_rev_c[r]
+//
+// 931 FMA per input sample for 64 channels of 2327 taps at D = 640: compute bound, so it belongs on tcgen05, not on
+// FFMA2 (ddc_tile_kernel reaches 27 TFLOP/s).  fp32 parity (1e-5) needs more than tf32's 11 significand bits: every
+// operand is split  v = hi + lo  (hi = v with the low 13 mantissa bits cleared, exactly representable in tf32;
+// lo = v - hi, exact in fp32) and three MMAs are issued per k-step,  hi*hi  into the main accumulator and
+// hi*lo + lo*hi  into a second one (its rounding errors are 2^-11 smaller); the dropped lo*lo term is 2^-22 relative.
+// The main accumulation is cut into `nseg` K segments with their own TMEM accumulators, summed in fp32 in the epilogue
+// (bounds the length of one tensor-core accumulation chain).
+//
+// CTA = 128 outputs x up to 64 channels (N = 128 columns), 6 warps:
+//   warp 0      TMA producer: per k-chunk of 32 floats  A tile [128 x 128 B] (raw fp32), B_hi and B_lo tiles, SWIZZLE_128B
+//   warps 2..5  split the raw A tile in place into hi (same bytes, masked) and write lo to a second tile at the same
+//               (swizzled) offsets - elementwise, so the swizzle never has to be decoded - then fence.proxy.async
+//   warp 1      one elected lane issues 12 tcgen05.mma per chunk (4 k-steps of 8 x 3 operand pairs), tcgen05.commit
+//               frees the stage; a final commit hands the accumulators to
+//   warps 2..5  epilogue: tcgen05.ld their 32 TMEM lanes, add the accumulators, derotate with the exact phase
+//               (double, like ddc_tile_kernel) and store out_iq (consecutive lanes = consecutive outputs of a channel).
+// 3 stages x 64 KB of shared memory, 512 TMEM columns, one CTA per SM.
+//
+// The first outputs of a block - whose windows reach back into the history buffer - stay on ddc_tile_kernel (the
+// tensor map addresses ONE buffer); so do odd decimations (row stride must be a multiple of 16 bytes) and buckets of
+// fewer than kDdcMmaMinChans channels.
+#pragma once
+#include "common.cuh"
+#include "ddc_bank.cuh"
+#include "tma_utils.cuh"
+
+namespace rcb {
+
+constexpr int kDdcMmaMinChans = 12;
+constexpr int kDdcMmaStages = 3;
+constexpr int kDdcMmaTile = 16384;                   // one [128 rows][32 floats] operand tile
+constexpr int kDdcMmaStageBytes = 4 * kDdcMmaTile;   // A (raw -> hi), A lo, B hi, B lo
+constexpr int kDdcMmaSmem = kDdcMmaStages * kDdcMmaStageBytes + 1024 /*alignment*/ + 256 /*barriers*/;
+constexpr int kDdcMmaThreads = 192;
+
+struct DdcMmaGroupDev {
+    int ch[64];   // indices into the DdcChanDev array, -1 = unused
+    int nch;
+    int ncols;    // MMA N: 2 * nch rounded up to a multiple of 16
+    int ntaps, decim;
+    int lead;     // 0 / 1 zero complex rows in front of B (the window base moved one sample back for 16-byte alignment)
+    int kchunks;  // ceil(2 * (ntaps + lead) / 32)
+    int o_head;   // first output this kernel computes (earlier ones: ddc_tile_kernel)
+    int nout;
+    int ldb;      // row length of B in floats (kchunks * 32)
+    int nseg;     // main accumulator segments (1..3)
+};
+
+// B operand of every group of a bucket, [hi | lo][group][128 columns][ldb] (K-major rows), from the channels'
+// composite taps.  grid (ceil(ldb / 256), 128, ngroups)
+__global__ void __launch_bounds__(256) ddc_mma_pack_kernel(const DdcChanDev* __restrict__ chans,
+                                                           const DdcMmaGroupDev* __restrict__ groups, int ngroups,
+                                                           float* __restrict__ b) {
+    const DdcMmaGroupDev& g = groups[blockIdx.z];
+    const int kk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kk >= g.ldb) return;
+    const int n = blockIdx.y, c = n >> 1, comp = n & 1;
+    float v = 0.f;
+    const int r = (kk >> 1) - g.lead, part = kk & 1;
+    if (c < g.nch && r >= 0 && r < g.ntaps && g.ch[c] >= 0) {
+        const float2 t = __ldg(chans[g.ch[c]].ctaps_rev + r);
+        v = comp ? (part ? t.x : t.y) : (part ? -t.y : t.x);
+    }
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    const size_t row = (size_t)blockIdx.z * 128 + n;
+    b[row * g.ldb + kk] = hi;
+    b[((size_t)ngroups * 128 + row) * g.ldb + kk] = v - hi;
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+        "l"(tm), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem], 128 x N x 8 tf32
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all MMAs issued so far by this thread arrive on `bar` when they have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// this warp's 32 TMEM lanes x 16 consecutive columns -> 16 registers per thread (thread = lane = accumulator row)
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// K-major SWIZZLE_128B operand tile ([rows][128 B], 8-row groups 1024 B apart), 1024-byte aligned
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);  // start address
+    d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major; canonical 1)
+    d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset: next 8-row group
+    d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    return d;
+}
+
+__global__ void __launch_bounds__(kDdcMmaThreads, 1)
+ddc_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+               const DdcChanDev* __restrict__ chans, const DdcMmaGroupDev* __restrict__ groups, int ngroups) {
+    extern __shared__ unsigned char ddc_mma_raw[];
+    const uint32_t raw_addr = smem_addr_u32(ddc_mma_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    unsigned char* base_p = ddc_mma_raw + (base - raw_addr);
+    const uint32_t bars = base + kDdcMmaStages * kDdcMmaStageBytes;
+    // barriers: full[3] @0, conv[3] @24, empty[3] @48, accum @72; tmem slot @96
+    auto bar_full = [&](int s) { return bars + 8u * s; };
+    auto bar_conv = [&](int s) { return bars + 24u + 8u * s; };
+    auto bar_empty = [&](int s) { return bars + 48u + 8u * s; };
+    const uint32_t bar_accum = bars + 72u;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_p + kDdcMmaStages * kDdcMmaStageBytes + 96);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const DdcMmaGroupDev& g = groups[blockIdx.y];
+    const int kchunks = g.kchunks;
+    const int tile = blockIdx.x;
+
+    if (tid == 0) {
+        for (int s = 0; s < kDdcMmaStages; ++s) {
+            mbar_init_a(bar_full(s), 1);
+            mbar_init_a(bar_conv(s), 4);
+            mbar_init_a(bar_empty(s), 1);
+        }
+        mbar_init_a(bar_accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        prefetch_tmap(&tm_a);
+        prefetch_tmap(&tm_b);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
+                         bars + 96u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kc = 0; kc < kchunks; ++kc) {
+                const int s = kc % kDdcMmaStages;
+                const uint32_t ph = (uint32_t)(kc / kDdcMmaStages) & 1u;
+                mbar_wait_a(bar_empty(s), ph ^ 1u);
+                const uint32_t st = base + (uint32_t)s * kDdcMmaStageBytes;
+                mbar_expect_tx_a(bar_full(s), 3u * kDdcMmaTile);
+                tma_load_2d(st, &tm_a, kc * 32, tile * 128, bar_full(s));
+                tma_load_2d(st + 2u * kDdcMmaTile, &tm_b, kc * 32, (int)blockIdx.y * 128, bar_full(s));
+                tma_load_2d(st + 3u * kDdcMmaTile, &tm_b, kc * 32, (ngroups + (int)blockIdx.y) * 128, bar_full(s));
+            }
+        }
+    } else if (warp == 1) {
+        // instruction descriptor: D fp32, A / B tf32, both K-major, M 128, N ncols
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.ncols >> 3) << 17) | ((128u >> 4) << 24);
+        const int nseg = g.nseg;
+        const uint32_t t_cross = tmem + 384u;
+        int seg = 0, seg_end = (kchunks + nseg - 1) / nseg;
+        bool seg_first = true;
+        for (int kc = 0; kc < kchunks; ++kc) {
+            const int s = kc % kDdcMmaStages;
+            const uint32_t ph = (uint32_t)(kc / kDdcMmaStages) & 1u;
+            if (kc == seg_end) {
+                ++seg;
+                seg_end = ((seg + 1) * kchunks + nseg - 1) / nseg;
+                seg_first = true;
+            }
+            mbar_wait_a(bar_full(s), ph);
+            mbar_wait_a(bar_conv(s), ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t st = base + (uint32_t)s * kDdcMmaStageBytes;
+                const uint64_t a_hi = tc_smem_desc(st), a_lo = tc_smem_desc(st + kDdcMmaTile);
+                const uint64_t b_hi = tc_smem_desc(st + 2u * kDdcMmaTile), b_lo = tc_smem_desc(st + 3u * kDdcMmaTile);
+                const uint32_t t_main = tmem + 128u * (uint32_t)seg;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint64_t adv = (uint64_t)(2 * j);  // 8 floats = 32 bytes along K inside the 128-byte swizzle row
+                    tc_mma_tf32(t_main, a_hi + adv, b_hi + adv, idesc, (seg_first && j == 0) ? 0u : 1u);
+                    tc_mma_tf32(t_cross, a_hi + adv, b_lo + adv, idesc, (kc == 0 && j == 0) ? 0u : 1u);
+                    tc_mma_tf32(t_cross, a_lo + adv, b_hi + adv, idesc, 1u);
+                }
+                tc_commit(bar_empty(s));
+            }
+            seg_first = false;
+            __syncwarp();
+        }
+        if (lane == 0) tc_commit(bar_accum);
+        __syncwarp();
+    } else {
+        const int ct = tid - 64;  // 0..127
+        for (int kc = 0; kc < kchunks; ++kc) {
+            const int s = kc % kDdcMmaStages;
+            const uint32_t ph = (uint32_t)(kc / kDdcMmaStages) & 1u;
+            mbar_wait_a(bar_full(s), ph);
+            float4* a = reinterpret_cast<float4*>(base_p + (size_t)s * kDdcMmaStageBytes);
+            float4* al = reinterpret_cast<float4*>(base_p + (size_t)s * kDdcMmaStageBytes + kDdcMmaTile);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int idx = ct + 128 * i;
+                const float4 v = a[idx];
+                float4 hi, lo;
+                hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                lo.x = v.x - hi.x;
+                lo.y = v.y - hi.y;
+                lo.z = v.z - hi.z;
+                lo.w = v.w - hi.w;
+                a[idx] = hi;
+                al[idx] = lo;
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(bar_conv(s));
+        }
+        // ---- epilogue ----
+        mbar_wait_a(bar_accum, 0u);
+        tc_fence_after();
+        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;
+        const int o = g.o_head + tile * 128 + row;
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+        const int nseg = g.nseg;
+        for (int c0 = 0; c0 < g.ncols; c0 += 16) {
+            float acc[16], t[16];
+            tc_ld16(trow + 384u + (uint32_t)c0, acc);
+            for (int sg = nseg - 1; sg >= 0; --sg) {
+                tc_ld16(trow + 128u * (uint32_t)sg + (uint32_t)c0, t);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[i] += t[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int cslot = (c0 >> 1) + i;
+                const int ci = (cslot < g.nch) ? g.ch[cslot] : -1;
+                if (ci >= 0 && o < g.nout) {
+                    const DdcChanDev& ch = chans[ci];
+                    double phs = ch.phase0 + ch.cyc * (double)o;
+                    phs -= floor(phs);
+                    double sn, cs;
+                    sincospi(-2.0 * phs, &sn, &cs);
+                    const float cf = (float)cs, sf = (float)sn;
+                    const float ax = acc[2 * i], ay = acc[2 * i + 1];
+                    ch.out_iq[o] = make_float2(fmaf(ax, cf, -ay * sf), fmaf(ax, sf, ay * cf));
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
+}  // namespace rcb

@@ -301,6 +301,17 @@ class DdcBank(object):
     def close(self, chan):
         check(self.e.lib.rcb_ddc_close(self.e.h, int(chan)), "rcb_ddc_close", self.e.h)
 
+    def set_tensor_cores(self, enable=True, nseg=0):
+        """Buckets of >= 12 channels sharing (decim, ntaps) run on tcgen05 (3 x tf32 split) by default; False keeps
+        every bucket on the CUDA-core kernel.  nseg 1..3: K segments with their own TMEM accumulator (0 = keep)."""
+        check(self.e.lib.rcb_ddc_set_tensor_cores(self.e.h, 1 if enable else 0, int(nseg)), "rcb_ddc_set_tensor_cores",
+              self.e.h)
+
+    def tensor_core_launches(self):
+        n = C.c_uint64(0)
+        check(self.e.lib.rcb_ddc_tensor_core_launches(self.e.h, C.byref(n)), "rcb_ddc_tensor_core_launches", self.e.h)
+        return int(n.value)
+
     def process(self, iq):
         iq = np.ascontiguousarray(iq, dtype=np.complex64)
         check(self.e.lib.rcb_ddc_process(self.e.h, iq.ctypes.data, len(iq), MEM_HOST), "rcb_ddc_process", self.e.h)

@@ -312,3 +312,106 @@ def test_two_engines_on_one_device_keep_their_shared_memory_opt_in(built_lib):
     finally:
         a.close()
         b.close()
+
+
+def _open_bank(engine, decim, taps, offs, fs, tensor_cores, nseg=0):
+    bank = DdcBank(engine)
+    bank.set_tensor_cores(tensor_cores, nseg)
+    ids = [bank.open(decim, taps, f, fs, OUT_IQ | OUT_FM, 5.0) for f in offs]
+    return bank, ids
+
+
+@pytest.mark.parametrize("nseg", [1, 3])
+def test_tensor_core_bank_matches_oracle_and_cuda_core_kernel(engine, nseg):
+    """24 channels sharing (D 96, 349 taps): the bucket runs on ddc_mma_kernel (tcgen05 kind::tf32, hi/lo split), the
+    block's first outputs on the CUDA-core kernel.  Same 1e-5 bar against the float64 oracle for every channel."""
+    from radiocapture_rf_b200.engine import Engine
+    x, fs, _ = synth.cfg1(1 << 18, seed=21)
+    decim, taps = fd.channel_taps(fs, 12500)
+    rng = np.random.default_rng(3)
+    offs = list(rng.uniform(-0.45 * fs, 0.45 * fs, 24))
+    bank, ids = _open_bank(engine, decim, taps, offs, fs, True, nseg)
+    l0 = bank.tensor_core_launches()
+    bank.process(x)
+    assert bank.tensor_core_launches() == l0 + 1
+    ys = {c: bank.pull(c, OUT_IQ) for c in ids}
+    fms = {c: bank.pull(c, OUT_FM) for c in ids}
+    e2 = Engine(0)
+    try:
+        bank2, ids2 = _open_bank(e2, decim, taps, offs, fs, False)
+        bank2.process(x)
+        assert bank2.tensor_core_launches() == 0
+        worst = worst_cc = 0.0
+        for cid, cid2, f in zip(ids, ids2, offs):
+            ref = gb.freq_xlating_fir(x, taps, decim, f, fs)
+            y = ys[cid]
+            n = min(len(y), len(ref))
+            assert n >= len(x) // decim
+            err = gb.rel_l2(y[:n], ref[:n])
+            worst = max(worst, err)
+            worst_cc = max(worst_cc, gb.rel_l2(y, bank2.pull(cid2, OUT_IQ)))
+            assert err <= TOL, (f, err)
+            fref = gb.quadrature_demod(ref[:n], 5.0)
+            assert _fm_err(fms[cid][:n], fref, 5.0) <= 2e-5
+    finally:
+        e2.close()
+    print("tensor-core bank nseg %d: worst rel_l2 vs oracle %.3g, vs CUDA-core kernel %.3g" % (nseg, worst, worst_cc))
+    assert worst_cc <= 5e-6
+
+
+def test_tensor_core_bank_ragged_blocks_and_two_column_groups(engine):
+    """70 channels (two column groups: 64 + 6) fed in ragged blocks - odd lengths flip the 16-byte alignment of the
+    window base (the `lead` row of the B operand), short blocks fall back to the CUDA-core kernel - equal the one-shot
+    result and the oracle."""
+    from radiocapture_rf_b200.engine import Engine
+    x, fs, _ = synth.cfg1(300000, seed=8)
+    decim, taps = fd.channel_taps(fs, 12500)
+    rng = np.random.default_rng(5)
+    offs = list(rng.uniform(-0.45 * fs, 0.45 * fs, 70))
+    bank, ids = _open_bank(engine, decim, taps, offs, fs, True)
+    bank.process(x)
+    one = {c: bank.pull(c, OUT_IQ) for c in ids}
+    e2 = Engine(0)
+    try:
+        bank2, ids2 = _open_bank(e2, decim, taps, offs, fs, True)
+        parts = {c: [] for c in ids2}
+        pos = 0
+        for blk in [50001, 96 * 700 + 1, 333, 100000, 7, 0, 40003]:
+            bank2.process(x[pos:pos + blk])
+            pos += blk
+            for c in ids2:
+                parts[c].append(bank2.pull(c, OUT_IQ))
+        bank2.process(x[pos:])
+        for c in ids2:
+            parts[c].append(bank2.pull(c, OUT_IQ))
+        assert bank2.tensor_core_launches() >= 4
+        for k, (c, c2, f) in enumerate(zip(ids, ids2, offs)):
+            yb = np.concatenate(parts[c2])
+            assert len(yb) == len(one[c])
+            assert gb.rel_l2(yb, one[c]) <= 2e-6, f
+            if k % 9 == 0 or k >= 64:
+                ref = gb.freq_xlating_fir(x, taps, decim, f, fs)
+                n = min(len(yb), len(ref))
+                assert gb.rel_l2(yb[:n], ref[:n]) <= TOL, f
+    finally:
+        e2.close()
+
+
+def test_tensor_core_bank_wideband_2327_taps(engine):
+    """The many-channel bench shape: fs 16 Msps, D 640, 2327 taps (147 k-chunks of the MMA pipeline), 64 channels."""
+    fs, rate = 16.0e6, 12500
+    decim, taps = fd.channel_taps(fs, rate)
+    assert decim == 640 and len(taps) == 2327
+    n = 1 << 19
+    rng = np.random.default_rng(9)
+    offs = list(rng.uniform(-0.45 * fs, 0.45 * fs, 64))
+    x = synth.wideband(n, fs, offs[:12], seed=13)
+    bank, ids = _open_bank(engine, decim, taps, offs, fs, True)
+    bank.process(x)
+    assert bank.tensor_core_launches() == 1
+    for k in [0, 1, 31, 62, 63]:
+        y = bank.pull(ids[k], OUT_IQ)
+        ref = gb.freq_xlating_fir(x, taps, decim, offs[k], fs)
+        m = min(len(y), len(ref))
+        assert m >= n // decim
+        assert gb.rel_l2(y[:m], ref[:m]) <= TOL, offs[k]
