@@ -55,6 +55,7 @@ struct DdcChan {
     double cyc = 0;             // frac(f0*D/fs)
     double phase_base = 0;      // phase (cycles) at output i_base
     uint64_t i_base = 0;
+    uint64_t taps_ver = 0;      // changes with every upload of the composite taps (open / retune / set_taps)
 };
 
 struct Stage {
@@ -165,6 +166,8 @@ struct rcb_ctx {
         float* d_mma_b = nullptr;
         size_t mma_b_cap = 0;     // floats
         uint64_t mma_launches = 0;
+        std::vector<long long> mma_b_sig;  // what d_mma_b holds (bucket shapes, channel ids, tap versions): unchanged ->
+                                           // the pack kernel is skipped
     } ddc;
 
     // ---- FFT ----
@@ -1586,6 +1589,8 @@ int ddc_upload_taps(rcb_t* h, DdcChan& c) {
     double cyc = c.center_freq * (double)c.decim / c.samp_rate;
     cyc -= floor(cyc);
     c.cyc = cyc;
+    static uint64_t ver_counter = 0;
+    c.taps_ver = ++ver_counter;
     return RCB_OK;
 }
 int ddc_ensure_hist(rcb_t* h) {
@@ -1723,8 +1728,11 @@ int ddc_process_chunk(rcb_t* h, const float2* d_x, size_t nsamples) {
         size_t max_nout = 0;
         size_t ci = 0;
         bool any_fm = false;
+        std::vector<const DdcChan*> order;
+        order.reserve(M);
         for (auto& kv : d.chans) {
             DdcChan& c = kv.second;
+            order.push_back(&c);
             // outputs i with newest sample  start + i*D  in [n0, n1)
             const uint64_t s_next = c.start_sample + c.i_next * (uint64_t)c.decim;
             size_t nout = 0;
@@ -1816,8 +1824,28 @@ int ddc_process_chunk(rcb_t* h, const float2* d_x, size_t nsamples) {
             cudaFree(d.d_mma_b);
             d.d_mma_b = nullptr;
             d.mma_b_cap = 0;
+            d.mma_b_sig.clear();
             CK(cudaMalloc(&d.d_mma_b, mma_b_floats * sizeof(float)));
             d.mma_b_cap = mma_b_floats;
+        }
+        bool mma_pack = true;
+        if (mma_groups) {
+            std::vector<long long> sig;
+            for (auto& b : buckets) {
+                auto mp = mma_plans.find(b.first);
+                if (mp == mma_plans.end()) continue;
+                sig.push_back(b.first[0]);
+                sig.push_back(b.first[1]);
+                sig.push_back(mp->second.lead);
+                sig.push_back((long long)mp->second.b_off);
+                sig.push_back((long long)b.second.size());
+                for (int idx : b.second) {
+                    sig.push_back(order[(size_t)idx]->id);
+                    sig.push_back((long long)order[(size_t)idx]->taps_ver);
+                }
+            }
+            mma_pack = (sig != d.mma_b_sig);
+            if (mma_pack) d.mma_b_sig.swap(sig);
         }
         DdcMmaGroupDev* h_mgroups = d.h_mgroups_ring ? d.h_mgroups_ring + (size_t)slot * d.mgroups_cap : nullptr;
         DdcMmaGroupDev* d_mgroups = d.d_mgroups_ring ? d.d_mgroups_ring + (size_t)slot * d.mgroups_cap : nullptr;
@@ -1849,7 +1877,7 @@ int ddc_process_chunk(rcb_t* h, const float2* d_x, size_t nsamples) {
                     g.s_first = b.first[2];
                     g.nout = (int)b.first[3];
                     auto mp = mma_plans.find(b.first);
-                    if (mp != mma_plans.end()) g.nout = mp->second.o_head;  // the head only
+                    if (mp != mma_plans.end()) g.nout = 0;  // ddc_head_kernel + ddc_mma_kernel cover the bucket
                 }
                 (void)first_group;
             }
@@ -1872,12 +1900,25 @@ int ddc_process_chunk(rcb_t* h, const float2* d_x, size_t nsamples) {
                         g.nout = (int)b.first[3];
                         g.ldb = pl.kchunks * 32;
                         g.nseg = std::max(1, std::min(std::min(3, d.mma_nseg), pl.kchunks));
+                        g.kq = std::max(1, (2 * g.decim + 16) / 32);
+#ifdef RCB_EXPERIMENTS
+                        if (const char* e = getenv("RCB_DDC_KQ")) g.kq = std::max(1, atoi(e));
+#endif
                     }
                 }
                 CK(cudaMemcpyAsync(d_mgroups, h_mgroups, mma_groups * sizeof(DdcMmaGroupDev), cudaMemcpyHostToDevice, h->stream));
                 static bool mma_attr_dev[64] = {};
                 if (!mma_attr_dev[h->device & 63]) {
-                    CK(cudaFuncSetAttribute(ddc_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDdcMmaSmem));
+                    CK(cudaFuncSetAttribute(ddc_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDdcMmaSmem));
+#ifdef RCB_EXPERIMENTS
+                    CK(cudaFuncSetAttribute(ddc_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDdcMmaSmem));
+                    CK(cudaFuncSetAttribute(ddc_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDdcMmaSmem));
+                    CK(cudaFuncSetAttribute(ddc_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDdcMmaSmem));
+                    CK(cudaFuncSetAttribute(ddc_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDdcMmaSmem));
+                    CK(cudaFuncSetAttribute(ddc_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDdcMmaSmem));
+                    CK(cudaFuncSetAttribute(ddc_mma_kernel<35>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDdcMmaSmem));
+                    CK(cudaFuncSetAttribute(ddc_mma_kernel<27>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDdcMmaSmem));
+#endif
                     mma_attr_dev[h->device & 63] = true;
                 }
                 mg = 0;
@@ -1895,17 +1936,51 @@ int ddc_process_chunk(rcb_t* h, const float2* d_x, size_t nsamples) {
                     const uint64_t bd[2] = {ldb, (uint64_t)2 * pl.ng * 128};
                     const uint64_t bs[1] = {ldb * 4};
                     const uint32_t box[2] = {32, 128};
-                    if (!tmap_encode_f32(&tm_a, 2, pl.base, ad, as, box, CU_TENSOR_MAP_SWIZZLE_128B) ||
+                    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+#ifdef RCB_EXPERIMENTS
+                    if (const char* e = getenv("RCB_DDC_PROMO"))
+                        if (atoi(e) == 256) promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+#endif
+                    if (!tmap_encode_f32(&tm_a, 2, pl.base, ad, as, box, CU_TENSOR_MAP_SWIZZLE_128B, promo) ||
                         !tmap_encode_f32(&tm_b, 2, bptr, bd, bs, box, CU_TENSOR_MAP_SWIZZLE_128B))
                         {
                         snprintf(h->err, sizeof(h->err), "ddc: tensor map encode failed");
                         return RCB_ECUDA;
                     }
-                    dim3 pg((unsigned)((ldb + 255) / 256), 128, (unsigned)pl.ng);
-                    ddc_mma_pack_kernel<<<pg, 256, 0, h->stream>>>(d.d_chans, d_mgroups + mg, pl.ng, bptr);
-                    CKL(h);
+                    if (mma_pack) {
+                        dim3 pg((unsigned)((ldb + 255) / 256), 128, (unsigned)pl.ng);
+                        ddc_mma_pack_kernel<<<pg, 256, 0, h->stream>>>(d.d_chans, d_mgroups + mg, pl.ng, bptr);
+                        CKL(h);
+                    }
+                    if (pl.o_head > 0) {
+                        dim3 hg((unsigned)pl.o_head, 64, (unsigned)pl.ng);
+                        ddc_head_kernel<<<hg, 128, 0, h->stream>>>(d.d_chans, d_mgroups + mg, d_x, (long long)nsamples,
+                                                                  d.d_hist[d.hist_cur], kDdcHistCap);
+                        CKL(h);
+                    }
                     dim3 grid((unsigned)((nrows + 127) / 128), (unsigned)pl.ng);
-                    ddc_mma_kernel<<<grid, kDdcMmaThreads, kDdcMmaSmem, h->stream>>>(tm_a, tm_b, d.d_chans, d_mgroups + mg, pl.ng);
+                    int dbg = 0;
+#ifdef RCB_EXPERIMENTS
+                    if (const char* e = getenv("RCB_DDC_DBG")) dbg = atoi(e);
+#endif
+                    if (dbg == 0)
+                        ddc_mma_kernel<0><<<grid, kDdcMmaThreads, kDdcMmaSmem, h->stream>>>(tm_a, tm_b, d.d_chans, d_mgroups + mg, pl.ng);
+#ifdef RCB_EXPERIMENTS
+                    else if (dbg == 1)
+                        ddc_mma_kernel<1><<<grid, kDdcMmaThreads, kDdcMmaSmem, h->stream>>>(tm_a, tm_b, d.d_chans, d_mgroups + mg, pl.ng);
+                    else if (dbg == 2)
+                        ddc_mma_kernel<2><<<grid, kDdcMmaThreads, kDdcMmaSmem, h->stream>>>(tm_a, tm_b, d.d_chans, d_mgroups + mg, pl.ng);
+                    else if (dbg == 3)
+                        ddc_mma_kernel<3><<<grid, kDdcMmaThreads, kDdcMmaSmem, h->stream>>>(tm_a, tm_b, d.d_chans, d_mgroups + mg, pl.ng);
+                    else if (dbg == 32)
+                        ddc_mma_kernel<32><<<grid, kDdcMmaThreads, kDdcMmaSmem, h->stream>>>(tm_a, tm_b, d.d_chans, d_mgroups + mg, pl.ng);
+                    else if (dbg == 35)
+                        ddc_mma_kernel<35><<<grid, kDdcMmaThreads, kDdcMmaSmem, h->stream>>>(tm_a, tm_b, d.d_chans, d_mgroups + mg, pl.ng);
+                    else if (dbg == 27)
+                        ddc_mma_kernel<27><<<grid, kDdcMmaThreads, kDdcMmaSmem, h->stream>>>(tm_a, tm_b, d.d_chans, d_mgroups + mg, pl.ng);
+                    else
+                        ddc_mma_kernel<4><<<grid, kDdcMmaThreads, kDdcMmaSmem, h->stream>>>(tm_a, tm_b, d.d_chans, d_mgroups + mg, pl.ng);
+#endif
                     CKL(h);
                     d.mma_launches++;
                     mg += pl.ng;
@@ -1920,7 +1995,7 @@ int ddc_process_chunk(rcb_t* h, const float2* d_x, size_t nsamples) {
                     int nout = (int)b.first[3];
                     {
                         auto mp = mma_plans.find(b.first);
-                        if (mp != mma_plans.end()) nout = mp->second.o_head;
+                        if (mp != mma_plans.end()) nout = 0;
                     }
                     if (nout == 0) {
                         gi += ng;

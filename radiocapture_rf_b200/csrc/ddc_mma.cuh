@@ -19,19 +19,20 @@
 // The main accumulation is cut into `nseg` K segments with their own TMEM accumulators, summed in fp32 in the epilogue
 // (bounds the length of one tensor-core accumulation chain).
 //
-// CTA = 128 outputs x up to 64 channels (N = 128 columns), 6 warps:
-//   warp 0      TMA producer: per k-chunk of 32 floats  A tile [128 x 128 B] (raw fp32), B_hi and B_lo tiles, SWIZZLE_128B
-//   warps 2..5  split the raw A tile in place into hi (same bytes, masked) and write lo to a second tile at the same
-//               (swizzled) offsets - elementwise, so the swizzle never has to be decoded - then fence.proxy.async
-//   warp 1      one elected lane issues 12 tcgen05.mma per chunk (4 k-steps of 8 x 3 operand pairs), tcgen05.commit
-//               frees the stage; a final commit hands the accumulators to
+// CTA = 128 outputs x up to 64 channels (N = 128 columns), 7 warps:
+//   warp 0      TMA producer of A: per k-chunk of 32 floats one tile [128 x 128 B] of raw fp32, SWIZZLE_128B (ring of 4)
+//   warp 6      TMA producer of B: the B_hi and B_lo tiles of the chunk (ring of 3)
+//   warps 2..5  split the raw A tile in place into hi (same bytes, masked) and write lo to a tile of the lo ring (2)
+//               at the same (swizzled) offsets - elementwise, the swizzle never has to be decoded - fence.proxy.async
+//   warp 1      one elected lane issues 12 tcgen05.mma per chunk (4 k-steps of 8 x 3 operand pairs); tcgen05.commit
+//               frees the three ring slots; a final commit hands the accumulators to
 //   warps 2..5  epilogue: tcgen05.ld their 32 TMEM lanes, add the accumulators, derotate with the exact phase
 //               (double, like ddc_tile_kernel) and store out_iq (consecutive lanes = consecutive outputs of a channel).
-// 3 stages x 64 KB of shared memory, 512 TMEM columns, one CTA per SM.
+// 192 KB of shared memory, 512 TMEM columns, one CTA per SM.
 //
-// The first outputs of a block - whose windows reach back into the history buffer - stay on ddc_tile_kernel (the
-// tensor map addresses ONE buffer); so do odd decimations (row stride must be a multiple of 16 bytes) and buckets of
-// fewer than kDdcMmaMinChans channels.
+// The first outputs of a block - whose windows reach back into the history buffer (the tensor map addresses ONE
+// buffer) - are computed by ddc_head_kernel; odd decimations (row stride must be a multiple of 16 bytes) and buckets of
+// fewer than kDdcMmaMinChans channels stay on ddc_tile_kernel.
 #pragma once
 #include "common.cuh"
 #include "ddc_bank.cuh"
@@ -40,11 +41,18 @@
 namespace rcb {
 
 constexpr int kDdcMmaMinChans = 12;
-constexpr int kDdcMmaStages = 3;
-constexpr int kDdcMmaTile = 16384;                   // one [128 rows][32 floats] operand tile
-constexpr int kDdcMmaStageBytes = 4 * kDdcMmaTile;   // A (raw -> hi), A lo, B hi, B lo
-constexpr int kDdcMmaSmem = kDdcMmaStages * kDdcMmaStageBytes + 1024 /*alignment*/ + 256 /*barriers*/;
-constexpr int kDdcMmaThreads = 192;
+constexpr int kDdcMmaTile = 16384;  // one [128 rows][32 floats] operand tile
+// three rings of different depth: what bounds a chunk's turn-around differs per operand (A: TMA latency + split + MMA,
+// A lo: split + MMA, B: TMA latency + MMA) - one common 3-stage ring ran the tensor pipe at 25 %
+constexpr int kDdcMmaSA = 4;        // A tiles (raw fp32 -> hi in place)
+constexpr int kDdcMmaSL = 2;        // A lo tiles
+constexpr int kDdcMmaSB = 4;        // B hi + B lo tile pairs
+constexpr int kDdcMmaOffLo = kDdcMmaSA * kDdcMmaTile;
+constexpr int kDdcMmaOffB = kDdcMmaOffLo + kDdcMmaSL * kDdcMmaTile;
+constexpr int kDdcMmaOffBar = kDdcMmaOffB + kDdcMmaSB * 2 * kDdcMmaTile;
+constexpr int kDdcMmaOffPar = kDdcMmaOffBar + 256;  // per-channel epilogue parameters: phase0[64], cyc[64], out_iq[64]
+constexpr int kDdcMmaSmem = kDdcMmaOffPar + 64 * 24 + 1024 /*alignment*/;
+constexpr int kDdcMmaThreads = 224;
 
 struct DdcMmaGroupDev {
     int ch[64];   // indices into the DdcChanDev array, -1 = unused
@@ -57,6 +65,7 @@ struct DdcMmaGroupDev {
     int nout;
     int ldb;      // row length of B in floats (kchunks * 32)
     int nseg;     // main accumulator segments (1..3)
+    int kq;       // k-chunks per output step (2 * decim / 32, rounded): chunk order of the K loop, see DdcChunkOrder
 };
 
 // B operand of every group of a bucket, [hi | lo][group][128 columns][ldb] (K-major rows), from the channels'
@@ -124,6 +133,64 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
     return d;
 }
 
+// Order in which the K loop visits its chunks.  Row o+1 of A is row o moved 2*decim floats = kq chunks along K, so the
+// tile of chunk kc + kq is the tile of chunk kc shifted by one row: visiting kc, kc + kq, kc + 2 kq, ... back to back
+// makes 127 of the 128 rows of every load an L2 hit on what the previous load fetched.  In natural order the re-use
+// distance is kq chunks x 148 CTAs x 16 KB (95 MB at decim 640): L2 cannot hold it and A is read 2.3 times from HBM.
+struct DdcChunkOrder {
+    int kc, j, q, n;
+    __device__ __forceinline__ DdcChunkOrder(int q_, int n_) : kc(0), j(0), q(q_), n(n_) {}
+    __device__ __forceinline__ void next() {
+        kc += q;
+        if (kc >= n) kc = ++j;
+    }
+};
+
+// Outputs [0, o_head) of the channels of an MMA group: their windows start in the history buffer.  One CTA per
+// (output, channel), threads stride the taps, block reduce.  grid (o_head, 64, ngroups), block 128
+__global__ void __launch_bounds__(128) ddc_head_kernel(const DdcChanDev* __restrict__ chans,
+                                                       const DdcMmaGroupDev* __restrict__ groups,
+                                                       const float2* __restrict__ x, long long nsamp,
+                                                       const float2* __restrict__ hist, int hist_cap) {
+    const DdcMmaGroupDev& g = groups[blockIdx.z];
+    const int o = blockIdx.x;
+    if ((int)blockIdx.y >= g.nch || o >= g.o_head || o >= g.nout) return;
+    const int ci = g.ch[blockIdx.y];
+    if (ci < 0) return;
+    const DdcChanDev& ch = chans[ci];
+    const long long w0 = ch.s_first + (long long)o * ch.decim - (ch.ntaps - 1);
+    float2 acc = make_float2(0.f, 0.f);
+    for (int r = threadIdx.x; r < ch.ntaps; r += 128) {
+        const float2 t = __ldg(ch.ctaps_rev + r);
+        const long long idx = w0 + r;
+        const float2 xv = (idx < nsamp) ? ddc_x_at(x, hist, hist_cap, idx) : make_float2(0.f, 0.f);
+        acc.x = fmaf(t.x, xv.x, fmaf(-t.y, xv.y, acc.x));
+        acc.y = fmaf(t.x, xv.y, fmaf(t.y, xv.x, acc.y));
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, s);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, s);
+    }
+    __shared__ float2 part[4];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float2 a = make_float2((part[0].x + part[1].x) + (part[2].x + part[3].x),
+                                     (part[0].y + part[1].y) + (part[2].y + part[3].y));
+        double ph = ch.phase0 + ch.cyc * (double)o;
+        ph -= floor(ph);
+        double s, c;
+        sincospi(-2.0 * ph, &s, &c);
+        const float cf = (float)c, sf = (float)s;
+        ch.out_iq[o] = make_float2(fmaf(a.x, cf, -a.y * sf), fmaf(a.x, sf, a.y * cf));
+    }
+}
+
+// DBG (experiments build only, timing studies - results are garbage): bit 0 = no MMA issue, bit 1 = no hi/lo conversion,
+// bit 2 = hi*hi MMAs only, bit 3 = no A loads, bit 4 = no B loads;
+// bit 5 (results valid if the tensor core ignores the low 13 mantissa bits of a tf32 operand): the raw A tile is the hi operand
+template <int DBG = 0>
 __global__ void __launch_bounds__(kDdcMmaThreads, 1)
 ddc_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                const DdcChanDev* __restrict__ chans, const DdcMmaGroupDev* __restrict__ groups, int ngroups) {
@@ -131,34 +198,55 @@ ddc_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const uint32_t raw_addr = smem_addr_u32(ddc_mma_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
     unsigned char* base_p = ddc_mma_raw + (base - raw_addr);
-    const uint32_t bars = base + kDdcMmaStages * kDdcMmaStageBytes;
-    // barriers: full[3] @0, conv[3] @24, empty[3] @48, accum @72; tmem slot @96
-    auto bar_full = [&](int s) { return bars + 8u * s; };
-    auto bar_conv = [&](int s) { return bars + 24u + 8u * s; };
-    auto bar_empty = [&](int s) { return bars + 48u + 8u * s; };
-    const uint32_t bar_accum = bars + 72u;
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_p + kDdcMmaStages * kDdcMmaStageBytes + 96);
+    const uint32_t bars = base + kDdcMmaOffBar;
+    // barriers (8 bytes each): full_a[4] @0, empty_a[4] @32, full_b[4] @64, empty_b[4] @96, conv[2] @128, empty_lo[2] @144,
+    // accum @160; tmem slot @176
+    auto bar_full_a = [&](int s) { return bars + 8u * s; };
+    auto bar_empty_a = [&](int s) { return bars + 32u + 8u * s; };
+    auto bar_full_b = [&](int s) { return bars + 64u + 8u * s; };
+    auto bar_empty_b = [&](int s) { return bars + 96u + 8u * s; };
+    auto bar_conv = [&](int s) { return bars + 128u + 8u * s; };
+    auto bar_empty_lo = [&](int s) { return bars + 144u + 8u * s; };
+    const uint32_t bar_accum = bars + 160u;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_p + kDdcMmaOffBar + 176);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const DdcMmaGroupDev& g = groups[blockIdx.y];
     const int kchunks = g.kchunks;
+    const int kq = g.kq;
     const int tile = blockIdx.x;
 
     if (tid == 0) {
-        for (int s = 0; s < kDdcMmaStages; ++s) {
-            mbar_init_a(bar_full(s), 1);
+        for (int s = 0; s < kDdcMmaSA; ++s) {
+            mbar_init_a(bar_full_a(s), 1);
+            mbar_init_a(bar_empty_a(s), 1);
+        }
+        for (int s = 0; s < kDdcMmaSB; ++s) {
+            mbar_init_a(bar_full_b(s), 1);
+            mbar_init_a(bar_empty_b(s), 1);
+        }
+        for (int s = 0; s < kDdcMmaSL; ++s) {
             mbar_init_a(bar_conv(s), 4);
-            mbar_init_a(bar_empty(s), 1);
+            mbar_init_a(bar_empty_lo(s), 1);
         }
         mbar_init_a(bar_accum, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&tm_a);
         prefetch_tmap(&tm_b);
     }
+    double* s_ph0 = reinterpret_cast<double*>(base_p + kDdcMmaOffPar);
+    double* s_cyc = s_ph0 + 64;
+    float2** s_out = reinterpret_cast<float2**>(s_cyc + 64);
+    if (tid >= 64 && tid < 128) {
+        // the epilogue's per-channel constants: one global read per channel per CTA instead of one per accumulator row
+        const int cslot = tid - 64;
+        const int ci = (cslot < g.nch) ? g.ch[cslot] : -1;
+        s_ph0[cslot] = (ci >= 0) ? chans[ci].phase0 : 0.0;
+        s_cyc[cslot] = (ci >= 0) ? chans[ci].cyc : 0.0;
+        s_out[cslot] = (ci >= 0) ? chans[ci].out_iq : nullptr;
+    }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
-                         bars + 96u)
-                     : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(bars + 176u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -168,15 +256,32 @@ ddc_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kc = 0; kc < kchunks; ++kc) {
-                const int s = kc % kDdcMmaStages;
-                const uint32_t ph = (uint32_t)(kc / kDdcMmaStages) & 1u;
-                mbar_wait_a(bar_empty(s), ph ^ 1u);
-                const uint32_t st = base + (uint32_t)s * kDdcMmaStageBytes;
-                mbar_expect_tx_a(bar_full(s), 3u * kDdcMmaTile);
-                tma_load_2d(st, &tm_a, kc * 32, tile * 128, bar_full(s));
-                tma_load_2d(st + 2u * kDdcMmaTile, &tm_b, kc * 32, (int)blockIdx.y * 128, bar_full(s));
-                tma_load_2d(st + 3u * kDdcMmaTile, &tm_b, kc * 32, (ngroups + (int)blockIdx.y) * 128, bar_full(s));
+            DdcChunkOrder ord(kq, kchunks);
+            for (int it = 0; it < kchunks; ++it, ord.next()) {
+                const int s = it % kDdcMmaSA;
+                mbar_wait_a(bar_empty_a(s), ((uint32_t)(it / kDdcMmaSA) & 1u) ^ 1u);
+                if (DBG & 8) {
+                    mbar_arrive_a(bar_full_a(s));
+                    continue;
+                }
+                mbar_expect_tx_a(bar_full_a(s), (uint32_t)kDdcMmaTile);
+                tma_load_2d(base + (uint32_t)s * kDdcMmaTile, &tm_a, ord.kc * 32, tile * 128, bar_full_a(s));
+            }
+        }
+    } else if (warp == 6) {
+        if (lane == 0) {
+            DdcChunkOrder ord(kq, kchunks);
+            for (int it = 0; it < kchunks; ++it, ord.next()) {
+                const int s = it % kDdcMmaSB, kc = ord.kc;
+                mbar_wait_a(bar_empty_b(s), ((uint32_t)(it / kDdcMmaSB) & 1u) ^ 1u);
+                const uint32_t st = base + (uint32_t)kDdcMmaOffB + (uint32_t)s * 2u * kDdcMmaTile;
+                if (DBG & 16) {
+                    mbar_arrive_a(bar_full_b(s));
+                    continue;
+                }
+                mbar_expect_tx_a(bar_full_b(s), 2u * kDdcMmaTile);
+                tma_load_2d(st, &tm_b, kc * 32, (int)blockIdx.y * 128, bar_full_b(s));
+                tma_load_2d(st + (uint32_t)kDdcMmaTile, &tm_b, kc * 32, (ngroups + (int)blockIdx.y) * 128, bar_full_b(s));
             }
         }
     } else if (warp == 1) {
@@ -187,29 +292,54 @@ ddc_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         int seg = 0, seg_end = (kchunks + nseg - 1) / nseg;
         bool seg_first = true;
         for (int kc = 0; kc < kchunks; ++kc) {
-            const int s = kc % kDdcMmaStages;
-            const uint32_t ph = (uint32_t)(kc / kDdcMmaStages) & 1u;
+            const int sa = kc % kDdcMmaSA, sl = kc % kDdcMmaSL, sb = kc % kDdcMmaSB;
             if (kc == seg_end) {
                 ++seg;
                 seg_end = ((seg + 1) * kchunks + nseg - 1) / nseg;
                 seg_first = true;
             }
-            mbar_wait_a(bar_full(s), ph);
-            mbar_wait_a(bar_conv(s), ph);
+            if (DBG & 32)
+                mbar_wait_a(bar_full_a(sa), (uint32_t)(kc / kDdcMmaSA) & 1u);  // the raw tile is the hi operand
+            else
+                mbar_wait_a(bar_conv(sl), (uint32_t)(kc / kDdcMmaSL) & 1u);   // A hi (in place) and A lo of this chunk
+            mbar_wait_a(bar_full_b(sb), (uint32_t)(kc / kDdcMmaSB) & 1u);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t st = base + (uint32_t)s * kDdcMmaStageBytes;
-                const uint64_t a_hi = tc_smem_desc(st), a_lo = tc_smem_desc(st + kDdcMmaTile);
-                const uint64_t b_hi = tc_smem_desc(st + 2u * kDdcMmaTile), b_lo = tc_smem_desc(st + 3u * kDdcMmaTile);
+                const uint32_t sb_addr = base + (uint32_t)kDdcMmaOffB + (uint32_t)sb * 2u * kDdcMmaTile;
+                const uint64_t a_hi = tc_smem_desc(base + (uint32_t)sa * kDdcMmaTile);
+                const uint64_t a_lo = tc_smem_desc(base + (uint32_t)kDdcMmaOffLo + (uint32_t)sl * kDdcMmaTile);
+                const uint64_t b_hi = tc_smem_desc(sb_addr), b_lo = tc_smem_desc(sb_addr + (uint32_t)kDdcMmaTile);
                 const uint32_t t_main = tmem + 128u * (uint32_t)seg;
+                if (!(DBG & 1) && !(DBG & 32)) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint64_t adv = (uint64_t)(2 * j);  // 8 floats = 32 bytes along K inside the 128-byte swizzle row
-                    tc_mma_tf32(t_main, a_hi + adv, b_hi + adv, idesc, (seg_first && j == 0) ? 0u : 1u);
-                    tc_mma_tf32(t_cross, a_hi + adv, b_lo + adv, idesc, (kc == 0 && j == 0) ? 0u : 1u);
-                    tc_mma_tf32(t_cross, a_lo + adv, b_hi + adv, idesc, 1u);
+                    for (int j = 0; j < 4; ++j) {
+                        const uint64_t adv = (uint64_t)(2 * j);  // 8 floats = 32 bytes along K inside the 128-byte swizzle row
+                        tc_mma_tf32(t_main, a_hi + adv, b_hi + adv, idesc, (seg_first && j == 0) ? 0u : 1u);
+                        if (!(DBG & 4)) {
+                            tc_mma_tf32(t_cross, a_hi + adv, b_lo + adv, idesc, (kc == 0 && j == 0) ? 0u : 1u);
+                            tc_mma_tf32(t_cross, a_lo + adv, b_hi + adv, idesc, 1u);
+                        }
+                    }
                 }
-                tc_commit(bar_empty(s));
+                if (DBG & 32) {
+                    // the 8 MMAs that need only what TMA delivered go first; the lo tile has until they are issued
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint64_t adv = (uint64_t)(2 * j);
+                        tc_mma_tf32(t_main, a_hi + adv, b_hi + adv, idesc, (seg_first && j == 0) ? 0u : 1u);
+                        tc_mma_tf32(t_cross, a_hi + adv, b_lo + adv, idesc, (kc == 0 && j == 0) ? 0u : 1u);
+                    }
+                    mbar_wait_a(bar_conv(sl), (uint32_t)(kc / kDdcMmaSL) & 1u);
+                    tc_fence_after();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint64_t adv = (uint64_t)(2 * j);
+                        tc_mma_tf32(t_cross, a_lo + adv, b_hi + adv, idesc, 1u);
+                    }
+                }
+                tc_commit(bar_empty_a(sa));
+                tc_commit(bar_empty_lo(sl));
+                tc_commit(bar_empty_b(sb));
             }
             seg_first = false;
             __syncwarp();
@@ -219,13 +349,13 @@ ddc_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     } else {
         const int ct = tid - 64;  // 0..127
         for (int kc = 0; kc < kchunks; ++kc) {
-            const int s = kc % kDdcMmaStages;
-            const uint32_t ph = (uint32_t)(kc / kDdcMmaStages) & 1u;
-            mbar_wait_a(bar_full(s), ph);
-            float4* a = reinterpret_cast<float4*>(base_p + (size_t)s * kDdcMmaStageBytes);
-            float4* al = reinterpret_cast<float4*>(base_p + (size_t)s * kDdcMmaStageBytes + kDdcMmaTile);
+            const int sa = kc % kDdcMmaSA, sl = kc % kDdcMmaSL;
+            mbar_wait_a(bar_full_a(sa), (uint32_t)(kc / kDdcMmaSA) & 1u);
+            mbar_wait_a(bar_empty_lo(sl), ((uint32_t)(kc / kDdcMmaSL) & 1u) ^ 1u);
+            float4* a = reinterpret_cast<float4*>(base_p + (size_t)sa * kDdcMmaTile);
+            float4* al = reinterpret_cast<float4*>(base_p + kDdcMmaOffLo + (size_t)sl * kDdcMmaTile);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < ((DBG & 2) ? 0 : 8); ++i) {
                 const int idx = ct + 128 * i;
                 const float4 v = a[idx];
                 float4 hi, lo;
@@ -237,12 +367,12 @@ ddc_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 lo.y = v.y - hi.y;
                 lo.z = v.z - hi.z;
                 lo.w = v.w - hi.w;
-                a[idx] = hi;
+                if (!(DBG & 32)) a[idx] = hi;
                 al[idx] = lo;
             }
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive_a(bar_conv(s));
+            if (lane == 0) mbar_arrive_a(bar_conv(sl));
         }
         // ---- epilogue ----
         mbar_wait_a(bar_accum, 0u);
@@ -260,19 +390,22 @@ ddc_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 #pragma unroll
                 for (int i = 0; i < 16; ++i) acc[i] += t[i];
             }
+            if (o < g.nout) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int cslot = (c0 >> 1) + i;
-                const int ci = (cslot < g.nch) ? g.ch[cslot] : -1;
-                if (ci >= 0 && o < g.nout) {
-                    const DdcChanDev& ch = chans[ci];
-                    double phs = ch.phase0 + ch.cyc * (double)o;
-                    phs -= floor(phs);
-                    double sn, cs;
-                    sincospi(-2.0 * phs, &sn, &cs);
-                    const float cf = (float)cs, sf = (float)sn;
-                    const float ax = acc[2 * i], ay = acc[2 * i + 1];
-                    ch.out_iq[o] = make_float2(fmaf(ax, cf, -ay * sf), fmaf(ax, sf, ay * cf));
+                for (int i = 0; i < 8; ++i) {
+                    const int cslot = (c0 >> 1) + i;
+                    float2* op = s_out[cslot];
+                    if (op) {
+                        // phase bookkeeping in double (cyc * o reaches 1e4 cycles), the rotation itself in float: the
+                        // reduced phase |ph| <= 0.5 rounds to float with 3e-8 cycles = 2e-7 rad
+                        double phs = fma(s_cyc[cslot], (double)o, s_ph0[cslot]);
+                        phs -= floor(phs);
+                        if (phs >= 0.5) phs -= 1.0;
+                        float sf, cf;
+                        sincospif(-2.0f * (float)phs, &sf, &cf);
+                        const float ax = acc[2 * i], ay = acc[2 * i + 1];
+                        op[o] = make_float2(fmaf(ax, cf, -ay * sf), fmaf(ax, sf, ay * cf));
+                    }
                 }
             }
         }

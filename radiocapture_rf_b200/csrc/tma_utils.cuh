@@ -26,7 +26,8 @@ inline rcb_tmap_encode_fn tmap_encoder() {
 // float32 tensor map of rank 2..4; dims / box in elements, strides (dims 1..rank-1) in bytes.  false when the driver
 // refuses the shape (misaligned base / stride, no encoder) - callers then use their non-TMA kernel.
 inline bool tmap_encode_f32(CUtensorMap* tm, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_b,
-                            const uint32_t* box, CUtensorMapSwizzle swz) {
+                            const uint32_t* box, CUtensorMapSwizzle swz,
+                            CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B) {
     rcb_tmap_encode_fn enc = tmap_encoder();
     if (!enc) return false;
     if (reinterpret_cast<uintptr_t>(base) & 15) return false;
@@ -43,7 +44,7 @@ inline bool tmap_encode_f32(CUtensorMap* tm, int rank, const void* base, const u
         }
     }
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, swz, promo,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -78,6 +79,10 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// pull a 2-D box into L2 only (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
