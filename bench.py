@@ -458,8 +458,8 @@ class DdcCtx(object):
         self.n = 1 << (log2n or cfg["log2n"])
         self.e = Engine(device)
         self.bank = DdcBank(self.e)
-        if not DDC_TENSOR_CORES:
-            self.bank.set_tensor_cores(False)
+        if DDC_TENSOR_CORES != 1:
+            self.bank.set_tensor_cores(DDC_TENSOR_CORES)
         fs, rate = cfg["fs"], cfg["rate"]
         decim = firdes.channel_decimation(fs, rate)
         taps = firdes.low_pass_2(1.0, fs, rate / 2, rate / 2, 20.0, firdes.WIN_HAMMING)
@@ -477,7 +477,8 @@ class DdcCtx(object):
         self.e.close()
 
 
-DDC_TENSOR_CORES = True  # --no-tensor-cores: keep every DDC bucket on the CUDA-core ddc_tile_kernel
+DDC_TENSOR_CORES = 1  # rcb_ddc_set_tensor_cores mode: 0 (--no-tensor-cores) CUDA-core ddc_tile_kernel for every bucket,
+                      # 1 ddc_mma2_kernel (default), 2 (--ddc-mode 2) ddc_mma_kernel
 USE_MULTI = False  # --multi: one rcb_pfb_process_multi call per step instead of one rcb_pfb_process call per stream
                    # (measured on cfg5: 202 vs 218 Gsps - the per-stream launches on their own CUDA streams overlap better)
 
@@ -623,8 +624,8 @@ def run_e2e_ddc(device, wl, steps, dist, local, log2n=24):
     chk = 0.0
     for _ in range(steps):
         ctx.bank.process(hin)
-        ys = ctx.bank.pull_all(OUT_IQ)     # one transfer per output kind for all channels
-        fs = ctx.bank.pull_all(OUT_FM)
+        ys = ctx.bank.pull_all(OUT_IQ, copy=False)     # one transfer per output kind for all channels, pinned staging
+        fs = ctx.bank.pull_all(OUT_FM, copy=False)
         d2h = sum(v.nbytes for v in ys.values()) + sum(v.nbytes for v in fs.values())
         chk += float(sum(v[-1] for v in fs.values() if len(v)))
     dt = time.perf_counter() - t0
@@ -849,13 +850,14 @@ def main():
                     help="device output layout: channel-major in blocks of this many frames (0 = plain [N][T])")
     ap.add_argument("--multi", action="store_true", help="multi-stream workloads: ONE rcb_pfb_process_multi launch per step instead of one call per stream")
     ap.add_argument("--no-tensor-cores", action="store_true", help="DDC workloads: CUDA-core kernel for every bucket")
+    ap.add_argument("--ddc-mode", type=int, default=1, choices=[1, 2], help="DDC tensor-core kernel generation")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ceiling", action="store_true", help="skip the bare-copy ceiling measurement of the e2e path")
     ap.add_argument("--no-also", action="store_true")
     args = ap.parse_args()
     global USE_MULTI, DDC_TENSOR_CORES
     USE_MULTI = bool(args.multi)
-    DDC_TENSOR_CORES = not args.no_tensor_cores
+    DDC_TENSOR_CORES = 0 if args.no_tensor_cores else args.ddc_mode
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference(args)

@@ -132,12 +132,14 @@ int rcb_ddc_close(rcb_t* h, int chan_id);
 int rcb_ddc_process(rcb_t* h, const void* iq, size_t nsamples, int in_mem);
 int rcb_ddc_pull(rcb_t* h, int chan_id, int which, void* dst, size_t cap_items, int dst_mem,
                  size_t* nitems);
-/* Buckets of >= 12 channels that share (decim, ntaps) with an even decim run on the tensor cores (ddc_mma_kernel:
- * tcgen05 kind::tf32, every operand split hi + lo -> 3 MMAs, fp32 accumulate in TMEM; same 1e-5 parity bar as the CUDA-core
- * kernel).  enable = 0 forces the CUDA-core ddc_tile_kernel for every bucket (what gr::filter::freq_xlating_fir_filter_ccc
- * instances do one by one, rc_frontend/channel.py:35).  nseg in 1..3 = K segments of the main accumulation that get their own
- * TMEM accumulator (0 = keep; default 3). */
-int rcb_ddc_set_tensor_cores(rcb_t* h, int enable, int nseg);
+/* Buckets of >= 12 channels that share (decim, ntaps) with an even decim run on the tensor cores (tcgen05 kind::tf32,
+ * every operand split hi + lo -> 3 MMAs per k-step, fp32 accumulators in TMEM; same 1e-5 parity bar as the CUDA-core
+ * kernel).  mode 0: CUDA-core ddc_tile_kernel for every bucket (what gr::filter::freq_xlating_fir_filter_ccc instances
+ * do one by one, rc_frontend/channel.py:35).  mode 1 (default): ddc_mma2_kernel, A operand in tensor memory; seg =
+ * k-chunks (32 floats of the window each) per accumulation segment before the accumulator is drained to registers
+ * (0 = keep; default 16).  mode 2: ddc_mma_kernel, A operand in shared memory; seg = 1..3 TMEM accumulators the main
+ * accumulation is cut into (0 = keep; default 3). */
+int rcb_ddc_set_tensor_cores(rcb_t* h, int mode, int seg);
 /* ddc_mma_kernel launches on this handle so far (which path a block took is otherwise invisible to the caller) */
 int rcb_ddc_tensor_core_launches(rcb_t* h, uint64_t* launches);
 

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "ddc_bank.cuh"
 #include "ddc_mma.cuh"
+#include "ddc_mma2.cuh"
 #include "demod.cuh"
 #include "fft_logpow.cuh"
 #include "fft_scan.cuh"
@@ -159,13 +160,17 @@ struct rcb_ctx {
         bool in_used[2] = {false, false};
         // tensor-core path (ddc_mma_kernel): group descriptors (pinned ring like the two above) and the packed B operand
         bool use_mma = true;      // rcb_ddc_set_tensor_cores
-        int mma_nseg = 3;
+        int mma_gen = 2;          // 2: ddc_mma2_kernel (A operand in TMEM), 1: ddc_mma_kernel (A operand in shared memory)
+        int mma_nseg = 3;         // generation 1: main accumulators
+        int mma_seg_len = 16;     // generation 2: k-chunks per accumulation segment
         DdcMmaGroupDev* d_mgroups_ring = nullptr;
         DdcMmaGroupDev* h_mgroups_ring = nullptr;  // pinned
         size_t mgroups_cap = 0;
         float* d_mma_b = nullptr;
         size_t mma_b_cap = 0;     // floats
         uint64_t mma_launches = 0;
+        cudaStream_t s_aux = nullptr;      // ddc_head_kernel runs beside ddc_mma*_kernel (fork / join events)
+        cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
         std::vector<long long> mma_b_sig;  // what d_mma_b holds (bucket shapes, channel ids, tap versions): unchanged ->
                                            // the pack kernel is skipped
     } ddc;
@@ -896,6 +901,9 @@ extern "C" int rcb_close(rcb_t* h) {
     cudaFree(h->ddc.d_mgroups_ring);
     if (h->ddc.h_mgroups_ring) cudaFreeHost(h->ddc.h_mgroups_ring);
     cudaFree(h->ddc.d_mma_b);
+    if (h->ddc.s_aux) cudaStreamDestroy(h->ddc.s_aux);
+    if (h->ddc.ev_fork) cudaEventDestroy(h->ddc.ev_fork);
+    if (h->ddc.ev_join) cudaEventDestroy(h->ddc.ev_join);
     for (int i = 0; i < 4; ++i)
         if (h->ddc.ev_slot[i]) cudaEventDestroy(h->ddc.ev_slot[i]);
     for (int i = 0; i < 2; ++i) {
@@ -1664,12 +1672,15 @@ extern "C" int rcb_ddc_set_taps(rcb_t* h, int chan_id, const float* taps, int nt
     return ddc_upload_taps(h, c);
 }
 
-extern "C" int rcb_ddc_set_tensor_cores(rcb_t* h, int enable, int nseg) {
-    if (!h || nseg < 0 || nseg > 3) return RCB_EINVAL;
+extern "C" int rcb_ddc_set_tensor_cores(rcb_t* h, int mode, int seg) {
+    if (!h || mode < 0 || mode > 2 || seg < 0) return RCB_EINVAL;
+    if (mode == 2 && seg > 3) return RCB_EINVAL;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
-    h->ddc.use_mma = (enable != 0);
-    if (nseg) h->ddc.mma_nseg = nseg;
+    h->ddc.use_mma = (mode != 0);
+    if (mode) h->ddc.mma_gen = (mode == 2) ? 1 : 2;
+    if (mode == 1 && seg) h->ddc.mma_seg_len = seg;
+    if (mode == 2 && seg) h->ddc.mma_nseg = seg;
     return RCB_OK;
 }
 
@@ -1900,6 +1911,7 @@ int ddc_process_chunk(rcb_t* h, const float2* d_x, size_t nsamples) {
                         g.nout = (int)b.first[3];
                         g.ldb = pl.kchunks * 32;
                         g.nseg = std::max(1, std::min(std::min(3, d.mma_nseg), pl.kchunks));
+                        g.seg_len = std::max(2, d.mma_seg_len);
                         g.kq = std::max(1, (2 * g.decim + 16) / 32);
 #ifdef RCB_EXPERIMENTS
                         if (const char* e = getenv("RCB_DDC_KQ")) g.kq = std::max(1, atoi(e));
@@ -1910,6 +1922,10 @@ int ddc_process_chunk(rcb_t* h, const float2* d_x, size_t nsamples) {
                 static bool mma_attr_dev[64] = {};
                 if (!mma_attr_dev[h->device & 63]) {
                     CK(cudaFuncSetAttribute(ddc_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDdcMmaSmem));
+                    CK(cudaFuncSetAttribute(ddc_mma2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kM2Smem));
+#ifdef RCB_EXPERIMENTS
+                    CK(cudaFuncSetAttribute(ddc_mma2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kM2Smem));
+#endif
 #ifdef RCB_EXPERIMENTS
                     CK(cudaFuncSetAttribute(ddc_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDdcMmaSmem));
                     CK(cudaFuncSetAttribute(ddc_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDdcMmaSmem));
@@ -1921,6 +1937,31 @@ int ddc_process_chunk(rcb_t* h, const float2* d_x, size_t nsamples) {
 #endif
                     mma_attr_dev[h->device & 63] = true;
                 }
+                if (!d.s_aux) {
+                    CK(cudaStreamCreateWithFlags(&d.s_aux, cudaStreamNonBlocking));
+                    CK(cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming));
+                    CK(cudaEventCreateWithFlags(&d.ev_join, cudaEventDisableTiming));
+                }
+                // the few outputs per channel whose windows start in the history buffer: small CTAs that fit beside the
+                // one-per-SM MMA CTAs, on their own stream
+                CK(cudaEventRecord(d.ev_fork, h->stream));
+                CK(cudaStreamWaitEvent(d.s_aux, d.ev_fork, 0));
+                bool any_head = false;
+                mg = 0;
+                for (auto& b : buckets) {
+                    auto mp = mma_plans.find(b.first);
+                    if (mp == mma_plans.end()) continue;
+                    const MmaPlan& pl = mp->second;
+                    if (pl.o_head > 0) {
+                        dim3 hg((unsigned)pl.o_head, 64, (unsigned)pl.ng);
+                        ddc_head_kernel<<<hg, 128, 0, d.s_aux>>>(d.d_chans, d_mgroups + mg, d_x, (long long)nsamples,
+                                                                 d.d_hist[d.hist_cur], kDdcHistCap);
+                        CKL(h);
+                        any_head = true;
+                    }
+                    mg += pl.ng;
+                }
+                if (any_head) CK(cudaEventRecord(d.ev_join, d.s_aux));
                 mg = 0;
                 for (auto& b : buckets) {
                     auto mp = mma_plans.find(b.first);
@@ -1952,18 +1993,19 @@ int ddc_process_chunk(rcb_t* h, const float2* d_x, size_t nsamples) {
                         ddc_mma_pack_kernel<<<pg, 256, 0, h->stream>>>(d.d_chans, d_mgroups + mg, pl.ng, bptr);
                         CKL(h);
                     }
-                    if (pl.o_head > 0) {
-                        dim3 hg((unsigned)pl.o_head, 64, (unsigned)pl.ng);
-                        ddc_head_kernel<<<hg, 128, 0, h->stream>>>(d.d_chans, d_mgroups + mg, d_x, (long long)nsamples,
-                                                                  d.d_hist[d.hist_cur], kDdcHistCap);
-                        CKL(h);
-                    }
+
                     dim3 grid((unsigned)((nrows + 127) / 128), (unsigned)pl.ng);
                     int dbg = 0;
 #ifdef RCB_EXPERIMENTS
                     if (const char* e = getenv("RCB_DDC_DBG")) dbg = atoi(e);
 #endif
-                    if (dbg == 0)
+                    if (d.mma_gen == 2 && dbg == 0)
+                        ddc_mma2_kernel<false><<<grid, kM2Threads, kM2Smem, h->stream>>>(tm_a, tm_b, d.d_chans, d_mgroups + mg, pl.ng);
+#ifdef RCB_EXPERIMENTS
+                    else if (d.mma_gen == 2 && dbg == 100)
+                        ddc_mma2_kernel<true><<<grid, kM2Threads, kM2Smem, h->stream>>>(tm_a, tm_b, d.d_chans, d_mgroups + mg, pl.ng);
+#endif
+                    else if (dbg == 0)
                         ddc_mma_kernel<0><<<grid, kDdcMmaThreads, kDdcMmaSmem, h->stream>>>(tm_a, tm_b, d.d_chans, d_mgroups + mg, pl.ng);
 #ifdef RCB_EXPERIMENTS
                     else if (dbg == 1)
@@ -1985,6 +2027,7 @@ int ddc_process_chunk(rcb_t* h, const float2* d_x, size_t nsamples) {
                     d.mma_launches++;
                     mg += pl.ng;
                 }
+                if (any_head) CK(cudaStreamWaitEvent(h->stream, d.ev_join, 0));
             }
             if (ngroups) {
                 CK(cudaMemcpyAsync(d.d_groups, d.h_groups, ngroups * sizeof(DdcGroupDev), cudaMemcpyHostToDevice, h->stream));

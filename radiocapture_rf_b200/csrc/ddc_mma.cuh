@@ -65,6 +65,7 @@ struct DdcMmaGroupDev {
     int nout;
     int ldb;      // row length of B in floats (kchunks * 32)
     int nseg;     // main accumulator segments (1..3)
+    int seg_len;  // ddc_mma2_kernel: k-chunks per accumulation segment (the finished accumulator is drained to registers)
     int kq;       // k-chunks per output step (2 * decim / 32, rounded): chunk order of the K loop, see DdcChunkOrder
 };
 

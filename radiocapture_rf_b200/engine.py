@@ -301,11 +301,11 @@ class DdcBank(object):
     def close(self, chan):
         check(self.e.lib.rcb_ddc_close(self.e.h, int(chan)), "rcb_ddc_close", self.e.h)
 
-    def set_tensor_cores(self, enable=True, nseg=0):
-        """Buckets of >= 12 channels sharing (decim, ntaps) run on tcgen05 (3 x tf32 split) by default; False keeps
-        every bucket on the CUDA-core kernel.  nseg 1..3: K segments with their own TMEM accumulator (0 = keep)."""
-        check(self.e.lib.rcb_ddc_set_tensor_cores(self.e.h, 1 if enable else 0, int(nseg)), "rcb_ddc_set_tensor_cores",
-              self.e.h)
+    def set_tensor_cores(self, mode=1, seg=0):
+        """Buckets of >= 12 channels sharing (decim, ntaps) run on tcgen05 (3 x tf32 split).  mode 0 / False: CUDA-core
+        kernel for every bucket; 1 / True (default): A operand in tensor memory, ``seg`` = k-chunks per accumulation
+        segment; 2: A operand in shared memory, ``seg`` = 1..3 accumulators.  seg 0 keeps the current setting."""
+        check(self.e.lib.rcb_ddc_set_tensor_cores(self.e.h, int(mode), int(seg)), "rcb_ddc_set_tensor_cores", self.e.h)
 
     def tensor_core_launches(self):
         n = C.c_uint64(0)
@@ -336,9 +336,10 @@ class DdcBank(object):
               "rcb_ddc_pull", self.e.h)
         return n.value
 
-    def pull_all(self, which=OUT_IQ, max_items=None):
-        """Every open channel's outputs of the last process() call in ONE device-to-host transfer.
-        Returns {chan_id: array}."""
+    def pull_all(self, which=OUT_IQ, max_items=None, copy=True):
+        """Every open channel's outputs of the last process() call in ONE device-to-host transfer into a pinned
+        staging block kept by this object.  Returns {chan_id: array}; with copy=False the arrays are views of the
+        staging block, valid until the next pull_all of the same kind (what a sink that serialises at once needs)."""
         n = C.c_size_t(0)
         st = self.e.lib.rcb_ddc_pull_all(self.e.h, int(which), None, 0, MEM_HOST, None, None, 0, C.byref(n))
         if st not in (0, _lib.RCB_ERANGE):
@@ -351,17 +352,23 @@ class DdcBank(object):
         dt = np.complex64 if which == OUT_IQ else np.float32
         ids = (C.c_int * m)()
         counts = (C.c_size_t * m)()
+        pins = self.__dict__.setdefault("_pins", {})
         while True:
-            out = np.empty((m, max_items), dtype=dt)
-            st = self.e.lib.rcb_ddc_pull_all(self.e.h, int(which), out.ctypes.data, max_items, MEM_HOST, ids, counts, m,
+            out = pins.get(which)
+            if out is None or out.shape[0] < m or out.shape[1] < max_items:
+                out = self.e.pinned((m, max_items), dt)
+                pins[which] = out
+            st = self.e.lib.rcb_ddc_pull_all(self.e.h, int(which), out.ctypes.data, out.shape[1], MEM_HOST, ids, counts, m,
                                              C.byref(n))
-            if st == _lib.RCB_ERANGE and max(counts) > max_items:   # rows longer than guessed: counts are valid, retry
+            if st == _lib.RCB_ERANGE and max(counts) > out.shape[1]:   # rows longer than guessed: counts are valid, retry
                 max_items = int(max(counts))
                 continue
             check(st, "rcb_ddc_pull_all", self.e.h)
             break
         self._last_max = max(int(max(counts)), 1)
-        return {int(ids[r]): out[r, :counts[r]].copy() for r in range(m)}
+        if copy:
+            return {int(ids[r]): out[r, :counts[r]].copy() for r in range(m)}
+        return {int(ids[r]): out[r, :counts[r]] for r in range(m)}
 
     def pull(self, chan, which=OUT_IQ):
         n = C.c_size_t(0)

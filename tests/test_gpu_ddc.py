@@ -314,9 +314,9 @@ def test_two_engines_on_one_device_keep_their_shared_memory_opt_in(built_lib):
         b.close()
 
 
-def _open_bank(engine, decim, taps, offs, fs, tensor_cores, nseg=0):
+def _open_bank(engine, decim, taps, offs, fs, tensor_cores, seg=0):
     bank = DdcBank(engine)
-    bank.set_tensor_cores(tensor_cores, nseg)
+    bank.set_tensor_cores(tensor_cores, seg)
     ids = [bank.open(decim, taps, f, fs, OUT_IQ | OUT_FM, 5.0) for f in offs]
     return bank, ids
 
@@ -332,8 +332,8 @@ def _second_block(bank, ids, x, cut):
             bank.tensor_core_launches() - l0)
 
 
-@pytest.mark.parametrize("nseg", [1, 3])
-def test_tensor_core_bank_matches_oracle_and_cuda_core_kernel(engine, nseg):
+@pytest.mark.parametrize("mode,seg", [(1, 0), (1, 4), (1, 1000), (2, 3), (2, 1)])
+def test_tensor_core_bank_matches_oracle_and_cuda_core_kernel(engine, mode, seg):
     """24 channels sharing (D 96, 349 taps): the bucket runs on ddc_mma_kernel (tcgen05 kind::tf32, hi/lo split), the
     block's first outputs on the CUDA-core kernel.  Channels on a carrier meet the 1e-5 bar against the float64 oracle;
     EMPTY channels (output 40-60 dB below the input: any fp32 summation order differs from float64 at the 1e-5 level
@@ -345,7 +345,7 @@ def test_tensor_core_bank_matches_oracle_and_cuda_core_kernel(engine, nseg):
     decim, taps = fd.channel_taps(fs, 12500)
     rng = np.random.default_rng(3)
     offs = list(carriers) + list(rng.uniform(-0.45 * fs, 0.45 * fs, 16))
-    bank, ids = _open_bank(engine, decim, taps, offs, fs, True, nseg)
+    bank, ids = _open_bank(engine, decim, taps, offs, fs, mode, seg)
     ys, fms, first, nl = _second_block(bank, ids, x, cut)
     assert nl == 1
     e2 = Engine(0)
@@ -372,8 +372,8 @@ def test_tensor_core_bank_matches_oracle_and_cuda_core_kernel(engine, nseg):
             assert e_mma <= max(3e-6, 3.0 * e_cc), (f, e_mma, e_cc)
     finally:
         e2.close()
-    print("\ntensor-core bank, nseg %d:  offset Hz | level | rel_l2 vs oracle | err/scale mma | err/scale cuda-core" % nseg)
-    for r in rows:
+    print("\ntensor-core bank, mode %d seg %d:  offset Hz | level | rel_l2 vs oracle | err/scale mma | err/scale cuda-core" % (mode, seg))
+    for r in rows[:10]:
         print("  %10.0f  %.2e  %.2e  %.2e  %.2e" % r)
 
 
@@ -419,7 +419,8 @@ def test_tensor_core_bank_ragged_blocks_and_two_column_groups(engine):
         e2.close()
 
 
-def test_tensor_core_bank_wideband_2327_taps(engine):
+@pytest.mark.parametrize("mode", [1, 2])
+def test_tensor_core_bank_wideband_2327_taps(engine, mode):
     """The many-channel bench shape: fs 16 Msps, D 640, 2327 taps (147 k-chunks of the MMA pipeline), 64 channels."""
     fs, rate = 16.0e6, 12500
     decim, taps = fd.channel_taps(fs, rate)
@@ -429,7 +430,7 @@ def test_tensor_core_bank_wideband_2327_taps(engine):
     offs = list(rng.uniform(-0.45 * fs, 0.45 * fs, 64))
     cut = 1 << 16
     x = synth.wideband(n + cut, fs, [offs[k] for k in (0, 1, 31, 62, 63)], seed=13)
-    bank, ids = _open_bank(engine, decim, taps, offs, fs, True)
+    bank, ids = _open_bank(engine, decim, taps, offs, fs, mode)
     ys, _, first, nl = _second_block(bank, ids, x, cut)
     assert nl == 1
     for k in [0, 1, 31, 62, 63]:
@@ -438,5 +439,5 @@ def test_tensor_core_bank_wideband_2327_taps(engine):
         m = min(len(y), len(ref))
         assert m >= n // decim - 1
         err = gb.rel_l2(y[:m], ref[:m])
-        print("2327 taps, channel %d: rel_l2 %.2e" % (k, err))
+        print("2327 taps, mode %d, channel %d: rel_l2 %.2e" % (mode, k, err))
         assert err <= TOL, offs[k]
