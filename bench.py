@@ -64,6 +64,18 @@ WORKLOADS = {
 }
 
 
+def load_tensor_peak():
+    """Dense tf32 ceiling for the DDC contraction: half the measured bf16 rate (MEASURED_PEAKS.json), else the
+    profiling recipe's nominal 1.1 PFLOP/s."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["bf16_tflops"]) / 2.0, "measured bf16_tflops / 2 (MEASURED_PEAKS.json; tf32 runs at half the bf16 rate)"
+        except Exception:
+            pass
+    return 1100.0, "fallback (B200_PROFILING.md 1.1 PFLOP/s dense tf32)"
+
+
 def load_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -81,6 +93,8 @@ def kernel_name(wl):
     if cfg.get("kind") == "fft":
         return "fft_cols_tma_kernel+fft_rows_kernel"
     if cfg.get("kind") == "ddc":
+        if cfg["nchan"] >= 12 and DDC_TENSOR_CORES:
+            return "ddc_mma2_kernel" if DDC_TENSOR_CORES == 1 else "ddc_mma_kernel"
         return "ddc_tile_kernel"
     n, tpa = cfg["nchans"], -(-cfg["ntaps"] // cfg["nchans"])
     pt = 1
@@ -465,6 +479,7 @@ class DdcCtx(object):
         taps = firdes.low_pass_2(1.0, fs, rate / 2, rate / 2, 20.0, firdes.WIN_HAMMING)
         rng = np.random.default_rng(seed)
         offs = [-62500.0] if cfg["nchan"] == 1 else list(rng.uniform(-0.45 * fs, 0.45 * fs, cfg["nchan"]))
+        self.decim = decim
         self.ids = [self.bank.open(decim, taps, f, fs, OUT_IQ | OUT_FM, 5.0) for f in offs]
         x = synth_block(self.n, 64, seed)
         self.d_in = self.e.to_device(x)
@@ -530,6 +545,35 @@ def side_run(device, wl, world, dist, local, peak, steps, out_block, log2n=None,
         c.close()
     return {"workload": cfg["desc"], "kernel": kernel_name(wl), "unit": "Msps", "value": rate / 1e6,
             "algorithmic_bytes_per_sample": bps, "roofline_frac": tot * bps / (ms * 1e-3) / 1e9 / peak}
+
+
+def ddc_side_run(device, wl, steps):
+    """Device-resident rate of a DDC-bank workload on this rank, tensor-core path and CUDA-core path."""
+    global DDC_TENSOR_CORES
+    cfg = WORKLOADS[wl]
+    out = {"workload": cfg["desc"], "unit": "Msps"}
+    keep = DDC_TENSOR_CORES
+    for name, mode in (("value", 1), ("cuda_core_value", 0)):
+        DDC_TENSOR_CORES = mode
+        ctx = DdcCtx(device, wl, seed=3)
+        for _ in range(3):
+            ctx.step()
+        ctx.e.sync()
+        ctx.e.timer_start()
+        for _ in range(steps):
+            ctx.step()
+        ms = ctx.e.timer_stop()
+        out[name] = ctx.n * steps / (ms * 1e-3) / 1e6
+        if mode == 1:
+            out["kernel"] = kernel_name(wl)
+            tpeak, _ = load_tensor_peak()
+            alg = out[name] * 1e6 * 8.0 * cfg["nchan"] * cfg["ntaps"] / ctx.decim / 1e12
+            out["algorithmic_tflops"] = alg
+            out["tensor_roofline_frac"] = 3.0 * alg / tpeak
+        ctx.close()
+    DDC_TENSOR_CORES = keep
+    out["per_rank"] = True
+    return out
 
 
 def sustained_run(device, wl, dist, local, peak, out_block, log2n, seconds=2.5):
@@ -706,6 +750,19 @@ def run_b200(args):
                 "algorithmic_bytes_per_sample": bps,
                 "algorithmic_bytes_per_launch": n_launch_samples * bps,
                 "kernel_ms_per_launch": kern_ms}
+    if is_ddc and kernel_name(wl).startswith("ddc_mma"):
+        # many-channel bank: a contraction, compute bound.  8 real flops per complex tap MAC; every MAC is issued as
+        # three tf32 MMAs (hi*hi, hi*lo, lo*hi), so the tensor pipe executes 3x the algorithmic flops
+        tpeak, tsrc = load_tensor_peak()
+        decim = ctxs[0].decim
+        flop_per_sample = 8.0 * cfg["nchan"] * cfg["ntaps"] / decim
+        alg = samples_rank * flop_per_sample / (ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": 3.0 * alg, "peak": tpeak, "unit": "TFLOP/s", "frac": 3.0 * alg / tpeak,
+                    "traffic": None, "peak_source": tsrc, "kernel": kernel_name(wl),
+                    "algorithmic_tflops": alg, "algorithmic_flop_per_sample": flop_per_sample,
+                    "note": "achieved = tf32 flops the tensor pipe executes (3 MMAs per algorithmic MAC for fp32 parity); "
+                            "algorithmic_tflops is the fp32 work of the filter bank",
+                    "hbm_frac": achieved / peak, "algorithmic_bytes_per_sample": bps, "kernel_ms_per_launch": kern_ms}
     spg = sum(c.n for c in ctxs)
     for c in ctxs:
         c.close()
@@ -760,6 +817,8 @@ def run_b200(args):
         also["cfg5"]["single_launch"] = {"value": m["value"], "unit": "Msps", "roofline_frac": m["roofline_frac"],
                                          "launch": "one rcb_pfb_process_multi call per step (one persistent launch walks the 8 streams)"}
         USE_MULTI = keep
+        # ---- K2: 64 xlat channels (rc_frontend/channel.py) on one 16 Msps source: tensor cores vs CUDA cores ----
+        also["ddc64"] = ddc_side_run(device, "ddc64", half)
 
     api = "rcb_pfb_process(host pinned in, host pinned out)"
     if is_fft:

@@ -159,6 +159,7 @@ struct rcb_ctx {
         cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
         bool in_used[2] = {false, false};
         // tensor-core path (ddc_mma_kernel): group descriptors (pinned ring like the two above) and the packed B operand
+        bool use_lone = true;     // frame-per-lane kernel for lone channels (experiments build: RCB_DDC_LONE=0 disables)
         bool use_mma = true;      // rcb_ddc_set_tensor_cores
         int mma_gen = 2;          // 2: ddc_mma2_kernel (A operand in TMEM), 1: ddc_mma_kernel (A operand in shared memory)
         int mma_nseg = 3;         // generation 1: main accumulators
@@ -2067,7 +2068,48 @@ int ddc_process_chunk(rcb_t* h, const float2* d_x, size_t nsamples) {
                         }
                     }
                     dim3 grid((unsigned)((nout + opw * oq - 1) / (opw * oq)), (unsigned)ng);
-                    if (lone)
+                    // a lone channel with a decimation that is not tiny: frame-per-lane kernel (P MACs per sample load)
+                    const int lone_p = (ntaps + decim - 1) / decim;
+                    const size_t lone_smem = (size_t)lone_p * decim * sizeof(float4) +
+                                             (size_t)(kDdcLoneWarps * (33 - lone_p) + lone_p - 1) * (decim | 1) * sizeof(float2);
+                    bool use_lone = d.use_lone;
+#ifdef RCB_EXPERIMENTS
+                    if (const char* e = getenv("RCB_DDC_LONE")) use_lone = atoi(e) != 0;
+#endif
+                    if (b.second.size() == 1 && decim >= 8 && lone_p >= 1 && lone_p <= 8 && lone_smem <= 200 * 1024 &&
+                        use_lone) {
+                        static bool lone_attr_dev[64] = {};
+                        if (!lone_attr_dev[h->device & 63]) {
+                            const int cap = 200 * 1024;
+                            CK(cudaFuncSetAttribute(ddc_lone_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                            CK(cudaFuncSetAttribute(ddc_lone_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                            CK(cudaFuncSetAttribute(ddc_lone_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                            CK(cudaFuncSetAttribute(ddc_lone_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                            CK(cudaFuncSetAttribute(ddc_lone_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                            CK(cudaFuncSetAttribute(ddc_lone_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                            CK(cudaFuncSetAttribute(ddc_lone_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                            CK(cudaFuncSetAttribute(ddc_lone_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                            lone_attr_dev[h->device & 63] = true;
+                        }
+                        const int per_cta = kDdcLoneWarps * (33 - lone_p);
+                        const unsigned lg = (unsigned)((nout + per_cta - 1) / per_cta);
+                        const int ci0 = b.second[0];
+                        const float2* hp = d.d_hist[d.hist_cur];
+#define RCB_LONE(PP)                                                                                                   \
+    ddc_lone_kernel<PP><<<lg, kDdcLoneWarps * 32, lone_smem, h->stream>>>(d.d_chans, ci0, d_x, (long long)nsamples, hp, \
+                                                                         kDdcHistCap)
+                        switch (lone_p) {
+                            case 1: RCB_LONE(1); break;
+                            case 2: RCB_LONE(2); break;
+                            case 3: RCB_LONE(3); break;
+                            case 4: RCB_LONE(4); break;
+                            case 5: RCB_LONE(5); break;
+                            case 6: RCB_LONE(6); break;
+                            case 7: RCB_LONE(7); break;
+                            default: RCB_LONE(8); break;
+                        }
+#undef RCB_LONE
+                    } else if (lone)
                         ddc_tile_kernel<8, 1><<<grid, 256, smem, h->stream>>>(d.d_chans, d.d_groups + gi, d_x, (long long)nsamples,
                                                                               d.d_hist[d.hist_cur], kDdcHistCap);
                     else if (oq == 8)

@@ -201,6 +201,101 @@ __global__ void __launch_bounds__(256) ddc_tile_kernel(const DdcChanDev* __restr
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// A lone channel (BASELINE config 1: one rc_frontend/channel.py DDC on a 2.4 Msps source, D 96, 349 taps).
+// ddc_tile_kernel gives a lone channel 16 outputs per warp with the LANES striding the taps: every MAC costs one LDS
+// and the tile load is not overlapped (104 Gsps = 0.13 of the HBM roofline).  Here the window is cut into FRAMES of D
+// samples, frame g = samples [B + gD, B + (g+1)D),  B = window start of output 0:
+//
+//     y[o] = sum_{p < P} sum_{q < D} ct_rev[pD + q] * X[o + p][q],      P = ceil(K / D)
+//
+// A lane owns one frame: it reads X[g][q] ONCE (frames sit D|1 samples apart in shared memory, so the 32 lanes' 8-byte
+// reads are conflict free) and feeds P accumulators - the partial sums of outputs g, g-1, ..., g-P+1 - with taps that
+// are the same for all lanes (broadcast LDS.128 of the (re, im, -im, re) quadruple): P complex MACs per sample load
+// instead of one.  The P partials of an output meet by shuffle (lane o takes part[p] from lane o + p), so a warp of 32
+// frames completes 32 - (P-1) outputs and consecutive warps overlap by P - 1 frames.
+// grid (ceil(nout / (4 * (33 - P))),), block 128, dynamic smem (taps P*D*16 + frames (4*(33-P)+P-1) * (D|1) * 8) bytes
+// ------------------------------------------------------------------------------------------------
+constexpr int kDdcLoneWarps = 4;
+template <int P>
+__global__ void __launch_bounds__(kDdcLoneWarps * 32) ddc_lone_kernel(const DdcChanDev* __restrict__ chans, int ci,
+                                                                      const float2* __restrict__ x, long long nsamp,
+                                                                      const float2* __restrict__ hist, int hist_cap) {
+    extern __shared__ __align__(16) unsigned char ddc_lone_smem[];
+    const DdcChanDev ch = chans[ci];
+    const int D = ch.decim, K = ch.ntaps;
+    constexpr int S = 33 - P;                       // outputs a warp completes
+    constexpr int F = kDdcLoneWarps * S + P - 1;    // frames of the CTA tile
+    const int stride = D | 1;
+    float4* s_taps = reinterpret_cast<float4*>(ddc_lone_smem);            // [P * D], zero beyond K
+    float2* s_x = reinterpret_cast<float2*>(s_taps + P * D);              // [F][stride]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int o_base = blockIdx.x * (kDdcLoneWarps * S);
+    if (o_base >= ch.nout) return;
+    for (int i = threadIdx.x; i < P * D; i += kDdcLoneWarps * 32)
+        s_taps[i] = (i < K) ? __ldg(ch.ctaps4_rev + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // frames o_base .. o_base + F - 1 = F * D consecutive samples starting at b0
+    const long long b0 = ch.s_first - (K - 1) + (long long)o_base * D;
+    if (b0 >= 0 && b0 + (long long)F * D <= nsamp) {
+        // interior tile: one 8-byte cp.async per sample, all in flight at once (a register-staged loop would expose
+        // one global-load latency per element: 90 per thread)
+        int q = threadIdx.x, g = 0;
+        for (int i = threadIdx.x; i < F * D; i += kDdcLoneWarps * 32) {
+            while (q >= D) {
+                q -= D;
+                ++g;
+            }
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_x + g * stride + q);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(x + b0 + i) : "memory");
+            q += kDdcLoneWarps * 32;
+        }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    } else {
+        // block edges: history before the block, zeros after it
+        for (int g = warp; g < F; g += kDdcLoneWarps) {
+            const long long fb = b0 + (long long)g * D;
+            for (int q = lane; q < D; q += 32) {
+                const long long idx = fb + q;
+                s_x[g * stride + q] = (idx < nsamp) ? ddc_x_at(x, hist, hist_cap, idx) : make_float2(0.f, 0.f);
+            }
+        }
+    }
+    __syncthreads();
+    const int g = warp * S + lane;  // this lane's frame within the tile
+    float2 part[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) part[p] = make_float2(0.f, 0.f);
+    if (g < F) {
+        const float2* xr = s_x + g * stride;
+#pragma unroll 4
+        for (int q = 0; q < D; ++q) {
+            const float2 xv = xr[q];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const float4 tv = s_taps[p * D + q];
+                part[p] = p2fmas(make_float2(tv.x, tv.y), xv.x, part[p]);
+                part[p] = p2fmas(make_float2(tv.z, tv.w), xv.y, part[p]);
+            }
+        }
+    }
+    // output o = frame index of its first frame; frame o + p holds its p-th partial
+    float2 acc = part[0];
+#pragma unroll
+    for (int p = 1; p < P; ++p) {
+        acc.x += __shfl_down_sync(0xffffffffu, part[p].x, p);
+        acc.y += __shfl_down_sync(0xffffffffu, part[p].y, p);
+    }
+    const int o = o_base + g;
+    if (lane < S && o < ch.nout) {
+        double ph = ch.phase0 + ch.cyc * (double)o;
+        ph -= floor(ph);
+        double sn, cs;
+        sincospi(-2.0 * ph, &sn, &cs);
+        const float cf = (float)cs, sf = (float)sn;
+        ch.out_iq[o] = make_float2(fmaf(acc.x, cf, -acc.y * sf), fmaf(acc.x, sf, acc.y * cf));
+    }
+}
+
 // FM demod of each channel's narrowband block + carry of the last sample.  grid (ceil(max_nout/256), M)
 __global__ void __launch_bounds__(256) ddc_fm_kernel(const DdcChanDev* __restrict__ chans) {
     const DdcChanDev ch = chans[blockIdx.y];

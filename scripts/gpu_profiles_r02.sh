@@ -14,7 +14,10 @@ cap pfb_tma_cfg5   pfb_fm_tma_multi        "--workload cfg5"
 cap pfb_tma_cfg2   pfb_fm_tma_kernel       "--workload cfg2 --log2n 26"
 cap pfb_ws_iqfm    pfb_fm_ws_kernel        "--workload cfg3_iqfm_p16 --log2n 26"
 cap ddc_tile_cfg1  ddc_tile_kernel         "--workload cfg1"
-cap ddc_tile_64    ddc_tile_kernel         "--workload ddc64 --log2n 22"
+cap ddc_tile_64    ddc_tile_kernel         "--workload ddc64 --log2n 22 --no-tensor-cores"
+cap ddc_mma2       ddc_mma2_kernel         "--workload ddc64"
+cap ddc_mma        "ddc_mma_kernel"        "--workload ddc64 --ddc-mode 2"
+cap ddc_head       ddc_head_kernel         "--workload ddc64"
 cap ddc_post       ddc_post_kernel         "--workload cfg1"
 cap fft_cols       fft_cols_tma_kernel     "--workload cfg4 --log2n 25"
 cap fft_rows       fft_rows_kernel         "--workload cfg4 --log2n 25"
@@ -25,3 +28,5 @@ timeout 240 ncu --set full --clock-control none --import-source on -k regex:"qua
 # launch list of the bench command (every launch with its device time; shares, not absolutes)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/r02_launches_cfg3.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-also --e2e-steps 1 --no-ceiling > gpurun_out/ncu_launches.log 2>&1
 grep -c pfb_fm1 gpurun_out/r02_launches_cfg3.csv
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r02_launches_ddc64.csv python bench.py --workload ddc64 --steps 3 --warmup 3 --no-cpu --no-also --e2e-steps 1 --no-ceiling > /dev/null 2>&1
+grep -c ddc_mma2 gpurun_out/r02_launches_ddc64.csv
