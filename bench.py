@@ -91,11 +91,11 @@ def kernel_name(wl):
     rcb_fft_process, csrc/b200chan.cu)."""
     cfg = WORKLOADS[wl]
     if cfg.get("kind") == "fft":
-        return "fft_cols_tma_kernel+fft_rows_kernel"
+        return "fft_frame_kernel" if cfg["length"] == (1 << 14) else "fft_cols_tma_kernel+fft_rows_kernel"
     if cfg.get("kind") == "ddc":
         if cfg["nchan"] >= 12 and DDC_TENSOR_CORES:
             return "ddc_mma2_kernel" if DDC_TENSOR_CORES == 1 else "ddc_mma_kernel"
-        return "ddc_tile_kernel"
+        return "ddc_lone_kernel" if cfg["nchan"] == 1 else "ddc_tile_kernel"
     n, tpa = cfg["nchans"], -(-cfg["ntaps"] // cfg["nchans"])
     pt = 1
     while pt < tpa:
@@ -547,6 +547,31 @@ def side_run(device, wl, world, dist, local, peak, steps, out_block, log2n=None,
             "algorithmic_bytes_per_sample": bps, "roofline_frac": tot * bps / (ms * 1e-3) / 1e9 / peak}
 
 
+def ddc_lone_side_run(device, wl, steps, e2e_steps, world, dist, local, peak):
+    """BASELINE config 1 (one rc_frontend/channel.py channel on a 2.4 Msps RTL-SDR source): device rate and the
+    end-to-end rate with complex64 and with the dongle's own u8 samples crossing PCIe."""
+    cfg = WORKLOADS[wl]
+    ctx = DdcCtx(device, wl, seed=3)
+    for _ in range(3):
+        ctx.step()
+    ctx.e.sync()
+    ctx.e.timer_start()
+    for _ in range(steps):
+        ctx.step()
+    ms = ctx.e.timer_stop()
+    v = ctx.n * steps / (ms * 1e-3) / 1e6
+    out = {"workload": cfg["desc"], "kernel": "ddc_lone_kernel", "unit": "Msps", "value": v, "per_rank": True,
+           "algorithmic_bytes_per_sample": ctx.bytes_per_sample,
+           "roofline_frac": v * 1e6 * ctx.bytes_per_sample / 1e9 / peak}
+    ctx.close()
+    for key, fmt in (("e2e", None), ("e2e_u8", "u8")):
+        ev, h2d, d2h, _ = run_e2e_ddc(device, wl, max(e2e_steps, 2), dist, local, in_fmt=fmt)
+        ev = ev * world if dist is None else allreduce_sum_min(dist, local, ev, world)
+        out[key] = {"value": ev, "unit": "Msps", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "rcb_ddc_process(host pinned in%s) + rcb_ddc_pull_all" % (", u8 wire format" if fmt else "")}
+    return out
+
+
 def ddc_side_run(device, wl, steps):
     """Device-resident rate of a DDC-bank workload on this rank, tensor-core path and CUDA-core path."""
     global DDC_TENSOR_CORES
@@ -651,13 +676,20 @@ def run_e2e(device, wl, steps, warmup, dist, local, log2n=26, out_block=0, in_fm
     return n * max(steps, 1) / max(dt_s, 1e-9) / 1e6, h2d, d2h, chk
 
 
-def run_e2e_ddc(device, wl, steps, dist, local, log2n=24):
-    """Host block in -> all channels' IQ+FM pulled back to the host (what SourceStream.push does)."""
+def run_e2e_ddc(device, wl, steps, dist, local, log2n=24, in_fmt=None):
+    """Host block in -> all channels' IQ+FM pulled back to the host (what SourceStream.push does).  in_fmt: the block
+    crosses PCIe in the SDR's wire format (rcb_ddc_set_input_format)."""
     from radiocapture_rf_b200.engine import OUT_FM, OUT_IQ
     ctx = DdcCtx(device, wl, seed=5, log2n=log2n)
     n = ctx.n
-    hin = ctx.e.pinned((n,), np.complex64)
-    hin[:] = synth_block(n, 64, 5)
+    if in_fmt:
+        fmt, dt, off, scale = RAW_FORMATS[in_fmt]
+        ctx.bank.set_input_format(fmt, off, scale)
+        hin = ctx.e.pinned((2 * n,), dt)
+        hin[:] = quantise(synth_block(n, 64, 5), in_fmt)
+    else:
+        hin = ctx.e.pinned((n,), np.complex64)
+        hin[:] = synth_block(n, 64, 5)
     for _ in range(2):   # warm-up incl. the pulls (staging buffers, row-length guess)
         ctx.bank.process(hin)
         ctx.bank.pull_all(OUT_IQ)
@@ -675,7 +707,7 @@ def run_e2e_ddc(device, wl, steps, dist, local, log2n=24):
     dt = time.perf_counter() - t0
     barrier(dist, local)
     ctx.close()
-    return n * steps / dt / 1e6, n * 8, d2h, chk
+    return n * steps / dt / 1e6, hin.nbytes, d2h, chk
 
 
 def run_e2e_fft(device, wl, steps, dist, local, log2n=26):
@@ -819,6 +851,8 @@ def run_b200(args):
         USE_MULTI = keep
         # ---- K2: 64 xlat channels (rc_frontend/channel.py) on one 16 Msps source: tensor cores vs CUDA cores ----
         also["ddc64"] = ddc_side_run(device, "ddc64", half)
+        # ---- K2: BASELINE config 1, one channel on a 2.4 Msps source ----
+        also["cfg1"] = ddc_lone_side_run(device, "cfg1", half, args.e2e_steps, world, dist, local, peak)
 
     api = "rcb_pfb_process(host pinned in, host pinned out)"
     if is_fft:

@@ -130,6 +130,13 @@ int rcb_ddc_retune(rcb_t* h, int chan_id, double center_freq);
 int rcb_ddc_set_taps(rcb_t* h, int chan_id, const float* taps, int ntaps);
 int rcb_ddc_close(rcb_t* h, int chan_id);
 int rcb_ddc_process(rcb_t* h, const void* iq, size_t nsamples, int in_mem);
+/* Wire-format input for the bank (the RTL-SDR sources of configs/ deliver u8, UHD sc8 / sc16 -
+ * configs/config_denver_usrp.py:20): after this call `iq` of rcb_ddc_process is interleaved integer I/Q, fmt / offset /
+ * scale as in rcb_pfb_set_input_format, nsamples still counts complex samples.  The block crosses PCIe in the wire
+ * format (2-4x fewer bytes: the end-to-end rate of a DDC bank is PCIe bound) and becomes complex64 on the device, chunk
+ * by chunk, in the staging buffer the DDC kernels read (same arithmetic as rcb_convert_iq: bit-identical to converting
+ * on the host first).  Streaming state is kept; fmt = 0 restores complex64. */
+int rcb_ddc_set_input_format(rcb_t* h, int fmt, float offset, float scale);
 int rcb_ddc_pull(rcb_t* h, int chan_id, int which, void* dst, size_t cap_items, int dst_mem,
                  size_t* nitems);
 /* Buckets of >= 12 channels that share (decim, ntaps) with an even decim run on the tensor cores (tcgen05 kind::tf32,
@@ -217,10 +224,18 @@ int rcb_fft_config(rcb_t* h, int length, const float* window, int avg_frames);
 int rcb_fft_reset(rcb_t* h);
 int rcb_fft_process(rcb_t* h, const void* iq, size_t nsamples, int in_mem, void* out_sums,
                     size_t cap_vectors, int out_mem, size_t* nvec);
-/* Which kernels run rcb_fft_process: 0 (default) = column pass / row pass / fold per L2-resident sub-batch on two
- * streams; 1 = ONE persistent launch per call (task queue over column and row tiles of all frames, scratch ring kept in
- * L2, block sums accumulated in frame order by the row tiles).  Same results bit for bit; the persistent kernel needs
- * frames of many tiles (2^18, 2^20 points) to be competitive. */
+/* Which kernels run rcb_fft_process.
+ * 0 (default): 16384-point frames - fft_vector.py:32, the reference's own scan length - run on fft_frame_kernel: the whole
+ *    frame lives in one SM's shared memory (bulk-copied in, both FFT passes in place, log-power summed per group of
+ *    about a dozen frames, 2 launches per call); every other length runs the column pass / row pass / fold pipeline per
+ *    L2-resident sub-batch on two streams.
+ * 1: ONE persistent launch per call for every length (task queue over column and row tiles of all frames, scratch ring
+ *    kept in L2, block sums accumulated in frame order by the row tiles); needs frames of many tiles (2^18, 2^20 points)
+ *    to be competitive.
+ * 2: the column / row / fold pipeline for every length.
+ * The block sum is associated in frame order by the tiled pipelines and in (frame-in-group, group) order by the
+ * frame-resident kernel - both independent of how the stream is split into calls - so a switch restarts the current
+ * averaging block (like rcb_fft_reset). */
 int rcb_fft_set_pipeline(rcb_t* h, int persistent);
 
 #ifdef __cplusplus

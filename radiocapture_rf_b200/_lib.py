@@ -89,6 +89,7 @@ _PROTOTYPES = {
     "rcb_pfb_reset": (C.c_int, [_vp]),
     "rcb_pfb_set_out_block": (C.c_int, [_vp, C.c_int]),
     "rcb_pfb_set_input_format": (C.c_int, [_vp, C.c_int, C.c_float, C.c_float]),
+    "rcb_ddc_set_input_format": (C.c_int, [_vp, C.c_int, C.c_float, C.c_float]),
     "rcb_pfb_process": (C.c_int, [_vp, _vp, _sz, C.c_int, _vp, _vp, _sz, C.c_int, C.POINTER(_sz)]),
     "rcb_pfb_process_multi": (C.c_int, [_vp, C.c_int, _vp, _sz, _vp, _sz]),
     "rcb_ddc_open": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_float,

@@ -21,6 +21,7 @@
 #include "demod.cuh"
 #include "fft_logpow.cuh"
 #include "fft_scan.cuh"
+#include "fft_frame.cuh"
 #include "pfb_fm.cuh"
 #include "pfb_fm_tma.cuh"
 #include "pfb_fm_ws.cuh"
@@ -155,6 +156,10 @@ struct rcb_ctx {
         unsigned long long slot_no = 0;
         cudaEvent_t ev_slot[4] = {nullptr, nullptr, nullptr, nullptr};
         float2* d_in2[2] = {nullptr, nullptr};   // host-input staging (chunked)
+        void* d_raw2[2] = {nullptr, nullptr};    // wire-format staging (rcb_ddc_set_input_format)
+        size_t raw_cap2[2] = {0, 0};             // bytes
+        int in_fmt = 0;
+        float in_off = 0.f, in_scale = 1.f;
         size_t in_cap2[2] = {0, 0};
         cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
         bool in_used[2] = {false, false};
@@ -909,6 +914,7 @@ extern "C" int rcb_close(rcb_t* h) {
         if (h->ddc.ev_slot[i]) cudaEventDestroy(h->ddc.ev_slot[i]);
     for (int i = 0; i < 2; ++i) {
         cudaFree(h->ddc.d_in2[i]);
+        cudaFree(h->ddc.d_raw2[i]);
         if (h->ddc.ev_in[i]) cudaEventDestroy(h->ddc.ev_in[i]);
         if (h->ddc.ev_done[i]) cudaEventDestroy(h->ddc.ev_done[i]);
     }
@@ -2194,9 +2200,12 @@ extern "C" int rcb_ddc_process(rcb_t* h, const void* iq, size_t nsamples, int in
             }
         }
     }
-    if (in_mem == RCB_MEM_DEVICE) return ddc_process_chunk(h, (const float2*)iq, nsamples);
-    // host input: chunks through two staging buffers, the H2D of chunk k + 1 (copy stream) overlaps the kernels of chunk k
+    if (in_mem == RCB_MEM_DEVICE && d.in_fmt == 0) return ddc_process_chunk(h, (const float2*)iq, nsamples);
+    // host input (and any wire-format input): chunks through two staging buffers, the H2D of chunk k + 1 (copy stream)
+    // overlaps the kernels of chunk k.  Wire formats travel as they are (2-4x fewer PCIe bytes) and become complex64 in
+    // the staging buffer on the device (convert_iq_kernel, the K5 arithmetic: bit-identical to rcb_convert_iq).
     const size_t csz = std::min(nsamples, kDdcChunk);
+    const size_t bps = pfb_in_bytes_per_sample(d.in_fmt);
     for (int i = 0; i < 2; ++i) {
         if (d.in_cap2[i] < csz) {
             CK(cudaStreamSynchronize(h->stream));
@@ -2206,6 +2215,14 @@ extern "C" int rcb_ddc_process(rcb_t* h, const void* iq, size_t nsamples, int in
             CK(cudaMalloc(&d.d_in2[i], csz * sizeof(float2)));
             d.in_cap2[i] = csz;
         }
+        if (d.in_fmt && in_mem == RCB_MEM_HOST && d.raw_cap2[i] < csz * bps) {
+            CK(cudaStreamSynchronize(h->stream));
+            cudaFree(d.d_raw2[i]);
+            d.d_raw2[i] = nullptr;
+            d.raw_cap2[i] = 0;
+            CK(cudaMalloc(&d.d_raw2[i], csz * bps));
+            d.raw_cap2[i] = csz * bps;
+        }
         if (!d.ev_in[i]) CK(cudaEventCreateWithFlags(&d.ev_in[i], cudaEventDisableTiming));
         if (!d.ev_done[i]) CK(cudaEventCreateWithFlags(&d.ev_done[i], cudaEventDisableTiming));
     }
@@ -2214,11 +2231,28 @@ extern "C" int rcb_ddc_process(rcb_t* h, const void* iq, size_t nsamples, int in
     while (done < nsamples) {
         const int sl = k & 1;
         const size_t n = std::min(csz, nsamples - done);
-        if (d.in_used[sl]) CK(cudaStreamWaitEvent(h->s_in, d.ev_done[sl], 0));  // the kernels that read this buffer are done
-        CK(cudaMemcpyAsync(d.d_in2[sl], (const float2*)iq + done, n * sizeof(float2), cudaMemcpyHostToDevice, h->s_in));
-        h->stats.h2d_bytes += n * sizeof(float2);
-        CK(cudaEventRecord(d.ev_in[sl], h->s_in));
-        CK(cudaStreamWaitEvent(h->stream, d.ev_in[sl], 0));
+        const void* d_raw = nullptr;
+        if (in_mem == RCB_MEM_HOST) {
+            if (d.in_used[sl]) CK(cudaStreamWaitEvent(h->s_in, d.ev_done[sl], 0));  // the kernels that read this buffer are done
+            void* dst = d.in_fmt ? d.d_raw2[sl] : (void*)d.d_in2[sl];
+            CK(cudaMemcpyAsync(dst, (const char*)iq + done * bps, n * bps, cudaMemcpyHostToDevice, h->s_in));
+            h->stats.h2d_bytes += n * bps;
+            CK(cudaEventRecord(d.ev_in[sl], h->s_in));
+            CK(cudaStreamWaitEvent(h->stream, d.ev_in[sl], 0));
+            d_raw = dst;
+        } else {
+            d_raw = (const char*)iq + done * bps;
+        }
+        if (d.in_fmt) {
+            const unsigned grid = (unsigned)((n + 1023) / 1024);
+            if (d.in_fmt == RCB_FMT_U8)
+                convert_iq_kernel<uint8_t><<<grid, 256, 0, h->stream>>>((const uint8_t*)d_raw, d.d_in2[sl], (long long)n, d.in_off, d.in_scale);
+            else if (d.in_fmt == RCB_FMT_S8)
+                convert_iq_kernel<int8_t><<<grid, 256, 0, h->stream>>>((const int8_t*)d_raw, d.d_in2[sl], (long long)n, d.in_off, d.in_scale);
+            else
+                convert_iq_kernel<int16_t><<<grid, 256, 0, h->stream>>>((const int16_t*)d_raw, d.d_in2[sl], (long long)n, d.in_off, d.in_scale);
+            CKL(h);
+        }
         rc = ddc_process_chunk(h, d.d_in2[sl], n);
         if (rc) return rc;
         CK(cudaEventRecord(d.ev_done[sl], h->stream));
@@ -2226,6 +2260,17 @@ extern "C" int rcb_ddc_process(rcb_t* h, const void* iq, size_t nsamples, int in
         done += n;
         ++k;
     }
+    return RCB_OK;
+}
+
+// Wire-format input for the DDC bank: see include/b200chan.h.  The channels' streaming state is kept
+// (the history is complex64 whatever the wire format), so the format may change between blocks.
+extern "C" int rcb_ddc_set_input_format(rcb_t* h, int fmt, float offset, float scale) {
+    if (!h) return RCB_EINVAL;
+    if (fmt != 0 && fmt != RCB_FMT_U8 && fmt != RCB_FMT_S8 && fmt != RCB_FMT_S16) return RCB_EINVAL;
+    h->ddc.in_fmt = fmt;
+    h->ddc.in_off = fmt ? offset : 0.f;
+    h->ddc.in_scale = fmt ? scale : 1.f;
     return RCB_OK;
 }
 
@@ -2439,7 +2484,11 @@ extern "C" int rcb_fft_set_pipeline(rcb_t* h, int persistent) {
     if (!h->fft.configured) return RCB_ESTATE;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
-    h->fft.use_scan = (persistent != 0);
+    if (persistent < 0 || persistent > 2) return RCB_EINVAL;
+    h->fft.use_scan = (persistent == 1);
+    h->fft.frame_off = (persistent != 0);
+    // the pipelines associate the block sum differently (frame order / group order): a switch restarts the block
+    if (fft_reset(h->fft, h->stream)) return fail_cuda(h, cudaGetLastError(), "fft_reset");
     return RCB_OK;
 }
 extern "C" int rcb_fft_process(rcb_t* h, const void* iq, size_t nsamples, int in_mem, void* out_sums, size_t cap_vectors,
@@ -2452,7 +2501,10 @@ extern "C" int rcb_fft_process(rcb_t* h, const void* iq, size_t nsamples, int in
     // one persistent launch per call (fft_scan.cuh); the round-1 three-kernel pipeline remains as the fallback for inputs
     // a TMA descriptor cannot address
     int rc = 1;
-    if (h->fft.use_scan)
+    if (h->fft.use_frame && !h->fft.frame_off)
+        rc = fft_process_frames(h->fft, (const float2*)iq, nsamples, in_mem, (float*)out_sums, cap_vectors, out_mem, nvec,
+                                h->stream, &launches, &h2d, &d2h);
+    else if (h->fft.use_scan)
         rc = fft_process_scan(h->fft, (const float2*)iq, nsamples, in_mem, (float*)out_sums, cap_vectors, out_mem, nvec,
                               h->stream, &launches, &h2d, &d2h, h->sm_count);
     if (rc == 1)

@@ -238,16 +238,17 @@ __global__ void __launch_bounds__(kDdcLoneWarps * 32) ddc_lone_kernel(const DdcC
     const long long b0 = ch.s_first - (K - 1) + (long long)o_base * D;
     if (b0 >= 0 && b0 + (long long)F * D <= nsamp) {
         // interior tile: one 8-byte cp.async per sample, all in flight at once (a register-staged loop would expose
-        // one global-load latency per element: 90 per thread)
-        int q = threadIdx.x, g = 0;
-        for (int i = threadIdx.x; i < F * D; i += kDdcLoneWarps * 32) {
-            while (q >= D) {
-                q -= D;
-                ++g;
+        // one global-load latency per batch).  A warp copies whole frames: no index arithmetic beyond two adds per copy
+        // (the first version kept a running (frame, offset) pair per thread and spent more instructions on the fill
+        // than on the MACs, profiles/r02_ddc_lone_v1_summary.txt)
+        const float2* src = x + b0;
+        for (int g = warp; g < F; g += kDdcLoneWarps) {
+            const float2* sg = src + (long long)g * D;
+            float2* dg = s_x + g * stride;
+            for (int q = lane; q < D; q += 32) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(dg + q);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(sg + q) : "memory");
             }
-            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_x + g * stride + q);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(x + b0 + i) : "memory");
-            q += kDdcLoneWarps * 32;
         }
         asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     } else {

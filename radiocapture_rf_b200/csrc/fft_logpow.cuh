@@ -372,6 +372,15 @@ struct FftState {
     unsigned* d_ctl = nullptr;    // [1 task counter | ring cols_done | ring rows_done | row tiles tile_seq]
     size_t ctl_words = 0;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
+    // frame-resident kernel (fft_frame.cuh): L = 16384, the reference's own scan length
+    bool use_frame = false;
+    bool frame_off = false;         // rcb_fft_set_pipeline(1 / 2): run the tiled pipelines instead
+    int fr_G = 0, fr_gpb = 0;       // frames per group, groups per averaging block
+    float2* d_tw_frame = nullptr;   // [1024] dense swizzled W_1024^{-ll m1}
+    float* d_carry = nullptr;       // [L] sums of the group a call ended in
+    float* d_acc_alt = nullptr;     // second block accumulator (fft_fold_groups_kernel reads one, writes the other)
+    float* d_partial = nullptr;     // [partial_rows][L] group sums of one launch
+    size_t partial_rows = 0;
 };
 
 inline void fft_free(FftState& s) {
@@ -399,6 +408,10 @@ inline void fft_free(FftState& s) {
     cudaFree(s.d_in);
     cudaFree(s.d_ring);
     cudaFree(s.d_ctl);
+    cudaFree(s.d_tw_frame);
+    cudaFree(s.d_carry);
+    cudaFree(s.d_acc_alt);
+    cudaFree(s.d_partial);
     for (int i = 0; i < 2; ++i) {
         if (s.ev_copy[i]) cudaEventDestroy(s.ev_copy[i]);
         if (s.ev_used[i]) cudaEventDestroy(s.ev_used[i]);
@@ -508,6 +521,31 @@ inline int fft_config(FftState& s, int L, const float* window, int avg, cudaStre
         FCK(cudaMalloc(&s.d_counter[0], sizeof(int)));
         FCK(cudaMalloc(&s.d_counter[1], sizeof(int)));
         FCK(cudaStreamSynchronize(st));
+    }
+    if (L == (1 << 14)) {
+        // fft_frame_kernel: whole frame in one SM's shared memory.  Groups of about a dozen frames: short enough that a
+        // call of a few averaging blocks fills the GPU, long enough that the group's flush and the one exposed frame
+        // load are a few per cent of its work.
+        const int R = 32, N = 1024;
+        std::vector<float2> tt((size_t)N);
+        for (int ll = 0; ll < R; ++ll) {
+            const int sw = ll & (R / 2 - 1);
+            for (int m1 = 0; m1 < R; ++m1) {
+                const double a = -2.0 * M_PI * (double)((ll * m1) % N) / (double)N;
+                tt[(size_t)ll * R + ((((m1 >> 1) ^ sw) << 1) | (m1 & 1))] = make_float2((float)cos(a), (float)sin(a));
+            }
+        }
+        FCK(cudaMalloc(&s.d_tw_frame, tt.size() * sizeof(float2)));
+        FCK(cudaMemcpyAsync(s.d_tw_frame, tt.data(), tt.size() * sizeof(float2), cudaMemcpyHostToDevice, st));
+        FCK(cudaStreamSynchronize(st));
+        FCK(cudaMalloc(&s.d_carry, (size_t)L * sizeof(float)));
+        FCK(cudaMemsetAsync(s.d_carry, 0, (size_t)L * sizeof(float), st));
+        FCK(cudaMalloc(&s.d_acc_alt, (size_t)L * sizeof(float)));
+        FCK(cudaMemsetAsync(s.d_acc_alt, 0, (size_t)L * sizeof(float), st));
+        const int ng = (avg + 11) / 12;
+        s.fr_G = (avg + ng - 1) / ng;
+        s.fr_gpb = (avg + s.fr_G - 1) / s.fr_G;
+        s.use_frame = true;
     }
     FCK(cudaEventCreateWithFlags(&s.ev_start, cudaEventDisableTiming));
     FCK(cudaMalloc(&s.d_acc, (size_t)L * sizeof(float)));

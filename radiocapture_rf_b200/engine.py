@@ -312,9 +312,25 @@ class DdcBank(object):
         check(self.e.lib.rcb_ddc_tensor_core_launches(self.e.h, C.byref(n)), "rcb_ddc_tensor_core_launches", self.e.h)
         return int(n.value)
 
+    _RAW_DTYPES = {_lib.FMT_U8: np.uint8, _lib.FMT_S8: np.int8, _lib.FMT_S16: np.int16}
+
+    def set_input_format(self, fmt, offset=0.0, scale=1.0):
+        """process() / process_device() then take interleaved integer I/Q (FMT_U8 / FMT_S8 / FMT_S16), sample =
+        (v + offset) * scale; the block crosses PCIe in the wire format.  fmt 0 = complex64 again.  Channel state is
+        kept."""
+        check(self.e.lib.rcb_ddc_set_input_format(self.e.h, int(fmt), float(offset), float(scale)),
+              "rcb_ddc_set_input_format", self.e.h)
+        self.in_fmt = int(fmt)
+
     def process(self, iq):
-        iq = np.ascontiguousarray(iq, dtype=np.complex64)
-        check(self.e.lib.rcb_ddc_process(self.e.h, iq.ctypes.data, len(iq), MEM_HOST), "rcb_ddc_process", self.e.h)
+        fmt = getattr(self, "in_fmt", 0)
+        if fmt:
+            iq = np.ascontiguousarray(iq, dtype=self._RAW_DTYPES[fmt]).reshape(-1)
+            n = len(iq) // 2
+        else:
+            iq = np.ascontiguousarray(iq, dtype=np.complex64)
+            n = len(iq)
+        check(self.e.lib.rcb_ddc_process(self.e.h, iq.ctypes.data, n, MEM_HOST), "rcb_ddc_process", self.e.h)
 
     def process_device(self, d_in, nsamples):
         p = d_in.ptr if isinstance(d_in, DeviceBuffer) else d_in
@@ -498,9 +514,11 @@ class FftScanner(object):
     def reset(self):
         check(self.e.lib.rcb_fft_reset(self.e.h), "rcb_fft_reset", self.e.h)
 
-    def set_pipeline(self, persistent):
-        """False (default): three kernels per L2-resident sub-batch; True: one persistent fused launch per call."""
-        check(self.e.lib.rcb_fft_set_pipeline(self.e.h, int(bool(persistent))), "rcb_fft_set_pipeline", self.e.h)
+    def set_pipeline(self, mode):
+        """0 / False (default): frame-resident kernel for 16384-point frames, three kernels per L2-resident sub-batch for
+        the other lengths; 1 / True: one persistent fused launch per call; 2: the three-kernel pipeline for every length.
+        Restarts the current averaging block."""
+        check(self.e.lib.rcb_fft_set_pipeline(self.e.h, int(mode)), "rcb_fft_set_pipeline", self.e.h)
 
     def process(self, iq):
         """Returns float32 [nvec][L]: one vector per completed block of avg frames."""

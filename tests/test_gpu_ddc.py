@@ -441,3 +441,105 @@ def test_tensor_core_bank_wideband_2327_taps(engine, mode):
         err = gb.rel_l2(y[:m], ref[:m])
         print("2327 taps, mode %d, channel %d: rel_l2 %.2e" % (mode, k, err))
         assert err <= TOL, offs[k]
+
+
+@pytest.mark.parametrize("decim,ntaps", [(96, 349), (96, 96), (96, 97), (8, 64), (9, 41), (33, 100), (50, 349),
+                                         (200, 701), (640, 2327), (97, 500)])
+def test_lone_channel_kernel_shapes(engine, decim, ntaps):
+    """ddc_lone_kernel (a lone channel of a decimation grid: frame-per-lane, P = ceil(ntaps / decim) in 1..8, two frames
+    per lane) and its fall-backs: odd and even P, decimations that are not multiples of the warp, a window shorter than
+    one frame, tiles that do not fit shared memory (D 640); blocks that start inside the history, interior tiles and a
+    ragged tail, streamed in uneven blocks."""
+    rng = np.random.default_rng(decim * 1000 + ntaps)
+    n = 122 * decim * 5 + 3 * decim + 7
+    x = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 0.1).astype(np.complex64)
+    x += (0.5 * np.exp(2j * np.pi * 0.1003 * np.arange(n))).astype(np.complex64)
+    taps = (rng.standard_normal(ntaps) / np.sqrt(ntaps)).astype(np.float32)
+    fs, f0 = 1.0e6, 0.1e6
+    bank = DdcBank(engine)
+    c = bank.open(decim, taps, f0, fs, OUT_IQ | OUT_FM, 3.0)
+    ys, fms, pos = [], [], 0
+    for b in (n // 3 + 1, 5, n // 2, n):
+        b = min(b, n - pos)
+        if b <= 0:
+            break
+        bank.process(x[pos:pos + b])
+        ys.append(bank.pull(c, OUT_IQ))
+        fms.append(bank.pull(c, OUT_FM))
+        pos += b
+    y, fm = np.concatenate(ys), np.concatenate(fms)
+    ref = gb.freq_xlating_fir(x, taps, decim, f0, fs)
+    m = min(len(y), len(ref))
+    assert m >= n // decim
+    assert gb.rel_l2(y[:m], ref[:m]) <= TOL
+    assert _fm_err(fm[:m], gb.quadrature_demod(ref[:m], 3.0), 3.0) <= TOL
+
+
+@pytest.mark.parametrize("name,dt,off,sc", [("u8", np.uint8, -127.4, 1 / 128.0), ("s8", np.int8, 0.0, 1 / 128.0),
+                                            ("s16", np.int16, 0.0, 1 / 32768.0)])
+@pytest.mark.parametrize("nchan,device_input", [(1, False), (3, True), (16, False)])
+def test_ddc_wire_format_input(engine, name, dt, off, sc, nchan, device_input):
+    """rcb_ddc_set_input_format (f4 for K2): the block crosses PCIe as u8 / sc8 / sc16 and is converted on the device.
+    Same samples bit-for-bit as feeding the complex64 conversion (K5's rule) to a fresh bank - lone-channel, tiled and
+    tensor-core kernels - streamed in ragged blocks incl. one longer than a staging chunk; <= 1e-5 against the oracle."""
+    from radiocapture_rf_b200 import _lib
+    from radiocapture_rf_b200.engine import Engine
+    fmt = {"u8": _lib.FMT_U8, "s8": _lib.FMT_S8, "s16": _lib.FMT_S16}[name]
+    fs = 2.4e6
+    decim, taps = fd.channel_taps(fs, 12500)
+    n = (1 << 22) + 96 * 300 + 11 if nchan == 1 else 96 * 3000 + 11
+    rng = np.random.default_rng(5)
+    info = np.iinfo(dt)
+    t = np.arange(n)
+    offs = [-62500.0, 437500.0, 12500.0] + list(rng.uniform(-1.0e6, 1.0e6, 13))
+    offs = offs[:nchan]
+    sig = sum(0.3 / len(offs) * np.exp(2j * np.pi * (f / fs * t + 0.3 * np.sin(2 * np.pi * 1e-4 * t))) for f in offs[:3])
+    sig = sig + (rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 0.02
+    amp = 127.0 if info.max < 256 else float(info.max)
+    raw = np.clip(np.round(np.stack([sig.real, sig.imag], 1) * amp - (off if name == "u8" else 0.0)), info.min,
+                  info.max).astype(dt).reshape(-1)
+    xf = ((raw.astype(np.float32) + np.float32(off)) * np.float32(sc)).view(np.complex64)
+    blocks = (n // 5, 7, n) if nchan > 1 else (96 * 100 + 3, n)
+    bank = DdcBank(engine)
+    ids = [bank.open(decim, taps, f, fs, OUT_IQ | OUT_FM, 5.0) for f in offs]
+    bank.set_input_format(fmt, off, sc)
+    e2 = Engine(0)
+    try:
+        bank2 = DdcBank(e2)
+        ids2 = [bank2.open(decim, taps, f, fs, OUT_IQ | OUT_FM, 5.0) for f in offs]
+        got = {c: [] for c in ids}
+        want = {c: [] for c in ids2}
+        pos = 0
+        for b in blocks:
+            b = min(b, n - pos)
+            if device_input:
+                chunk = np.ascontiguousarray(raw[2 * pos:2 * (pos + b)])
+                d_raw = engine.dev_alloc(max(chunk.nbytes, 16))
+                _lib.check(engine.lib.rcb_memcpy(engine.h, d_raw.ptr, chunk.ctypes.data, chunk.nbytes, _lib.COPY_H2D),
+                           "h2d", engine.h)
+                bank.process_device(d_raw, b)
+                d_x = e2.to_device(xf[pos:pos + b])
+                bank2.process_device(d_x, b)
+            else:
+                bank.process(raw[2 * pos:2 * (pos + b)])
+                bank2.process(xf[pos:pos + b])
+            for c, c2 in zip(ids, ids2):
+                got[c].append((bank.pull(c, OUT_IQ), bank.pull(c, OUT_FM)))
+                want[c2].append((bank2.pull(c2, OUT_IQ), bank2.pull(c2, OUT_FM)))
+            pos += b
+        for c, c2 in zip(ids, ids2):
+            y = np.concatenate([p[0] for p in got[c]])
+            y2 = np.concatenate([p[0] for p in want[c2]])
+            assert np.array_equal(y, y2)
+            assert np.array_equal(np.concatenate([p[1] for p in got[c]]), np.concatenate([p[1] for p in want[c2]]))
+        for c, f in list(zip(ids, offs))[:3]:
+            y = np.concatenate([p[0] for p in got[c]])
+            m = min(len(y), 3000)
+            ref = gb.freq_xlating_fir(xf[:96 * m], taps, decim, f, fs)
+            assert gb.rel_l2(y[:len(ref)], ref) <= TOL
+        # back to complex64 without losing the stream position
+        bank.set_input_format(0)
+        bank.process(xf[:96 * 10])
+        assert len(bank.pull(ids[0], OUT_IQ)) in (10, 11)
+    finally:
+        e2.close()

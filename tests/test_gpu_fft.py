@@ -33,9 +33,9 @@ def test_fft_persistent_pipeline_matches_oracle_and_default(engine, length, avg,
     x, _ = synth.scan_stream(n, 2.4e6, length, seed=14, ncarriers=5)
     w = fd.blackmanharris(length)
     sc = FftScanner(engine, length, w, avg)
+    sc.set_pipeline(2)          # the tiled three-kernel pipeline (16384-point frames default to fft_frame_kernel)
     base = sc.process(x)
-    sc.reset()
-    sc.set_pipeline(True)
+    sc.set_pipeline(1)
     out = sc.process(x)
     assert out.shape == (nblocks, length)
     _check_logsum(out, gb.logpower_block_sums(x[:length * avg * nblocks], length, w, avg), avg)
@@ -56,7 +56,17 @@ def test_fft_persistent_pipeline_matches_oracle_and_default(engine, length, avg,
     assert np.array_equal(engine.to_host(d_out, (nblocks, length), np.float32), out)
 
 
-def _check_logsum(out, ref, avg):
+def _every_frame_strong(x, length, w, avg, nblocks):
+    """[nblocks][L] mask of the bins that stay within 40 dB of the frame maximum in EVERY frame of their block.  (A bin
+    whose block sum is strong can still hold a deep null in one frame - 100 dB down happens on the synthetic streams -
+    and that one log10 then carries the float32 rounding floor of the whole transform, in any float32 FFT.)"""
+    fr = np.asarray(x[:length * avg * nblocks], np.complex128).reshape(nblocks, avg, length) * np.asarray(w, np.float64)
+    p = np.abs(np.fft.fftshift(np.fft.fft(fr, axis=2), axes=2)) ** 2
+    lp = np.log10(np.maximum(p, 1e-18))
+    return (lp - lp.max(axis=2, keepdims=True)).min(axis=1) >= -4.0
+
+
+def _check_logsum(out, ref, avg, mask=None):
     """float32 FFT rounding is relative to the STRONGEST bins of a frame (~5e-7 of their amplitude), so
     bins 100+ dB down (Blackman-Harris leaves >110 dB of dynamic range on synthetic data) carry large
     relative errors in any float32 implementation, GNU Radio's FFTW float path included.  Parity is
@@ -65,7 +75,7 @@ def _check_logsum(out, ref, avg):
     out = np.asarray(out, np.float64)
     err = np.abs(out - ref)
     for b in range(ref.shape[0]):
-        strong = ref[b] >= ref[b].max() - 4.0 * avg
+        strong = (ref[b] >= ref[b].max() - 4.0 * avg) if mask is None else mask[b]
         assert strong.sum() > 0
         assert err[b][strong].max() <= 1e-4 * avg, (b, err[b][strong].max())
     assert err.mean() <= 2e-4 * np.sqrt(avg), err.mean()
@@ -142,3 +152,79 @@ def test_fft_rejects_unsupported(engine, built_lib):
     w = np.ones(1000, np.float32)
     st = built_lib.rcb_fft_config(engine.h, 1000, w.ctypes.data, 10)
     assert st == _lib.RCB_EUNSUPPORTED
+
+
+@pytest.mark.parametrize("avg,nblocks,frames_extra", [(100, 2, 37), (7, 5, 3), (1, 9, 0), (12, 3, 11), (25, 2, 24), (13, 4, 5)])
+def test_fft_frame_resident_kernel_16384(engine, avg, nblocks, frames_extra):
+    """fft_frame_kernel (the reference's own scan length, fft_vector.py:32 `length = 1024*16`): whole frame in one SM's
+    shared memory, sums per group of frames, one fold.  Parity bar of the tiled pipeline against the float64 oracle;
+    agreement with the three-kernel pipeline (different association of the sum); the same BITS for any split of the
+    stream into calls - blocks and groups cut anywhere, calls that end inside a group twice in a row; device-resident
+    input at an address the bulk copies cannot use (8-byte aligned); device-resident output."""
+    length = 16384
+    nfr = avg * nblocks + frames_extra
+    n = length * nfr
+    x, _ = synth.scan_stream(n, 2.4e6, length, seed=21 + avg, ncarriers=5)
+    w = fd.blackmanharris(length)
+    sc = FftScanner(engine, length, w, avg)
+    out = sc.process(x)
+    assert out.shape == (nblocks, length)
+    ref = gb.logpower_block_sums(x[:length * avg * nblocks], length, w, avg)
+    mask = _every_frame_strong(x, length, w, avg, nblocks)
+    _check_logsum(out, ref, avg, mask)
+    # the tiled pipeline on the same stream
+    sc.set_pipeline(2)
+    tiled = sc.process(x)
+    # (two different FFT factorisations: bins far below the strongest carry each one's own float32 rounding noise, so they
+    # are compared where _check_logsum compares - within 40 dB of the frame maximum in every frame - and on average)
+    for b in range(nblocks):
+        strong = mask[b]
+        assert np.abs(out[b][strong] - tiled[b][strong]).max() <= 2e-4 * avg
+    assert np.abs(out - tiled).mean() <= 4e-4 * np.sqrt(avg)
+    sc.set_pipeline(0)
+    # ragged calls
+    cuts = [1, 2, 1, max(avg - 3, 1), 5, avg + 1, 3 * avg + 2, 1]
+    parts, pos = [], 0
+    for c in cuts:
+        c = min(c, nfr - pos)
+        if c <= 0:
+            break
+        parts.append(sc.process(x[pos * length:(pos + c) * length]))
+        pos += c
+    if pos < nfr:
+        parts.append(sc.process(x[pos * length:]))
+    split = np.concatenate([p for p in parts if len(p)], axis=0)
+    assert np.array_equal(split, out)
+    # device-resident, input one sample off 16-byte alignment, device output
+    sc.reset()
+    d_in = engine.dev_alloc((n + 1) * 8)
+    from radiocapture_rf_b200._lib import COPY_H2D, check
+    check(engine.lib.rcb_memcpy(engine.h, d_in.ptr + 8, x.ctypes.data, x.nbytes, COPY_H2D), "h2d", engine.h)
+    d_out = engine.dev_alloc(nblocks * length * 4)
+    assert sc.process_device(d_in.ptr + 8, n, d_out, nblocks) == nblocks
+    engine.sync()
+    assert np.array_equal(engine.to_host(d_out, (nblocks, length), np.float32), out)
+    # aligned device input
+    sc.reset()
+    d_al = engine.to_device(x)
+    assert sc.process_device(d_al, n, d_out, nblocks) == nblocks
+    engine.sync()
+    assert np.array_equal(engine.to_host(d_out, (nblocks, length), np.float32), out)
+
+
+def test_fft_frame_resident_kernel_many_frames(engine):
+    """A call of several thousand frames (more groups than SMs, several waves) and the linear-power / argmax check
+    through avg = 1."""
+    length, avg, nblocks = 16384, 100, 21
+    n = length * avg * nblocks
+    base, _ = synth.scan_stream(length * 300, 2.4e6, length, seed=5, ncarriers=7)
+    x = np.tile(base, avg * nblocks // 300)
+    assert len(x) == n
+    w = fd.blackmanharris(length)
+    sc = FftScanner(engine, length, w, avg)
+    out = sc.process(x)
+    assert out.shape == (nblocks, length)
+    ref = gb.logpower_block_sums(x[:length * 300], length, w, avg)      # blocks repeat with period 3
+    for b in range(nblocks):
+        _check_logsum(out[b:b + 1], ref[b % 3:b % 3 + 1], avg)
+    assert np.array_equal(out[0], out[3]) and np.array_equal(out[1], out[19])
