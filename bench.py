@@ -547,6 +547,24 @@ def side_run(device, wl, world, dist, local, peak, steps, out_block, log2n=None,
             "algorithmic_bytes_per_sample": bps, "roofline_frac": tot * bps / (ms * 1e-3) / 1e9 / peak}
 
 
+def fft_side_run(device, wl, steps, peak):
+    """Device-resident rate of a scan workload (K3) on this rank."""
+    cfg = WORKLOADS[wl]
+    ctx = FftCtx(device, wl, seed=3)
+    for _ in range(3):
+        ctx.step()
+    ctx.e.sync()
+    ctx.e.timer_start()
+    for _ in range(steps):
+        ctx.step()
+    ms = ctx.e.timer_stop()
+    v = ctx.n * steps / (ms * 1e-3) / 1e6
+    out = {"workload": cfg["desc"], "kernel": kernel_name(wl), "unit": "Msps", "value": v, "per_rank": True,
+           "algorithmic_bytes_per_sample": 8, "roofline_frac": v * 1e6 * 8 / 1e9 / peak}
+    ctx.close()
+    return out
+
+
 def ddc_lone_side_run(device, wl, steps, e2e_steps, world, dist, local, peak):
     """BASELINE config 1 (one rc_frontend/channel.py channel on a 2.4 Msps RTL-SDR source): device rate and the
     end-to-end rate with complex64 and with the dongle's own u8 samples crossing PCIe."""
@@ -851,6 +869,9 @@ def run_b200(args):
         USE_MULTI = keep
         # ---- K2: 64 xlat channels (rc_frontend/channel.py) on one 16 Msps source: tensor cores vs CUDA cores ----
         also["ddc64"] = ddc_side_run(device, "ddc64", half)
+        # ---- K3: the reference's own scan (fft_vector.py:32, 16384 points x 100 frames) and BASELINE config 4 (2^20) ----
+        also["fft_scan_16k"] = fft_side_run(device, "cfg4_16k", half, peak)
+        also["cfg4"] = fft_side_run(device, "cfg4", half, peak)
         # ---- K2: BASELINE config 1, one channel on a 2.4 Msps source ----
         also["cfg1"] = ddc_lone_side_run(device, "cfg1", half, args.e2e_steps, world, dist, local, peak)
 

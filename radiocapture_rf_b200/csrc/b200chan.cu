@@ -2076,8 +2076,8 @@ int ddc_process_chunk(rcb_t* h, const float2* d_x, size_t nsamples) {
                     dim3 grid((unsigned)((nout + opw * oq - 1) / (opw * oq)), (unsigned)ng);
                     // a lone channel with a decimation that is not tiny: frame-per-lane kernel (P MACs per sample load)
                     const int lone_p = (ntaps + decim - 1) / decim;
-                    const size_t lone_smem = (size_t)lone_p * decim * sizeof(float4) +
-                                             (size_t)(kDdcLoneWarps * (33 - lone_p) + lone_p - 1) * (decim | 1) * sizeof(float2);
+                    const size_t lone_smem = 16 + (size_t)decim * ((lone_p + 1) & ~1) * sizeof(float2) +
+                                             (size_t)(kDdcLoneWarps * (33 - lone_p) + lone_p - 1) * ddc_lone_pitch(decim) * sizeof(float2);
                     bool use_lone = d.use_lone;
 #ifdef RCB_EXPERIMENTS
                     if (const char* e = getenv("RCB_DDC_LONE")) use_lone = atoi(e) != 0;

@@ -17,6 +17,7 @@
 #pragma once
 #include "common.cuh"
 #include "fft_packed.cuh"
+#include "pfb_fm_tma.cuh"  // mbarrier / bulk-copy helpers
 
 namespace rcb {
 
@@ -209,14 +210,18 @@ __global__ void __launch_bounds__(256) ddc_tile_kernel(const DdcChanDev* __restr
 //
 //     y[o] = sum_{p < P} sum_{q < D} ct_rev[pD + q] * X[o + p][q],      P = ceil(K / D)
 //
-// A lane owns one frame: it reads X[g][q] ONCE (frames sit D|1 samples apart in shared memory, so the 32 lanes' 8-byte
-// reads are conflict free) and feeds P accumulators - the partial sums of outputs g, g-1, ..., g-P+1 - with taps that
-// are the same for all lanes (broadcast LDS.128 of the (re, im, -im, re) quadruple): P complex MACs per sample load
-// instead of one.  The P partials of an output meet by shuffle (lane o takes part[p] from lane o + p), so a warp of 32
-// frames completes 32 - (P-1) outputs and consecutive warps overlap by P - 1 frames.
-// grid (ceil(nout / (4 * (33 - P))),), block 128, dynamic smem (taps P*D*16 + frames (4*(33-P)+P-1) * (D|1) * 8) bytes
+// A lane owns one frame: it reads X[g][q] ONCE (frames sit ddc_lone_pitch(D) samples apart in shared memory: the 32
+// lanes' 8-byte reads are 2-way conflicted at worst) and feeds P accumulators - the partial sums of outputs g, g-1, ..., g-P+1 - with taps that
+// are the same for all lanes (broadcast LDS.128 = two taps (re, im)): P complex MACs per sample load instead of one.
+// The P partials of an output meet by shuffle (lane o takes part[p] from lane o + p), so a warp of 32 frames completes
+// 32 - (P-1) outputs and consecutive warps overlap by P - 1 frames.
+// grid (ceil(nout / (W * (33 - P))),), block W * 32 (W = kDdcLoneWarps), dynamic smem 16 + taps D*PP*8 + frames
+// (W*(33-P)+P-1) * ddc_lone_pitch(D) * 8 bytes
 // ------------------------------------------------------------------------------------------------
-constexpr int kDdcLoneWarps = 4;
+constexpr int kDdcLoneWarps = 2;   // small CTAs (48 KB tile for D 96): four per SM, their fill and MAC phases interleave
+// frame pitch in shared memory (samples): >= D + 2 (a bulk copy starts on a 16-byte boundary, i.e. up to one sample
+// early, and moves an even number of samples) and = 2 (mod 4), so 16 lanes x 8 bytes hit 8 distinct bank pairs (2-way)
+__host__ __device__ constexpr int ddc_lone_pitch(int D) { return D + 2 + ((2 - (D + 2)) & 3); }
 template <int P>
 __global__ void __launch_bounds__(kDdcLoneWarps * 32) ddc_lone_kernel(const DdcChanDev* __restrict__ chans, int ci,
                                                                       const float2* __restrict__ x, long long nsamp,
@@ -226,59 +231,88 @@ __global__ void __launch_bounds__(kDdcLoneWarps * 32) ddc_lone_kernel(const DdcC
     const int D = ch.decim, K = ch.ntaps;
     constexpr int S = 33 - P;                       // outputs a warp completes
     constexpr int F = kDdcLoneWarps * S + P - 1;    // frames of the CTA tile
-    const int stride = D | 1;
-    float4* s_taps = reinterpret_cast<float4*>(ddc_lone_smem);            // [P * D], zero beyond K
-    float2* s_x = reinterpret_cast<float2*>(s_taps + P * D);              // [F][stride]
+    const int pitch = ddc_lone_pitch(D);
+    constexpr int PP = (P + 1) & ~1;                // taps per q, padded to an even count (one LDS.128 = two taps)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(ddc_lone_smem);
+    float2* s_taps = reinterpret_cast<float2*>(ddc_lone_smem + 16);       // [D][PP]: ct_rev[p * D + q] at [q][p], zero beyond K
+    float2* s_x = s_taps + D * PP;                                        // [F][pitch]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int o_base = blockIdx.x * (kDdcLoneWarps * S);
     if (o_base >= ch.nout) return;
-    for (int i = threadIdx.x; i < P * D; i += kDdcLoneWarps * 32)
-        s_taps[i] = (i < K) ? __ldg(ch.ctaps4_rev + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     // frames o_base .. o_base + F - 1 = F * D consecutive samples starting at b0
     const long long b0 = ch.s_first - (K - 1) + (long long)o_base * D;
-    if (b0 >= 0 && b0 + (long long)F * D <= nsamp) {
-        // interior tile: one 8-byte cp.async per sample, all in flight at once (a register-staged loop would expose
-        // one global-load latency per batch).  A warp copies whole frames: no index arithmetic beyond two adds per copy
-        // (the first version kept a running (frame, offset) pair per thread and spent more instructions on the fill
-        // than on the MACs, profiles/r02_ddc_lone_v1_summary.txt)
-        const float2* src = x + b0;
-        for (int g = warp; g < F; g += kDdcLoneWarps) {
-            const float2* sg = src + (long long)g * D;
-            float2* dg = s_x + g * stride;
-            for (int q = lane; q < D; q += 32) {
-                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(dg + q);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(sg + q) : "memory");
-            }
+    // interior tile: every frame arrives by ONE bulk copy (cp.async.bulk, SASS UBLKCP) - asynchronous, no registers, the
+    // whole 47 KB in flight at once.  (Version 1 used 8-byte cp.async: LDGSTS.64 costs one LSU wavefront PER LANE, the
+    // fill took three times as long as the MACs; a register-staged loop kept only the 8 loads in flight the scheduler
+    // chose to: 4 GB/s per CTA by Little's law, profiles/r02_ddc_lone_v3_summary.txt.)
+    const bool interior = (b0 >= 1 && b0 + (long long)F * D + 2 <= nsamp);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, kDdcLoneWarps * 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const float2* src0 = x + b0;
+    if (interior) {
+        // every thread starts the copies of its own frames (UBLKCP is issued lane by lane: spread over all warps), after
+        // posting their byte count: the barrier expects one arrival per thread
+        uint32_t bytes = 0;
+        for (int g = threadIdx.x; g < F; g += kDdcLoneWarps * 32) {
+            const uint32_t off = (uint32_t)((reinterpret_cast<uintptr_t>(src0 + (long long)g * D) >> 3) & 1u);
+            bytes += (((uint32_t)D + off + 1u) & ~1u) * 8u;
         }
-        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-    } else {
+        mbar_expect_tx(bar, bytes);
+        for (int g = threadIdx.x; g < F; g += kDdcLoneWarps * 32) {
+            const float2* sg = src0 + (long long)g * D;
+            const uint32_t off = (uint32_t)((reinterpret_cast<uintptr_t>(sg) >> 3) & 1u);
+            tma_bulk_g2s(s_x + g * pitch, sg - off, (((uint32_t)D + off + 1u) & ~1u) * 8u, bar);
+        }
+    }
+    for (int i = threadIdx.x; i < D * PP; i += kDdcLoneWarps * 32) {
+        const int q = i / PP, p = i - q * PP;
+        const int r = p * D + q;
+        s_taps[i] = (p < P && r < K) ? __ldg(ch.ctaps_rev + r) : make_float2(0.f, 0.f);
+    }
+    if (!interior) {
         // block edges: history before the block, zeros after it
         for (int g = warp; g < F; g += kDdcLoneWarps) {
             const long long fb = b0 + (long long)g * D;
             for (int q = lane; q < D; q += 32) {
                 const long long idx = fb + q;
-                s_x[g * stride + q] = (idx < nsamp) ? ddc_x_at(x, hist, hist_cap, idx) : make_float2(0.f, 0.f);
+                s_x[g * pitch + q] = (idx < nsamp) ? ddc_x_at(x, hist, hist_cap, idx) : make_float2(0.f, 0.f);
             }
         }
     }
     __syncthreads();
+    if (interior) mbar_wait(bar, 0);
     const int g = warp * S + lane;  // this lane's frame within the tile
-    float2 part[P];
+    // complex MAC as two real-scalar MACs on the (re, im) pair of the tap:  A += t * x.re,  B += t * x.im,
+    // acc = (A.x - B.y, A.y + B.x) - only (re, im) of a tap is loaded, two taps per LDS.128
+    float2 pa[P], pb[P];
 #pragma unroll
-    for (int p = 0; p < P; ++p) part[p] = make_float2(0.f, 0.f);
+    for (int p = 0; p < P; ++p) pa[p] = pb[p] = make_float2(0.f, 0.f);
     if (g < F) {
-        const float2* xr = s_x + g * stride;
+        // (a bulk copy started one sample early when the frame's first sample sits on an odd 8-byte address)
+        const float2* xr = s_x + g * pitch +
+                           (interior ? (int)((reinterpret_cast<uintptr_t>(src0 + (long long)g * D) >> 3) & 1u) : 0);
 #pragma unroll 4
         for (int q = 0; q < D; ++q) {
             const float2 xv = xr[q];
+            const float4* tq = reinterpret_cast<const float4*>(s_taps + q * PP);
 #pragma unroll
-            for (int p = 0; p < P; ++p) {
-                const float4 tv = s_taps[p * D + q];
-                part[p] = p2fmas(make_float2(tv.x, tv.y), xv.x, part[p]);
-                part[p] = p2fmas(make_float2(tv.z, tv.w), xv.y, part[p]);
+            for (int pp = 0; pp < PP / 2; ++pp) {
+                const float4 tv = tq[pp];
+                pa[2 * pp] = p2fmas(make_float2(tv.x, tv.y), xv.x, pa[2 * pp]);
+                pb[2 * pp] = p2fmas(make_float2(tv.x, tv.y), xv.y, pb[2 * pp]);
+                if (2 * pp + 1 < P) {
+                    pa[2 * pp + 1] = p2fmas(make_float2(tv.z, tv.w), xv.x, pa[2 * pp + 1]);
+                    pb[2 * pp + 1] = p2fmas(make_float2(tv.z, tv.w), xv.y, pb[2 * pp + 1]);
+                }
             }
         }
     }
+    float2 part[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) part[p] = make_float2(pa[p].x - pb[p].y, pa[p].y + pb[p].x);
     // output o = frame index of its first frame; frame o + p holds its p-th partial
     float2 acc = part[0];
 #pragma unroll

@@ -13,7 +13,7 @@ x = (np.exp(1j * np.cumsum(rng.uniform(-0.3, 0.3, (rows, n)), axis=1)) * 0.5).as
 fm = e.quad_demod(x, 5.0) if hasattr(e, "quad_demod") else None
 raw = rng.integers(0, 255, 2 << 24, dtype=np.uint8)
 if hasattr(e, "convert_iq"):
-    e.convert_iq(raw, _lib.FMT_U8, -127.4, 1 / 128.0)
+    e.convert_iq(raw, "u8")
 pd = PostDemod.p25_c4fm(e, rows)
 pd.process(x)
 pa = PostDemod.analog_fm(e, 64)

@@ -13,7 +13,7 @@ cap pfb_ws_p16     pfb_fm_ws_kernel        "--workload cfg3_p16 --log2n 26"
 cap pfb_tma_cfg5   pfb_fm_tma_multi        "--workload cfg5"
 cap pfb_tma_cfg2   pfb_fm_tma_kernel       "--workload cfg2 --log2n 26"
 cap pfb_ws_iqfm    pfb_fm_ws_kernel        "--workload cfg3_iqfm_p16 --log2n 26"
-cap ddc_tile_cfg1  ddc_tile_kernel         "--workload cfg1"
+cap ddc_lone_cfg1  ddc_lone_kernel         "--workload cfg1"
 cap ddc_tile_64    ddc_tile_kernel         "--workload ddc64 --log2n 22 --no-tensor-cores"
 cap ddc_mma2       ddc_mma2_kernel         "--workload ddc64"
 cap ddc_mma        "ddc_mma_kernel"        "--workload ddc64 --ddc-mode 2"
@@ -22,6 +22,8 @@ cap ddc_post       ddc_post_kernel         "--workload cfg1"
 cap fft_cols       fft_cols_tma_kernel     "--workload cfg4 --log2n 25"
 cap fft_rows       fft_rows_kernel         "--workload cfg4 --log2n 25"
 cap fft_fold       fft_fold_kernel         "--workload cfg4 --log2n 25"
+cap fft_frame      fft_frame_kernel        "--workload cfg4_16k"
+cap fft_fold_groups fft_fold_groups_kernel "--workload cfg4_16k"
 cap arm_fir_p256   pfb_arm_fir_kernel      "--workload cfg3_p256 --log2n 24"
 # K4 / K5 / K6 through small driver scripts
 timeout 240 ncu --set full --clock-control none --import-source on -k regex:"quad_demod_rows|convert_iq|post_p25|post_fir_rat|post_fm_deemph|post_squelch" -c 8 -o gpurun_out/r02_k456 python scripts/exp/k456_driver.py > gpurun_out/ncu_k456.log 2>&1; tail -1 gpurun_out/ncu_k456.log
