@@ -708,7 +708,7 @@ def run_e2e_ddc(device, wl, steps, dist, local, log2n=24, in_fmt=None):
     else:
         hin = ctx.e.pinned((n,), np.complex64)
         hin[:] = synth_block(n, 64, 5)
-    for _ in range(2):   # warm-up incl. the pulls (staging buffers, row-length guess)
+    for _ in range(3):   # warm-up incl. the pulls (staging buffers, row-length guess, PCIe link out of its idle state)
         ctx.bank.process(hin)
         ctx.bank.pull_all(OUT_IQ)
         ctx.bank.pull_all(OUT_FM)
@@ -739,7 +739,8 @@ def run_e2e_fft(device, wl, steps, dist, local, log2n=26):
     base = synth_block(min(n, 1 << 22), 1024, 5)
     for i in range(0, n, len(base)):
         hin[i:i + len(base)] = base[:min(len(base), n - i)]
-    out = sc.process(hin)
+    for _ in range(3):   # staging buffers, lazy kernel loading, PCIe link out of its idle state (measured: the first two calls
+        out = sc.process(hin)   # of a process take 50 - 85 ms instead of 10)
     barrier(dist, local)
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -850,7 +851,7 @@ def run_b200(args):
             r = side_run(device, wl, world, dist, local, peak, half, out_block, args.log2n, in_fmt=name,
                          bytes_per_sample=rd + 4)
             r["workload"] += ", %s wire format read directly (rcb_pfb_set_input_format)" % name
-            ev, h2d_i, d2h_i, _ = run_e2e(device, wl, max(args.e2e_steps, 1), 1, dist, local, out_block=out_block,
+            ev, h2d_i, d2h_i, _ = run_e2e(device, wl, max(args.e2e_steps, 1), 3, dist, local, out_block=out_block,
                                           in_fmt=name)
             ev = ev * world if dist is None else allreduce_sum_min(dist, local, ev, world)
             r["e2e"] = {"value": ev, "unit": "Msps", "h2d_bytes_per_step": h2d_i, "d2h_bytes_per_step": d2h_i}
@@ -883,7 +884,7 @@ def run_b200(args):
         e2e_v, h2d, d2h, chk = run_e2e_ddc(device, wl, args.e2e_steps, dist, local)
         api = "rcb_ddc_process(host pinned in) + rcb_ddc_pull_all(host out) for IQ and FM"
     else:
-        e2e_v, h2d, d2h, chk = run_e2e(device, wl, args.e2e_steps, 1, dist, local, out_block=out_block)
+        e2e_v, h2d, d2h, chk = run_e2e(device, wl, args.e2e_steps, 3, dist, local, out_block=out_block)
     e2e_v = e2e_v * world if dist is None else allreduce_sum_min(dist, local, e2e_v, world)
     e2e = {"value": e2e_v, "unit": "Msps", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": api,
            "checksum": chk}

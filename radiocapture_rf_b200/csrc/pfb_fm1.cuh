@@ -21,6 +21,16 @@
 #include "pfb_fm_tma.cuh"
 #include "tma_utils.cuh"
 
+// static share of a CTA's even part of the work (the rest is handed out in chunks of RCB_FM1_TAIL_CHUNK iterations, each
+// preceded by a warm-up iteration) - tuning knobs of scripts/exp builds, defaults measured on the bench shape
+#ifndef RCB_FM1_STAT_NUM
+#define RCB_FM1_STAT_NUM 7
+#define RCB_FM1_STAT_DEN 8
+#endif
+#ifndef RCB_FM1_TAIL_CHUNK
+#define RCB_FM1_TAIL_CHUNK 4
+#endif
+
 namespace rcb {
 
 struct PfbFm1Geom {
@@ -109,9 +119,9 @@ __global__ void __launch_bounds__(256, 2) pfb_fm1_kernel(const __grid_constant__
     // work distribution as in pfb_fm_tma_kernel: static run (7/8 of the even share) + dynamic tail chunks, each range
     // preceded by a warm-up iteration (recomputes the 8 frames before it: the carried angles are rebuilt, nothing
     // is stored)
-    constexpr int kTailChunk = 4;
+    constexpr int kTailChunk = RCB_FM1_TAIL_CHUNK;
     const int NI = (p.T + FPI - 1) / FPI;
-    const int stat = (int)(((long long)(NI / (int)gridDim.x) * 7) / 8);
+    const int stat = (int)(((long long)(NI / (int)gridDim.x) * RCB_FM1_STAT_NUM) / RCB_FM1_STAT_DEN);
     const int tail0 = stat * (int)gridDim.x;
     __shared__ int s_next;
     int cur0, cur1;

@@ -14,7 +14,7 @@ for k,v in a.items():
 print(' pcie', d['e2e'].get('pcie_ceiling'))
 print(' clocks', d['clocks'])
 PY
-for wl in cfg1 cfg2 cfg4 cfg4_16k cfg5 ddc64 cfg3_p16 cfg3_p8 cfg3_iqfm_p16; do
+for wl in cfg1 cfg2 cfg4 cfg4_16k cfg5 ddc64 cfg3_p16 cfg3_p8; do
   timeout 200 python bench.py --workload $wl --steps 10 --warmup 3 --e2e-steps 2 > gpurun_out/r02_bench_$wl.json 2>/dev/null
   python - "$wl" <<'PY'
 import json, sys

@@ -3,11 +3,12 @@
 dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel of each bench workload, per input sample of the
 launch that was captured (bench.py multiplies by the samples one launch processes for `roofline.traffic`).
 
-    python scripts/make_traffic.py [directory holding the .ncu-rep files, default gpurun_out]"""
+    python scripts/make_traffic.py [directory holding the .ncu-rep files, default gpurun_out] [output, default profiles/traffic.json]"""
 import csv, io, json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 src = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out")
+dst = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "profiles", "traffic.json")
 # workload -> (capture, input samples of the captured launch, algorithmic bytes per sample)
 CAPS = {
     "cfg3": ("r02_pfb_fm1", 1 << 26, 12.0),
@@ -45,4 +46,4 @@ for wl, (cap, n, alg) in CAPS.items():
                "source": "%s.ncu-rep: dram read %.1f MB + write %.1f MB over 2^%d input samples" % (cap, rd / 1e6, wr / 1e6,
                                                                                                    n.bit_length() - 1)}
     print(wl, doc[wl])
-json.dump(doc, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+json.dump(doc, open(dst, "w"), indent=1)
