@@ -22,10 +22,12 @@
 #include "tma_utils.cuh"
 
 // static share of a CTA's even part of the work (the rest is handed out in chunks of RCB_FM1_TAIL_CHUNK iterations, each
-// preceded by a warm-up iteration) - tuning knobs of scripts/exp builds, defaults measured on the bench shape
+// preceded by a warm-up iteration) - compile-time knobs; measured on the bench shape (2^28 samples, 296 CTAs): static
+// share 5/8: 0.6735 of the roofline, 3/4: 0.7017, 7/8: 0.6987-0.6997, 15/16: 0.6893, 31/32: 0.6632; tail
+// chunks of 8 instead of 4 iterations (at 7/8): 0.6975
 #ifndef RCB_FM1_STAT_NUM
-#define RCB_FM1_STAT_NUM 7
-#define RCB_FM1_STAT_DEN 8
+#define RCB_FM1_STAT_NUM 3
+#define RCB_FM1_STAT_DEN 4
 #endif
 #ifndef RCB_FM1_TAIL_CHUNK
 #define RCB_FM1_TAIL_CHUNK 4
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(256, 2) pfb_fm1_kernel(const __grid_constant__
         }
     }
 
-    // work distribution as in pfb_fm_tma_kernel: static run (7/8 of the even share) + dynamic tail chunks, each range
+    // work distribution as in pfb_fm_tma_kernel: static run (RCB_FM1_STAT_NUM / DEN of the even share) + dynamic tail chunks, each range
     // preceded by a warm-up iteration (recomputes the 8 frames before it: the carried angles are rebuilt, nothing
     // is stored)
     constexpr int kTailChunk = RCB_FM1_TAIL_CHUNK;

@@ -199,14 +199,26 @@ class BinStream(object):
             self.channels.pop(cid, None)
             self.bank.close(cid)
 
-    def push_device(self, d_ptr, nsamples):
-        """`nsamples` complex64 samples of this bin, resident on the device (a row of the PFB output)."""
+    def launch_device(self, d_ptr, nsamples):
+        """Queue the second stage over `nsamples` complex64 samples of this bin, resident on the device (a row of the
+        PFB output).  Asynchronous: the bins of a source are queued one after the other on their own CUDA streams and
+        run side by side; `collect` then fetches the results."""
         self.bank.process_device(d_ptr, nsamples)
+
+    def collect(self):
+        """Every channel's block in one transfer (rcb_ddc_pull_all), delivered to the sinks."""
+        got = self.bank.pull_all(OUT_IQ, copy=False)
         for cid, ch in list(self.channels.items()):
-            ch.deliver(self.bank.pull(cid, OUT_IQ))
+            y = got.get(cid)
+            if y is not None and len(y):
+                ch.deliver(np.array(y))
         # the parent reuses (or frees) the PFB output row after this call: nothing of this bin may still be reading it
-        # (rcb_ddc_pull returns without a sync when a block produced no output)
+        # (a block that produced no output returns without a sync)
         self.engine.sync()
+
+    def push_device(self, d_ptr, nsamples):
+        self.launch_device(d_ptr, nsamples)
+        self.collect()
 
     def close(self):
         self.engine.close()
@@ -270,9 +282,13 @@ class PfbSourceStream(SourceStream):
                   "rcb_memcpy h2d", self.engine.h)
             self.pfb.process_device(self._d_in, nfr * n, self._d_iq, None, nfr)   # bin m = row m, nfr samples
             self.engine.sync()
-            for m, bs in list(self.bins.items()):
-                if bs.channels:
-                    bs.push_device(self._d_iq.ptr + m * nfr * 8, nfr)
+            # second stage: queue every bin that has channels (each on its own handle / CUDA stream, so the banks
+            # overlap on the GPU), then fetch each bin's outputs with one transfer
+            active = [(m, bs) for m, bs in list(self.bins.items()) if bs.channels]
+            for m, bs in active:
+                bs.launch_device(self._d_iq.ptr + m * nfr * 8, nfr)
+            for m, bs in active:
+                bs.collect()
 
     def stop(self):
         # reader first (it pushes into the bins), then the bin engines under the lock, then the parent engine
