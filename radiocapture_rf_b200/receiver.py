@@ -54,6 +54,17 @@ class SourceStream(object):
         self._thread = None
         self._stop = threading.Event()
         self.post_push = []         # callables run at the end of push() under the lock (split2 feeds its halves here)
+        # "format": "u8" | "s8" | "s16" - the source delivers the SDR's wire format (an RTL-SDR capture, a UHD sc8 / sc16
+        # recording): the bytes go to the GPU as they are (rcb_ddc_set_input_format), a quarter / half of the PCIe traffic
+        self.raw_format = cfg.get("format")
+        self._raw_dtype = None
+        if self.raw_format not in (None, "fc32", "complex64"):
+            if self.raw_format not in Engine._FMT:
+                raise ValueError("source %s: unknown sample format %r" % (source_id, self.raw_format))
+            if not hasattr(self.bank, "set_input_format") or type(self) is not SourceStream:
+                raise ValueError("source %s: format %r needs the xlat-mode GPU bank" % (source_id, self.raw_format))
+            code, self._raw_dtype, off, scale = Engine._FMT[self.raw_format]
+            self.bank.set_input_format(code, off, scale)
         channel_mod.register_source(self.address, self)
 
     # ---- channel management (called by channel objects) ------------------------------------------
@@ -85,7 +96,7 @@ class SourceStream(object):
         """Channelise one wideband block and deliver each channel's narrowband samples to its sink."""
         with self.lock:
             self.bank.process(iq)
-            self.samples_in += len(iq)
+            self.samples_in += len(iq) // 2 if self._raw_dtype is not None else len(iq)   # raw blocks: interleaved I, Q
             if hasattr(self.bank, "pull_all") and len(self.channels) > 1:
                 outs = self.bank.pull_all(OUT_IQ)     # one device-to-host transfer for every channel of the source
                 for cid, ch in list(self.channels.items()):
@@ -103,14 +114,20 @@ class SourceStream(object):
                 path = self.cfg["path"]
                 with open(path, "rb") as fh:
                     while not self._stop.is_set():
-                        blk = np.fromfile(fh, dtype=np.complex64, count=self.block_samples)
-                        if len(blk) == 0:
+                        if self._raw_dtype is not None:
+                            blk = np.fromfile(fh, dtype=self._raw_dtype, count=2 * self.block_samples)
+                            blk = blk[:len(blk) & ~1]            # whole (I, Q) pairs
+                            nblk = len(blk) // 2
+                        else:
+                            blk = np.fromfile(fh, dtype=np.complex64, count=self.block_samples)
+                            nblk = len(blk)
+                        if nblk == 0:
                             if not self.cfg.get("loop", False):
                                 break
                             fh.seek(0)
                             continue
                         self.push(blk)
-                        self._pace(len(blk))
+                        self._pace(nblk)
             elif kind == "synthetic":
                 gen = self.cfg.get("generator")
                 n0 = 0

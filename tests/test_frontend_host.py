@@ -37,8 +37,15 @@ class FakeBank(object):
         del self.chans[cid]
         self.calls.append(("close", cid))
 
+    def set_input_format(self, fmt, offset=0.0, scale=1.0):
+        self.fmt = (fmt, offset, scale)
+        self.calls.append(("set_input_format", fmt, offset, scale))
+
     def process(self, iq):
-        self.last_n = len(iq)
+        raw = getattr(self, "fmt", None) is not None
+        self.last_n = len(iq) // 2 if raw else len(iq)
+        self.blocks = getattr(self, "blocks", [])
+        self.blocks.append((np.asarray(iq).dtype, len(iq)))
 
     def pull(self, cid, which=1):
         return np.zeros(self.last_n // self.chans[cid]["decim"], np.complex64)
@@ -283,3 +290,32 @@ def test_pfb_mode_bin_arithmetic_and_host_fallback():
         assert ch.source_id == 0 and ch.decim == 96 and ch.offset == 437500      # fallback: single-stage channel
     finally:
         tb.stop()
+
+
+def test_file_source_in_the_sdr_wire_format(tmp_path):
+    """A source whose samples are the SDR's own bytes ("format": "u8", an RTL-SDR capture): the reader hands the bank
+    interleaved uint8 (I, Q) pairs untouched (rcb_ddc_set_input_format converts on the device), counts complex samples,
+    drops a trailing odd byte; an unknown format is refused loudly (so is pfb mode, which needs the GPU engine)."""
+    import time
+    from radiocapture_rf_b200 import _lib
+    from radiocapture_rf_b200.receiver import SourceStream
+    raw = (np.arange(2 * 5000 + 1) % 251).astype(np.uint8)
+    path = tmp_path / "capture.u8"
+    raw.tofile(path)
+    cfg = {"type": "file", "path": str(path), "format": "u8", "center_freq": 855e6, "samp_rate": 2400000}
+    src = SourceStream(7, cfg, block_samples=2048, engine_factory=FakeEngine)
+    try:
+        bank = src.bank
+        assert bank.calls[0] == ("set_input_format", _lib.FMT_U8, -127.4, 1.0 / 128.0)
+        src.start()
+        for _ in range(200):
+            if src.samples_in >= 5000:
+                break
+            time.sleep(0.01)
+        assert src.samples_in == 5000
+        assert [b[0] for b in bank.blocks] == [np.dtype(np.uint8)] * 3
+        assert [b[1] for b in bank.blocks] == [4096, 4096, 2 * 5000 - 8192]
+    finally:
+        src.stop()
+    with pytest.raises(ValueError):
+        SourceStream(8, dict(cfg, format="u12"), engine_factory=FakeEngine)
