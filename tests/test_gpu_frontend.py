@@ -114,3 +114,40 @@ def test_fft_vector_and_peak_detection_mirror(engine, tmp_path):
                      skip_discarded=False)
     vec2 = tb2.run(x)
     np.testing.assert_allclose(vec2, vec, atol=1e-4)
+
+
+def test_file_source_in_u8_wire_format_matches_oracle(tmp_path):
+    """f4 through the server's own ingest: a source entry with "format": "u8" (an RTL-SDR capture) - the reader thread
+    hands the bytes to the GPU bank untouched, rcb_ddc_set_input_format converts on the device, and the channel's sink
+    receives the DDC of the converted stream (float64 oracle, 1e-5)."""
+    import time
+    from oracle import gr_blocks as gb, gr_firdes as fd
+    from radiocapture_rf_b200 import channel as channel_mod
+    from radiocapture_rf_b200.receiver import SourceStream
+    fs = 2400000
+    n = 96 * 600
+    t = np.arange(n)
+    sig = 0.5 * np.exp(2j * np.pi * (-62500.0 / fs * t + 0.2 * np.sin(2 * np.pi * 2e-4 * t)))
+    raw = np.clip(np.round(np.stack([sig.real, sig.imag], 1) * 127.0 + 127.4), 0, 255).astype(np.uint8).reshape(-1)
+    path = tmp_path / "cap.u8"
+    raw.tofile(path)
+    cfg = {"type": "file", "path": str(path), "format": "u8", "center_freq": 855050000, "samp_rate": fs}
+    src = SourceStream(90, cfg, block_samples=96 * 200)
+    try:
+        ch = channel_mod.channel(src, 0, 12500, fs, -62500, sink="capture")
+        ch.start()
+        src.start()
+        for _ in range(500):
+            if src.samples_in >= n:
+                break
+            time.sleep(0.01)
+        assert src.samples_in == n
+    finally:
+        src.stop()
+    y = ch.sink.data()
+    xf = ((raw.astype(np.float32) - np.float32(127.4)) * np.float32(1 / 128.0)).view(np.complex64)
+    decim, taps = fd.channel_taps(fs, 12500)
+    ref = gb.freq_xlating_fir(xf, taps, decim, -62500.0, fs)
+    m = min(len(y), len(ref))
+    assert m >= 590
+    assert gb.rel_l2(y[:m], ref[:m]) <= 1e-5
